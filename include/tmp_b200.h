@@ -1,0 +1,104 @@
+/* tmp_b200.h -- C ABI of libtmp_b200.so: the B200 (sm_100a) kernels under the `tri_mbt_vsltcls` training hot path.
+ *
+ * The reference (AITRICS/Medical_Tri_Modal_Pilot) has no native layer at all: its "operator API" is Python
+ * (SURVEY.md 8b). Each entry point below names the reference code it replaces (file:line under the reference
+ * root). The Python host (medical_tri_modal_pilot_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; tensors are row-major contiguous; `bf16`
+ * buffers are passed as void*; every call is asynchronous on `stream` (a cudaStream_t), allocates nothing,
+ * keeps no global state and never synchronises. Return 0 on success, >0 = cudaError_t, <0 = argument/driver
+ * error; tmp_last_error() returns the message (thread-local). D = 256 channels, H = 4 heads of 64 everywhere
+ * (control/config.py:97,99 defaults; the kernels are specialised for them).
+ */
+#ifndef TMP_B200_H
+#define TMP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int tmp_abi_version(void);
+const char* tmp_last_error(void);
+
+/* ---- a3/a4/a14: lengths and masks ------------------------------------------------------------------------
+ * kv_len[3,B] int32 = number of attendable keys per (stream, sample) INCLUDING the 4 bottleneck keys and CLS.
+ * Replaces get_attn_pad_mask/get_non_pad_mask (builder/models/src/transformer/utils.py:79-125) as called from
+ * TrimodalTransformerEncoder_MBT.forward (mbt_encoder.py:703-714, 748) and the image length code in
+ * tri_mbt_vsltcls.py:226-237. `missing` = trainer.py:68-84 code (0 all, 1 txt missing, 2 img missing, 3 both);
+ * with skip_missing the de-selected streams of a sample get kv_len 0 (exact: SURVEY.md Appendix A). */
+int tmp_build_lengths(const long long* input_lengths, const long long* txt_lengths, const float* img_time, int n_img,
+                      int multiimages, const long long* missing, int skip_missing, int B, int T_v, int T_i, int T_t,
+                      int32_t* kv_len, void* stream);
+/* test-only: mask[b,q,k] = (k >= kv_len[b]) as uint8 [B,T,T], the tensor the reference materialises. */
+int tmp_debug_materialize_mask(const int32_t* kv_len, int B, int T, uint8_t* mask, void* stream);
+
+/* ---- a1: UMSE / TIE embedding (tri_mbt_vsltcls.py:183-190) -------------------------------------------------
+ * x[n_tok,3] fp32 (time, value, feature-id-as-float) -> E[n_tok,256] (fp32 or bf16).
+ * val4/tim4: HOST arrays of 4 device pointers {Linear.weight[256], Linear.bias, LayerNorm.weight, LayerNorm.bias}
+ * of ie_vslt / ie_time; Wfeat = ie_feat.weight[20,256]. */
+int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* const* val4, const float* const* tim4,
+                       const float* Wfeat, void* out, int out_is_bf16, void* stream);
+
+/* ---- a1+a2+a5: stream prologue --------------------------------------------------------------------------
+ * X0[B, 5+n, 256] bf16 = [bottlenecks(4); Dropout(LN_in([CLS; E]) (+PE))]   (mbt_encoder.py:697-699, 719-729)
+ * kind 0 (vslt): E from x[B,n,3] as above.  kind 1 (img/txt): E = proj[B*n,256] + ie_time(times[b, j / (n/n_slots)])
+ * + ie_feat[feat_id]   (tri_mbt_vsltcls.py:216-224).  pe = positional_encoding.pe rows (txt only) or NULL. */
+int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
+                            const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
+                            const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
+                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, void* X0, void* stream);
+/* gradient accumulators are fp32 and ADDED to: g_val/g_tim [4,256] (dW, db, dLN.w, dLN.b), g_feat[20,256],
+ * g_cls[256], g_bott[4,256], g_ln[2,256]; dproj[B*n,256] bf16 is written (kind 1). */
+int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
+                            const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
+                            const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
+                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, const void* dX0, float* g_val,
+                            float* g_tim, float* g_feat, float* g_cls, float* g_bott, float* g_ln, void* dproj,
+                            void* stream);
+
+/* ---- a9: LayerNorm (module.py:130-144: unbiased std, eps on std) ------------------------------------------
+ * fwd: if add != NULL: sum_out = x + add, y = LN(sum_out) (encoder.py:27-30 residual fused); else y = LN(x).
+ * bwd: dx = dres + dLN(dy; x); dgamma/dbeta fp32 += ; optional dx_drop = dropout(seed,salt)(dx). rows of 256. */
+int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
+                      void* sum_out, void* y, void* stream);
+int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows, void* dx,
+                      void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* ---- a10/a11: tcgen05 GEMMs -------------------------------------------------------------------------------
+ * out[M,N] = residual + dropout( gate>0 ? relu?(alpha * A[M,K].B[N,K]^T + bias) : 0 )
+ * A, B bf16 K-major (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70, module.py:74-80).
+ * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out_bf16 and/or out_f32 receive the result. */
+int tmp_gemm_bias_act_fwd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
+                          const float* bias, int relu, const void* gate, int ld_gate, const void* residual, int ld_res,
+                          float drop_p, uint32_t seed, uint32_t salt, void* out_bf16, float* out_f32, int ld_out,
+                          void* stream);
+/* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0) */
+int tmp_gemm_wgrad(const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW, void* stream);
+/* out[N] fp32 += column sums of dY[M,N] bf16 (bias gradient) */
+int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream);
+
+/* ---- a10: modality-aware attention (attention.py:24-49, 65-84) ----------------------------------------------
+ * qkv[B*T,768] bf16 = Q|K|V with head h at columns h*64; kv_len[B] (or NULL = unmasked);
+ * O[B*T,ld_o] bf16; lse2[B,H,T_lse] fp32 (log2-domain logsumexp of the scaled scores, kept for backward). */
+int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, int T, int H, void* O, int ld_o, float* lse2,
+                     int T_lse, void* stream);
+/* delta[B,H,T_lse] and dQ_acc[B*T,256] fp32 are workspaces; dQKV[B*T,768] bf16 receives dQ|dK|dV. T_lse % 128 == 0. */
+int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B, int T, int H,
+                     const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV, void* stream);
+
+/* ---- a7: bottleneck exchange (mbt_encoder.py:764-776), in place on rows 0..3 of Y_m[B,T_m,256] bf16 -------- */
+int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
+                           void* stream);
+int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
+                           const long long* missing, int B, void* stream);
+
+/* ---- helpers ---------------------------------------------------------------------------------------------- */
+int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt, void* stream);
+/* descs: device array of n_desc records {const float* src; bf16* dst; bf16* dst_t; int R; int C} (24+8 bytes) */
+int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMP_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of libtmp_b200.so (C ABI in include/tmp_b200.h).
+
+The product path has NO CPU / PyTorch fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtmp_b200.so")
+
+_vp, _i, _ll, _f, _u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint32
+_pp = C.POINTER(C.c_void_p)
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+SIGNATURES = {
+    "tmp_abi_version": [],
+    "tmp_last_error": [],
+    "tmp_build_lengths": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "tmp_debug_materialize_mask": [_vp, _i, _i, _vp, _vp],
+    "tmp_umse_embed_fwd": [_vp, _ll, _pp, _pp, _vp, _vp, _i, _vp],
+    "tmp_stream_prologue_fwd": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
+                                _u32, _vp, _vp],
+    "tmp_stream_prologue_bwd": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
+                                _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tmp_layernorm_fwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
+    "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp],
+    "tmp_gemm_bias_act_fwd": [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp, _i, _f, _u32, _u32, _vp, _vp,
+                              _i, _vp],
+    "tmp_gemm_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
+    "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
+    "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
+    "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "tmp_bottleneck_mix_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp],
+    "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
+}
+_RESTYPES = {"tmp_last_error": C.c_char_p}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (built by medical_tri_modal_pilot_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m medical_tri_modal_pilot_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback for this path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().tmp_last_error() or b"").decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors) -> "C.Array":
+    """HOST array of device pointers (for the `const float* const*` branch-parameter blocks)."""
+    arr = (C.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr

@@ -1,0 +1,69 @@
+// common.cu -- error string, driver entry-point lookup for TMA descriptors, device properties.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tmp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  return fn;
+}
+
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer) {
+  auto fn = get_encode();
+  if (!fn) return TMP_ERR_DRIVER;
+  if (((uintptr_t)gaddr & 15) || (row_stride_bytes & 15)) {
+    set_error("TMA operand not 16-byte aligned (addr=%p stride=%llu)", gaddr, (unsigned long long)row_stride_bytes);
+    return TMP_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gaddr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult=%d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+              box_outer);
+    return TMP_ERR_DRIVER;
+  }
+  return TMP_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+}  // namespace tmp
+
+extern "C" const char* tmp_last_error(void) { return tmp::g_err; }
+extern "C" int tmp_abi_version(void) { return 1; }

@@ -1,0 +1,41 @@
+// common.cuh -- host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define TMP_OK 0
+#define TMP_ERR_ARG (-1)
+#define TMP_ERR_DRIVER (-2)
+
+namespace tmp {
+
+void set_error(const char* fmt, ...);
+
+// cuTensorMapEncodeTiled resolved at run time through the runtime API (no link-time libcuda dependency:
+// the library must load on the CPU-only build box).
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer);
+
+int num_sms();
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return TMP_OK;
+}
+
+}  // namespace tmp
+
+#define TMP_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      tmp::set_error(__VA_ARGS__);  \
+      return TMP_ERR_ARG;           \
+    }                               \
+  } while (0)

@@ -1,0 +1,482 @@
+// embed.cu -- UMSE / TIE embedding and the encoder prologue (SURVEY.md §8 a1, a2 (UMSE add), a5).
+//
+// Reference (tri_mbt_vsltcls.py:183-190, 216-224; mbt_encoder.py:697-729):
+//   E[b,l,:]  = ReLU(LN(x_val * w_v + b_v)) + ReLU(LN(x_time * w_t + b_t)) + W_feat[int(x_feat)]      (vslt)
+//   E[b,j,:]  = proj[b,j,:] + ReLU(LN(time_b * w_t + b_t)) + W_feat[18 | 19]                          (img | txt)
+//   X0[b,:,:] = [ bottlenecks(4) ; Dropout(LN_in([CLS ; E]) (+ PE for txt)) ]
+// Linear(1,256)->LayerNorm is rank-1 in the scalar, so mean/variance over the 256 channels are closed-form
+// polynomials of the scalar (no cross-lane reduction): mean = s*wbar + bbar, var = s^2*A + 2s*C + Dv.
+//
+// One warp per token row, lane l owns channels 8l..8l+7: every global access is a 16 B vector per lane,
+// 512 B contiguous per warp (bf16 rows).
+#include "common.cuh"
+#include "rowwise.cuh"
+
+using namespace tc05;
+using namespace rw;
+
+namespace {
+
+struct Branch {            // nn.Sequential(Linear(1,256), LayerNorm(256, eps=1e-5), ReLU)
+  const float* w;          // [256]  (Linear.weight[:,0])
+  const float* b;          // [256]
+  const float* g;          // [256]  LayerNorm.weight
+  const float* be;         // [256]  LayerNorm.bias
+};
+
+struct BranchLane {        // per-lane constants of one branch
+  float wc[8], bc[8];      // centred: w - mean(w), b - mean(b)
+  float g[8], be[8];
+  float A, C, Dv;          // var(w), cov(w,b), var(b)   (population, over the 256 channels)
+};
+
+__device__ __forceinline__ void branch_setup(const Branch& br, int lane, BranchLane& L) {
+  float w[8], b[8];
+  load8_f32(br.w + lane * 8, w);
+  load8_f32(br.b + lane * 8, b);
+  load8_f32(br.g + lane * 8, L.g);
+  load8_f32(br.be + lane * 8, L.be);
+  float sw = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sw += w[i]; sb += b[i]; }
+  warp_sum2(sw, sb);
+  const float wm = sw * (1.f / D), bm = sb * (1.f / D);
+  float a = 0.f, c = 0.f, d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    L.wc[i] = w[i] - wm;
+    L.bc[i] = b[i] - bm;
+    a += L.wc[i] * L.wc[i];
+    c += L.wc[i] * L.bc[i];
+    d += L.bc[i] * L.bc[i];
+  }
+  warp_sum2(a, c);
+  d = warp_sum(d);
+  L.A = a * (1.f / D); L.C = c * (1.f / D); L.Dv = d * (1.f / D);
+}
+__device__ __forceinline__ float branch_rstd(const BranchLane& L, float s) {
+  const float var = fmaxf(fmaf(s, fmaf(s, L.A, 2.f * L.C), L.Dv), 0.f);
+  return rsqrtf(var + 1e-5f);
+}
+// acc[i] += ReLU(LN(s*w+b))[channel i of this lane]
+__device__ __forceinline__ void branch_add(const BranchLane& L, float s, float rstd, float (&acc)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float zh = fmaf(s, L.wc[i], L.bc[i]) * rstd;
+    acc[i] += fmaxf(fmaf(zh, L.g[i], L.be[i]), 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw UMSE/TIE embedding (a1): x[n_tok,3] (time,value,feat) -> E[n_tok,256]; used for the bit-exact gather
+// parity test and the HBM-roofline measurement (12 B in + 512 B bf16 out per token).
+// ------------------------------------------------------------------------------------------------
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) umse_embed_fwd_kernel(const float* __restrict__ x, long long n_tok, Branch val,
+                                                             Branch tim, const float* __restrict__ Wfeat,
+                                                             void* __restrict__ out) {
+  __shared__ __align__(16) float sW[20 * D];
+  for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = Wfeat[i];
+  const int lane = threadIdx.x & 31;
+  BranchLane V, Tm;
+  branch_setup(val, lane, V);
+  branch_setup(tim, lane, Tm);
+  __syncthreads();
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_grp = (n_tok + 31) / 32;
+  for (long long grp = gw; grp < n_grp; grp += warps) {
+    const long long tok = grp * 32 + lane;
+    float xt = 0.f, xv = 0.f, xf = 0.f;
+    if (tok < n_tok) {
+      xt = __ldg(x + tok * 3);
+      xv = __ldg(x + tok * 3 + 1);
+      xf = __ldg(x + tok * 3 + 2);
+    }
+    const float rv = branch_rstd(V, xv), rt = branch_rstd(Tm, xt);
+    int fid = __float2int_rz(xf);  // C truncation == .type(torch.IntTensor) (tri_mbt_vsltcls.py:187)
+    fid = min(max(fid, 0), 19);
+    const int cnt = (int)min(32LL, n_tok - grp * 32);
+#pragma unroll 2
+    for (int j = 0; j < cnt; ++j) {
+      const float sv = __shfl_sync(0xffffffffu, xv, j), st = __shfl_sync(0xffffffffu, xt, j);
+      const float rsv = __shfl_sync(0xffffffffu, rv, j), rst = __shfl_sync(0xffffffffu, rt, j);
+      const int f = __shfl_sync(0xffffffffu, fid, j);
+      float e[8];
+      // reference order: value_embedding + time_embedding + feat_embedding (tri_mbt_vsltcls.py:189)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = 0.f;
+      branch_add(V, sv, rsv, e);
+      branch_add(Tm, st, rst, e);
+      const float4 f0 = *reinterpret_cast<const float4*>(&sW[f * D + lane * 8]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&sW[f * D + lane * 8 + 4]);
+      e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w;
+      e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
+      const long long row = grp * 32 + j;
+      if (OUT_BF16) store8_bf16((bf16*)out + row * D + lane * 8, e);
+      else store8_f32((float*)out + row * D + lane * 8, e);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream prologue: builds the layer-0 input of one modality stream, X0[B, T=5+n, 256] bf16.
+// KIND 0 = vslt (UMSE triples), KIND 1 = img/txt (projected rows + shared time branch + constant feature id).
+// ------------------------------------------------------------------------------------------------
+struct PrologueParams {
+  int B, n, T;                 // T = 5 + n
+  // KIND 0
+  const float* x;              // [B, n, 3]
+  Branch val;
+  // KIND 1
+  const bf16* proj;            // [B*n, 256]
+  const float* times;          // [B * n_slots]
+  int n_slots, rows_per_slot;  // n = n_slots * rows_per_slot
+  int feat_id;
+  // common
+  Branch tim;
+  const float* Wfeat;          // [20,256]
+  const float* cls;            // [256]
+  const float* bottlenecks;    // [4,256]
+  const float* ln_g;           // layer_norms_in[m] weight/bias (nn.LayerNorm eps 1e-5)
+  const float* ln_b;
+  const float* pe;             // [>=T-4, 256] or null
+  uint32_t drop_thr16; float drop_scale; uint32_t seed, salt;
+  bf16* X0;                    // [B, T, 256]
+};
+
+template <int KIND>
+__device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, const BranchLane& V, const BranchLane& Tm,
+                                                   const float* sW, int b, int t, int lane, float (&e)[8], float& s_val,
+                                                   float& s_time, int& fid) {
+  // returns false for bottleneck rows (t < 4)
+  if (t < 4) return false;
+  if (t == 4) {
+    load8_f32(p.cls + lane * 8, e);
+    return true;
+  }
+  const int j = t - 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = 0.f;
+  if (KIND == 0) {
+    const float* xr = p.x + ((size_t)b * p.n + j) * 3;
+    s_time = __ldg(xr); s_val = __ldg(xr + 1);
+    fid = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19);
+    branch_add(V, s_val, branch_rstd(V, s_val), e);
+  } else {
+    load8_bf16(p.proj + ((size_t)b * p.n + j) * D + lane * 8, e);
+    s_time = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
+    fid = p.feat_id;
+  }
+  branch_add(Tm, s_time, branch_rstd(Tm, s_time), e);
+  const float4 f0 = *reinterpret_cast<const float4*>(&sW[fid * D + lane * 8]);
+  const float4 f1 = *reinterpret_cast<const float4*>(&sW[fid * D + lane * 8 + 4]);
+  e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w;
+  e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
+  return true;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams p) {
+  __shared__ __align__(16) float sW[20 * D];
+  for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
+  const int lane = threadIdx.x & 31;
+  BranchLane V, Tm;
+  if (KIND == 0) branch_setup(p.val, lane, V);
+  branch_setup(p.tim, lane, Tm);
+  float lg[8], lb[8];
+  load8_f32(p.ln_g + lane * 8, lg);
+  load8_f32(p.ln_b + lane * 8, lb);
+  __syncthreads();
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long rows = (long long)p.B * p.T;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const int b = (int)(row / p.T), t = (int)(row % p.T);
+    bf16* dst = p.X0 + row * D + lane * 8;
+    float e[8], sv = 0.f, st = 0.f;
+    int fid = 0;
+    if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
+      load8_f32(p.bottlenecks + t * D + lane * 8, e);
+      store8_bf16(dst, e);
+      continue;
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1 += e[i];
+    const float mean = warp_sum(s1) * (1.f / D);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] -= mean; s2 += e[i] * e[i]; }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.f / D) + 1e-5f);
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = fmaf(e[i] * rstd, lg[i], lb[i]);
+    if (p.pe) {
+      float pe[8];
+      load8_f32(p.pe + (size_t)(t - 4) * D + lane * 8, pe);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] += pe[i];
+    }
+    if (p.drop_thr16) {
+      const uint32_t base = (uint32_t)row * D + lane * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        y[i] = dropout_keep(p.seed, p.salt, base + i, p.drop_thr16) ? y[i] * p.drop_scale : 0.f;
+    }
+    store8_bf16(dst, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the stream prologue. Gradient accumulators (fp32, atomically added):
+//   g_val / g_tim : [4,256] each = (dLinear.weight, dLinear.bias, dLN.weight, dLN.bias)
+//   g_feat [20,256], g_cls [256], g_bott [4,256], g_ln [2,256] = (dLN_in.weight, dLN_in.bias)
+//   dproj [B*n,256] bf16 (KIND 1): gradient wrt the projected rows
+// ------------------------------------------------------------------------------------------------
+struct PrologueBwdParams {
+  PrologueParams f;
+  const bf16* dX0;   // [B, T, 256]
+  float* g_val; float* g_tim; float* g_feat; float* g_cls; float* g_bott; float* g_ln;
+  bf16* dproj;
+};
+
+struct BranchAcc { float dw[8], db[8], dg[8], dbe[8]; };
+
+__device__ __forceinline__ void branch_bwd(const BranchLane& L, float s, const float (&de)[8], BranchAcc& acc) {
+  const float rstd = branch_rstd(L, s);
+  float zh[8], dzh[8];
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    zh[i] = fmaf(s, L.wc[i], L.bc[i]) * rstd;
+    const float pre = fmaf(zh[i], L.g[i], L.be[i]);
+    const float gm = pre > 0.f ? de[i] : 0.f;
+    acc.dbe[i] += gm;
+    acc.dg[i] += gm * zh[i];
+    dzh[i] = gm * L.g[i];
+    m1 += dzh[i];
+    m2 += dzh[i] * zh[i];
+  }
+  warp_sum2(m1, m2);
+  m1 *= (1.f / D); m2 *= (1.f / D);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dz = rstd * (dzh[i] - m1 - zh[i] * m2);
+    acc.dw[i] += dz * s;
+    acc.db[i] += dz;
+  }
+}
+
+__device__ __forceinline__ void flush8(float* sm, const float (&v)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&sm[lane * 8 + i], v[i]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdParams q) {
+  const PrologueParams& p = q.f;
+  extern __shared__ __align__(16) float sm[];
+  float* sW = sm;                 // [20*256] forward table
+  float* sG = sm + 20 * D;        // [20*256] feature-embedding gradient
+  float* sAcc = sG + 20 * D;      // [15*256]: val(4) tim(4) cls(1) bott(4) ln(2)
+  for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) { sW[i] = p.Wfeat[i]; sG[i] = 0.f; }
+  for (int i = threadIdx.x; i < 15 * D; i += blockDim.x) sAcc[i] = 0.f;
+  const int lane = threadIdx.x & 31;
+  BranchLane V, Tm;
+  if (KIND == 0) branch_setup(p.val, lane, V);
+  branch_setup(p.tim, lane, Tm);
+  float lg[8];
+  load8_f32(p.ln_g + lane * 8, lg);
+  BranchAcc aV, aT;
+  float a_cls[8], a_lng[8], a_lnb[8], a_feat[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    aV.dw[i] = aV.db[i] = aV.dg[i] = aV.dbe[i] = 0.f;
+    aT.dw[i] = aT.db[i] = aT.dg[i] = aT.dbe[i] = 0.f;
+    a_cls[i] = a_lng[i] = a_lnb[i] = a_feat[i] = 0.f;
+  }
+  __syncthreads();
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long rows = (long long)p.B * p.T;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const int b = (int)(row / p.T), t = (int)(row % p.T);
+    float g[8];
+    load8_bf16(q.dX0 + row * D + lane * 8, g);
+    float e[8], sv = 0.f, st = 0.f;
+    int fid = 0;
+    if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
+      flush8(sAcc + (9 + t) * D, g, lane);  // bottleneck parameter rows
+      continue;
+    }
+    if (p.drop_thr16) {
+      const uint32_t base = (uint32_t)row * D + lane * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        g[i] = dropout_keep(p.seed, p.salt, base + i, p.drop_thr16) ? g[i] * p.drop_scale : 0.f;
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1 += e[i];
+    const float mean = warp_sum(s1) * (1.f / D);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] -= mean; s2 += e[i] * e[i]; }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.f / D) + 1e-5f);
+    float de[8], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float yh = e[i] * rstd;
+      a_lng[i] += g[i] * yh;
+      a_lnb[i] += g[i];
+      de[i] = g[i] * lg[i];   // d yhat
+      m1 += de[i];
+      m2 += de[i] * yh;
+      e[i] = yh;
+    }
+    warp_sum2(m1, m2);
+    m1 *= (1.f / D); m2 *= (1.f / D);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) de[i] = rstd * (de[i] - m1 - e[i] * m2);
+    if (t == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a_cls[i] += de[i];
+      continue;
+    }
+    if (KIND == 0) {
+      branch_bwd(V, sv, de, aV);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sG[fid * D + lane * 8 + i], de[i]);
+    } else {
+      store8_bf16(q.dproj + ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a_feat[i] += de[i];
+    }
+    branch_bwd(Tm, st, de, aT);
+  }
+  if (KIND == 0) {
+    flush8(sAcc + 0 * D, aV.dw, lane); flush8(sAcc + 1 * D, aV.db, lane);
+    flush8(sAcc + 2 * D, aV.dg, lane); flush8(sAcc + 3 * D, aV.dbe, lane);
+  } else {
+    flush8(sG + p.feat_id * D, a_feat, lane);
+  }
+  flush8(sAcc + 4 * D, aT.dw, lane); flush8(sAcc + 5 * D, aT.db, lane);
+  flush8(sAcc + 6 * D, aT.dg, lane); flush8(sAcc + 7 * D, aT.dbe, lane);
+  flush8(sAcc + 8 * D, a_cls, lane);
+  flush8(sAcc + 13 * D, a_lng, lane); flush8(sAcc + 14 * D, a_lnb, lane);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+    if (KIND == 0) atomicAdd(&q.g_val[i], sAcc[i]);
+    atomicAdd(&q.g_tim[i], sAcc[4 * D + i]);
+    atomicAdd(&q.g_bott[i], sAcc[9 * D + i]);
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(&q.g_cls[i], sAcc[8 * D + i]);
+    atomicAdd(&q.g_ln[i], sAcc[13 * D + i]);
+    atomicAdd(&q.g_ln[D + i], sAcc[14 * D + i]);
+  }
+  if (KIND == 0) {
+    for (int i = threadIdx.x; i < 20 * D; i += blockDim.x)
+      if (sG[i] != 0.f) atomicAdd(&q.g_feat[i], sG[i]);
+  } else {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&q.g_feat[p.feat_id * D + i], sG[p.feat_id * D + i]);
+  }
+}
+
+int grid_for_rows(long long rows) {
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)tmp::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+// branch parameter block: 4 pointers (Linear.weight[256,1], Linear.bias, LayerNorm.weight, LayerNorm.bias)
+extern "C" int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* const* val4, const float* const* tim4,
+                                  const float* Wfeat, void* out, int out_is_bf16, void* stream) {
+  TMP_REQUIRE(x && val4 && tim4 && Wfeat && out && n_tok >= 0, "umse_embed_fwd: bad argument");
+  if (n_tok == 0) return TMP_OK;
+  Branch v{val4[0], val4[1], val4[2], val4[3]}, t{tim4[0], tim4[1], tim4[2], tim4[3]};
+  long long grp = (n_tok + 31) / 32;
+  long long blocks = (grp + 7) / 8;
+  const long long cap = (long long)tmp::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (out_is_bf16)
+    umse_embed_fwd_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_tok, v, t, Wfeat, out);
+  else
+    umse_embed_fwd_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_tok, v, t, Wfeat, out);
+  return tmp::check_launch("umse_embed_fwd_kernel");
+}
+
+static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float* x, const float* const* val4,
+                         const void* proj, const float* times, int n_slots, int feat_id, const float* const* tim4,
+                         const float* Wfeat, const float* cls, const float* bottlenecks, const float* ln_g,
+                         const float* ln_b, const float* pe, float drop_p, uint32_t seed, uint32_t salt, void* X0) {
+  TMP_REQUIRE(kind == 0 || kind == 1, "prologue: kind must be 0 (vslt) or 1 (img/txt)");
+  TMP_REQUIRE(B > 0 && n >= 0 && tim4 && Wfeat && cls && bottlenecks && ln_g && ln_b && X0, "prologue: bad argument");
+  TMP_REQUIRE(kind == 1 || (x && val4), "prologue: vslt stream needs x and the value branch");
+  TMP_REQUIRE(kind == 0 || (proj && times && n_slots > 0 && n % n_slots == 0 && feat_id >= 0 && feat_id < 20),
+              "prologue: img/txt stream needs proj, times, n_slots | n, feat id in [0,20)");
+  TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "prologue: dropout p out of range");
+  p.B = B; p.n = n; p.T = 5 + n;
+  p.x = x;
+  if (val4) p.val = Branch{val4[0], val4[1], val4[2], val4[3]}; else p.val = Branch{nullptr, nullptr, nullptr, nullptr};
+  p.proj = (const bf16*)proj; p.times = times; p.n_slots = n_slots > 0 ? n_slots : 1;
+  p.rows_per_slot = n_slots > 0 ? n / n_slots : n; if (p.rows_per_slot < 1) p.rows_per_slot = 1;
+  p.feat_id = feat_id;
+  p.tim = Branch{tim4[0], tim4[1], tim4[2], tim4[3]};
+  p.Wfeat = Wfeat; p.cls = cls; p.bottlenecks = bottlenecks; p.ln_g = ln_g; p.ln_b = ln_b; p.pe = pe;
+  p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.seed = seed; p.salt = salt;
+  p.X0 = (bf16*)X0;
+  return TMP_OK;
+}
+
+extern "C" int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, const float* const* val4,
+                                       const void* proj, const float* times, int n_slots, int feat_id,
+                                       const float* const* tim4, const float* Wfeat, const float* cls,
+                                       const float* bottlenecks, const float* ln_g, const float* ln_b, const float* pe,
+                                       float drop_p, uint32_t seed, uint32_t salt, void* X0, void* stream) {
+  PrologueParams p;
+  int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                         ln_b, pe, drop_p, seed, salt, X0);
+  if (rc) return rc;
+  const int grid = grid_for_rows((long long)B * p.T);
+  if (kind == 0) stream_prologue_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else stream_prologue_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return tmp::check_launch("stream_prologue_fwd_kernel");
+}
+
+extern "C" int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float* const* val4,
+                                       const void* proj, const float* times, int n_slots, int feat_id,
+                                       const float* const* tim4, const float* Wfeat, const float* cls,
+                                       const float* bottlenecks, const float* ln_g, const float* ln_b, const float* pe,
+                                       float drop_p, uint32_t seed, uint32_t salt, const void* dX0, float* g_val,
+                                       float* g_tim, float* g_feat, float* g_cls, float* g_bott, float* g_ln,
+                                       void* dproj, void* stream) {
+  PrologueBwdParams q;
+  // X0 is not written by the backward; pass dX0 to satisfy the non-null check
+  int rc = fill_prologue(q.f, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                         ln_b, pe, drop_p, seed, salt, const_cast<void*>(dX0));
+  if (rc) return rc;
+  TMP_REQUIRE(dX0 && g_tim && g_feat && g_cls && g_bott && g_ln, "prologue_bwd: null gradient buffer");
+  TMP_REQUIRE(kind == 1 || g_val, "prologue_bwd: vslt needs g_val");
+  TMP_REQUIRE(kind == 0 || dproj, "prologue_bwd: img/txt needs dproj");
+  q.dX0 = (const bf16*)dX0;
+  q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
+  q.dproj = (bf16*)dproj;
+  const int smem = (20 + 20 + 15) * D * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  long long blocks = ((long long)B * q.f.T + 7) / 8;
+  if (blocks > tmp::num_sms()) blocks = tmp::num_sms();
+  if (kind == 0) stream_prologue_bwd_kernel<0><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(q);
+  else stream_prologue_bwd_kernel<1><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(q);
+  return tmp::check_launch("stream_prologue_bwd_kernel");
+}

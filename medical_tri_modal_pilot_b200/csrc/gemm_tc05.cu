@@ -1,0 +1,444 @@
+// gemm_tc05.cu -- tcgen05/TMEM/TMA GEMMs for the fusion-encoder blocks:
+//   * gemm_tn : C[M,N] = epilogue(A[M,K] . B[N,K]^T)      both operands K-major (activations x nn.Linear /
+//               Conv1d(k=1) weights as stored by the reference, `[out,in]`). Used for QKV, FFN1, FFN2, the
+//               768->256 projections and (with pre-transposed weights) every dgrad.
+//   * gemm_wgrad : dW[N,K] += dY[M,N]^T . X[M,K]          both operands MN-major (reduction over tokens),
+//               split over M across CTAs, fp32 atomics into the parameter gradient.
+// Warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
+// (TMEM -> registers -> fused bias/ReLU/dropout/residual -> global). Accumulators are double-buffered in TMEM
+// so the epilogue of tile i overlaps the MMAs of tile i+1; the kernel is persistent over output tiles.
+#include "common.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kThreads = 192;
+
+struct EpiParams {
+  int M, N, K;
+  float alpha;            // scale on the accumulator
+  const float* bias;      // [N] fp32 or null
+  int relu;               // apply ReLU after bias
+  const bf16* gate;       // [M, ld_gate] : multiply by (gate > 0)  (ReLU backward) or null
+  int ld_gate;
+  const bf16* residual;   // [M, ld_res] added last, or null
+  int ld_res;
+  uint32_t drop_thr16;    // 0 = no dropout; else round(p*65536)
+  float drop_scale;       // 1/(1-p)
+  uint32_t seed, salt;
+  bf16* out;              // [M, ld_out] bf16 (or null)
+  float* out_f32;         // [M, ld_out] fp32 (or null)
+  int ld_out;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blks = (p.M + BM - 1) / BM;
+  const int n_blks = p.N / BN;
+  const int k_blks = p.K / BK;
+  const int num_tiles = m_blks * n_blks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blks) * BM, n0 = (tile % n_blks) * BN;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_sdesc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sdesc_sw128(sb + k * 32, 16, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_blks) * BM, n0 = (tile % n_blks) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem_base, quarter * 32, acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+          if (p.gate) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(g + q);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (!(bf16lo_to_f32(w[t]) > 0.f)) v[q * 8 + t * 2] = 0.f;
+                if (!(bf16hi_to_f32(w[t]) > 0.f)) v[q * 8 + t * 2 + 1] = 0.f;
+              }
+            }
+          }
+          if (p.drop_thr16) {
+            const uint32_t base = (uint32_t)row * (uint32_t)p.N + (uint32_t)col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = dropout_keep(p.seed, p.salt, base + j, p.drop_thr16) ? v[j] * p.drop_scale : 0.f;
+          }
+          if (p.residual) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(g + q);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[q * 8 + t * 2] += bf16lo_to_f32(w[t]);
+                v[q * 8 + t * 2 + 1] += bf16hi_to_f32(w[t]);
+              }
+            }
+          }
+          if (p.out) {
+            uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)row * p.ld_out + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              o[q] = u;
+            }
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: dW[N,K] (+)= sum_m dY[m,N]^T X[m,K].  A = dY^T (MN-major), B = X^T (MN-major).
+// grid = (N/128, K/BNW, splits).  Each CTA reduces rows [m_begin, m_end) and atomically adds its
+// 128 x BNW fp32 tile into dW.  Optional column-sum of dY (bias gradient) is NOT done here.
+// ------------------------------------------------------------------------------------------------
+template <int BNW>
+struct WgradSmem {
+  static constexpr int kStages = (BNW == 256) ? 4 : 6;
+  static constexpr int kABytes = 128 * BK * 2;   // 2 chunks of [64 m-rows x 64 n-cols]
+  static constexpr int kBBytes = BNW * BK * 2;   // BNW/64 chunks of [64 m-rows x 64 k-cols]
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int ldw,
+                  float* __restrict__ dW, int rows_per_split) {
+  using L = WgradSmem<BNW>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = (uint32_t*)(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 128;   // rows of dW
+  const int k0 = blockIdx.y * BNW;   // cols of dW
+  const int m_begin = blockIdx.z * rows_per_split;
+  const int m_end = min(M, m_begin + rows_per_split);
+  const int k_blks = (m_end - m_begin + BK - 1) / BK;  // reduction blocks (OOB rows are zero-filled by TMA)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BNW);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (k_blks > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          const int m = m_begin + kb * BK;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tma_load_2d(sa + c * (BK * 128), &tmY, &full_bar[stage], n0 + c * 64, m);
+#pragma unroll
+          for (int c = 0; c < BNW / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmX, &full_bar[stage], k0 + c * 64, m);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // MN-major: 16 reduction rows = 2048 B per UMMA_K step; LBO = one 64-wide chunk = BK*128 B
+            const uint64_t adesc = make_sdesc_sw128(sa + k * 2048, BK * 128, 1024);
+            const uint64_t bdesc = make_sdesc_sw128(sb + k * 2048, BK * 128, 1024);
+            umma_ss(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar);
+      }
+    } else {
+      const int quarter = warp & 3;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const int row = n0 + quarter * 32 + lane;
+      float* dst = dW + (size_t)row * ldw + k0;
+#pragma unroll 1
+      for (int c = 0; c < BNW / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem_base, quarter * 32, c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + j),
+                       "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                       "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BNW);
+  }
+}
+
+template <int BN>
+int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, int grid, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      tmp::set_error("cudaFuncSetAttribute(gemm_tn): %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  gemm_tn_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, p);
+  return tmp::check_launch("gemm_tn_kernel");
+}
+
+template <int BNW>
+int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, cudaStream_t st) {
+  using L = WgradSmem<BNW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      tmp::set_error("cudaFuncSetAttribute(gemm_wgrad): %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int tiles = (N / 128) * (K / BNW);
+  int splits = (tmp::num_sms() + tiles - 1) / tiles;
+  int rows_per_split = (M + splits - 1) / splits;
+  rows_per_split = ((rows_per_split + BK - 1) / BK) * BK;
+  if (rows_per_split < BK) rows_per_split = BK;
+  splits = (M + rows_per_split - 1) / rows_per_split;
+  dim3 grid(N / 128, K / BNW, splits);
+  gemm_wgrad_kernel<BNW><<<grid, kThreads, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split);
+  return tmp::check_launch("gemm_wgrad_kernel");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int tmp_gemm_bias_act_fwd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
+                                     const float* bias, int relu, const void* gate, int ld_gate, const void* residual,
+                                     int ld_res, float drop_p, uint32_t seed, uint32_t salt, void* out_bf16,
+                                     float* out_f32, int ld_out, void* stream) {
+  TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
+  TMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  TMP_REQUIRE(N % 128 == 0 && K % BK == 0, "gemm: N must be a multiple of 128 and K of 64 (N=%d K=%d)", N, K);
+  TMP_REQUIRE(ld_out % 8 == 0 && (!gate || ld_gate % 8 == 0) && (!residual || ld_res % 8 == 0),
+              "gemm: leading dimensions must be multiples of 8");
+  TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p out of range");
+  const int sms = tmp::num_sms();
+  const int m_blks = (M + BM - 1) / BM;
+  int BN = 256;
+  if (N % 256 != 0 || m_blks * (N / 256) < sms) BN = 128;
+  CUtensorMap tmA, tmB;
+  int rc = tmp::encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
+  if (rc) return rc;
+  rc = tmp::encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN);
+  if (rc) return rc;
+  EpiParams p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.bias = bias; p.relu = relu;
+  p.gate = (const bf16*)gate; p.ld_gate = ld_gate;
+  p.residual = (const bf16*)residual; p.ld_res = ld_res;
+  p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.seed = seed; p.salt = salt;
+  p.out = (bf16*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
+  const int tiles = m_blks * (N / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  if (BN == 256) return launch_tn<256>(tmA, tmB, p, grid, (cudaStream_t)stream);
+  return launch_tn<128>(tmA, tmB, p, grid, (cudaStream_t)stream);
+}
+
+extern "C" int tmp_gemm_wgrad(const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
+                              void* stream) {
+  TMP_REQUIRE(dY && X && dW, "wgrad: null operand");
+  TMP_REQUIRE(M > 0 && N % 128 == 0 && K % 128 == 0, "wgrad: need N,K multiples of 128 (M=%d N=%d K=%d)", M, N, K);
+  CUtensorMap tmY, tmX;
+  int rc = tmp::encode_tmap_2d_bf16(&tmY, dY, (uint64_t)N, (uint64_t)M, (uint64_t)ldy * 2, 64, BK);
+  if (rc) return rc;
+  rc = tmp::encode_tmap_2d_bf16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
+  if (rc) return rc;
+  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, (cudaStream_t)stream);
+  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, (cudaStream_t)stream);
+}

@@ -1,0 +1,422 @@
+// rowops.cu -- HBM-bound pieces of the fusion encoder:
+//   * tmp_build_lengths / tmp_debug_materialize_mask : key-padding lengths (mbt_encoder.py:703-714,748;
+//     tri_mbt_vsltcls.py:226-237; utils.py:79-125) kept on device as int32, never as a [B*H,T,T] bool tensor
+//   * tmp_layernorm_fwd / bwd : the reference's hand-written LayerNorm (module.py:130-144: unbiased std,
+//     eps added to std) with the residual add / residual gradient fused, one warp per row
+//   * tmp_bottleneck_mix_fwd / bwd : modality-aware bottleneck exchange (mbt_encoder.py:764-776)
+//   * tmp_colsum : bias gradients; tmp_dropout_apply; tmp_cast_weights : fp32 master -> bf16 (+transposed) copies
+#include "common.cuh"
+#include "rowwise.cuh"
+
+using namespace tc05;
+using namespace rw;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// lengths (a3, a4)
+// ------------------------------------------------------------------------------------------------
+__global__ void build_lengths_kernel(const long long* __restrict__ input_lengths, const long long* __restrict__ txt_lengths,
+                                     const float* __restrict__ img_time, int n_img, int multiimages,
+                                     const long long* __restrict__ missing, int skip_missing, int B, int T_v, int T_i,
+                                     int T_t, int32_t* __restrict__ kv_len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // vslt: input_lengths + 1 (CLS, mbt_encoder.py:704) + 4 bottleneck keys (:748)
+  int v = (int)input_lengths[b] + 1 + 4;
+  // img: 49 * #(img_time != 10) (tri_mbt_vsltcls.py:229-232) + 1 + 4; unmasked when --multiimages 0 (:144,:234)
+  int im = T_i;
+  if (multiimages) {
+    int cnt = 0;
+    for (int k = 0; k < n_img; ++k) cnt += (img_time[b * n_img + k] - 10.0f) != 0.0f;
+    im = 49 * cnt + 1 + 4;
+  }
+  // txt: caller passes txt_lengths + 2 (tri_mbt_vsltcls.py:237), encoder adds 1 and maps 3 -> 0 (mbt_encoder.py:704-707)
+  int t = (int)txt_lengths[b] + 3;
+  if (t == 3) t = 0;
+  t += 4;
+  if (skip_missing && missing) {
+    const long long m = missing[b];  // 0 = all, 1 = txt missing, 2 = img missing, 3 = both (trainer.py:68-84)
+    if (m == 2 || m == 3) im = 0;
+    if (m == 1 || m == 3) t = 0;
+  }
+  kv_len[b] = min(max(v, 0), T_v);
+  kv_len[B + b] = min(max(im, 0), T_i);
+  kv_len[2 * B + b] = min(max(t, 0), T_t);
+}
+
+// mask[b,q,k] = (k >= kv_len[b])   -- test-only restatement of get_attn_pad_mask
+__global__ void materialize_mask_kernel(const int32_t* __restrict__ kv_len, int B, int T, uint8_t* __restrict__ mask) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * T * T;
+  if (idx >= total) return;
+  const int k = (int)(idx % T);
+  const int b = (int)(idx / ((size_t)T * T));
+  mask[idx] = k >= kv_len[b];
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (reference module.py:130-144): y = gamma * (z - mean) / (std_unbiased + eps) + beta
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ln_stats(float (&c)[8], float& r, float& s_std) {
+  float s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1 += c[i];
+  const float mean = warp_sum(s1) * (1.f / D);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i] -= mean; s2 += c[i] * c[i]; }
+  s_std = sqrtf(warp_sum(s2) * (1.f / (D - 1)));
+  r = 1.f / (s_std + 1e-6f);
+}
+
+// ADD: h = x + o written to `sum_out`, then normalised.  x,o,sum_out,y: [rows,256] bf16
+template <bool ADD>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ o,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, long long rows,
+                                                            bf16* __restrict__ sum_out, bf16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  float g[8], be[8];
+  load8_f32(gamma + lane * 8, g);
+  load8_f32(beta + lane * 8, be);
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    float c[8];
+    load8_bf16(x + row * D + lane * 8, c);
+    if (ADD) {
+      float a[8];
+      load8_bf16(o + row * D + lane * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] += a[i];
+      store8_bf16(sum_out + row * D + lane * 8, c);
+      // normalise the bf16-rounded sum: it is what the backward pass and the residual path see
+      load8_bf16(sum_out + row * D + lane * 8, c);
+    }
+    float r, sd;
+    ln_stats(c, r, sd);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(c[i] * r, g[i], be[i]);
+    store8_bf16(y + row * D + lane * 8, v);
+  }
+}
+
+// dx = dres + LN'(dy; x).  Optionally also writes dx_drop = dropout_mask(seed,salt) * dx / (1-p)
+// (the gradient entering the previous block's FFN2 when its output dropout is active).
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ dres,
+                                                            const float* __restrict__ gamma, long long rows,
+                                                            bf16* __restrict__ dx, bf16* __restrict__ dx_drop,
+                                                            uint32_t drop_thr16, float drop_scale, uint32_t seed,
+                                                            uint32_t salt, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+  __shared__ float sAcc[2 * D];
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sAcc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float g[8], ag[8], ab[8];
+  load8_f32(gamma + lane * 8, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = 0.f;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    float c[8], gy[8];
+    load8_bf16(x + row * D + lane * 8, c);
+    load8_bf16(dy + row * D + lane * 8, gy);
+    float r, sd;
+    ln_stats(c, r, sd);
+    float gbar = 0.f, gc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ab[i] += gy[i];
+      ag[i] += gy[i] * c[i] * r;
+      gy[i] *= g[i];
+      gbar += gy[i];
+      gc += gy[i] * c[i];
+    }
+    warp_sum2(gbar, gc);
+    gbar *= (1.f / D);
+    // d/dc: r*g - r^2 * (sum g.c) / ((n-1) * std) * c ; then subtract the mean (only the first term has one)
+    const float k2 = sd > 0.f ? r * r * gc / ((D - 1) * sd) : 0.f;
+    float out[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = r * (gy[i] - gbar) - k2 * c[i];
+    if (dres) {
+      float a[8];
+      load8_bf16(dres + row * D + lane * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] += a[i];
+    }
+    store8_bf16(dx + row * D + lane * 8, out);
+    if (dx_drop) {
+      const uint32_t base = (uint32_t)row * D + lane * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        out[i] = dropout_keep(seed, salt, base + i, drop_thr16) ? out[i] * drop_scale : 0.f;
+      store8_bf16(dx_drop + row * D + lane * 8, out);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sAcc[lane * 8 + i], ag[i]);
+    atomicAdd(&sAcc[D + lane * 8 + i], ab[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sAcc[i]);
+    atomicAdd(&dbeta[i], sAcc[D + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bottleneck exchange (a7). Y_m: [B, T_m, 256] bf16; rows 0..3 of every present stream are replaced by the
+// per-sample mean over the modalities selected by `missing` (0: v,i,t  1: v,i  2: v,t  3: v).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mix_weights(long long code, float (&w)[3]) {
+  switch (code) {
+    case 0: w[0] = w[1] = w[2] = 1.f / 3.f; break;
+    case 1: w[0] = w[1] = 0.5f; w[2] = 0.f; break;
+    case 2: w[0] = w[2] = 0.5f; w[1] = 0.f; break;
+    default: w[0] = 1.f; w[1] = w[2] = 0.f; break;
+  }
+}
+
+__global__ void bottleneck_mix_fwd_kernel(bf16* __restrict__ Yv, bf16* __restrict__ Yi, bf16* __restrict__ Yt, int Tv,
+                                          int Ti, int Tt, const long long* __restrict__ missing, int B) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * 4) return;
+  const int b = row >> 2, r = row & 3;
+  float w[3];
+  mix_weights(missing[b], w);
+  bf16* pv = Yv + ((size_t)b * Tv + r) * D + lane * 8;
+  bf16* pi = Yi + ((size_t)b * Ti + r) * D + lane * 8;
+  bf16* pt = Yt + ((size_t)b * Tt + r) * D + lane * 8;
+  float acc[8], a[8];
+  load8_bf16(pv, acc);
+  // sum first, scale once: the reference takes torch.mean over the selected stack (mbt_encoder.py:765-768)
+  if (w[1] != 0.f) { load8_bf16(pi, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
+  if (w[2] != 0.f) { load8_bf16(pt, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= w[0];
+  store8_bf16(pv, acc);
+  store8_bf16(pi, acc);
+  store8_bf16(pt, acc);
+}
+
+// gradient: g = sum over present dY_m rows; dY_m rows <- w_m * g.  A null pointer = stream absent in the upper layer.
+__global__ void bottleneck_mix_bwd_kernel(bf16* __restrict__ dYv, bf16* __restrict__ dYi, bf16* __restrict__ dYt,
+                                          int Tv, int Ti, int Tt, int upper_has_it,
+                                          const long long* __restrict__ missing, int B) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * 4) return;
+  const int b = row >> 2, r = row & 3;
+  float w[3];
+  mix_weights(missing[b], w);
+  bf16* pv = dYv + ((size_t)b * Tv + r) * D + lane * 8;
+  bf16* pi = dYi + ((size_t)b * Ti + r) * D + lane * 8;
+  bf16* pt = dYt + ((size_t)b * Tt + r) * D + lane * 8;
+  float g[8], a[8], o[8];
+  load8_bf16(pv, g);
+  if (upper_has_it) {
+    load8_bf16(pi, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += a[i];
+    load8_bf16(pt, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += a[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[0];
+  store8_bf16(pv, o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[1];
+  store8_bf16(pi, o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[2];
+  store8_bf16(pt, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (bf16 in, fp32 atomics out)
+// block = 256 threads = (N/8 column groups) x (rows in flight)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dY, int ld, long long M, int N,
+                                                     long long rows_per_block, float* __restrict__ out) {
+  extern __shared__ float sacc[];  // [N]
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int groups = N / 8;
+  const int lanes_r = blockDim.x / groups;   // row lanes
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (rl < lanes_r) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(M, r0 + rows_per_block);
+    for (long long r = r0 + rl; r < r1; r += lanes_r) {
+      float v[8];
+      load8_bf16(dY + r * ld + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sacc[cg * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&out[i], sacc[i]);
+}
+
+__global__ void dropout_apply_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8,
+                                     uint32_t thr16, float scale, uint32_t seed, uint32_t salt) {
+  const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i8 >= n8) return;
+  float v[8];
+  load8_bf16(in + i8 * 8, v);
+  const uint32_t base = (uint32_t)(i8 * 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = dropout_keep(seed, salt, base + i, thr16) ? v[i] * scale : 0.f;
+  store8_bf16(out + i8 * 8, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight refresh: fp32 master [R,C] -> bf16 [R,C] and bf16 transposed [C,R], batched over a descriptor table
+// ------------------------------------------------------------------------------------------------
+struct CastDesc { const float* src; bf16* dst; bf16* dst_t; int R, C; };
+
+__global__ void cast_weights_kernel(const CastDesc* __restrict__ descs) {
+  __shared__ float tile[32][33];
+  const CastDesc d = descs[blockIdx.z];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= d.C || r0 >= d.R) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < d.R && c < d.C) {
+      v = d.src[(size_t)r * d.C + c];
+      if (d.dst) d.dst[(size_t)r * d.C + c] = __float2bfloat16(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (d.dst_t) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < d.R && c < d.C) d.dst_t[(size_t)c * d.R + r] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+
+int rows_grid(long long rows) {
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)tmp::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int tmp_build_lengths(const long long* input_lengths, const long long* txt_lengths, const float* img_time,
+                                 int n_img, int multiimages, const long long* missing, int skip_missing, int B, int T_v,
+                                 int T_i, int T_t, int32_t* kv_len, void* stream) {
+  TMP_REQUIRE(input_lengths && txt_lengths && kv_len && B > 0, "build_lengths: bad argument");
+  TMP_REQUIRE(!multiimages || img_time, "build_lengths: --multiimages 1 needs img_time");
+  build_lengths_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      input_lengths, txt_lengths, img_time, n_img, multiimages, missing, skip_missing, B, T_v, T_i, T_t, kv_len);
+  return tmp::check_launch("build_lengths_kernel");
+}
+
+extern "C" int tmp_debug_materialize_mask(const int32_t* kv_len, int B, int T, uint8_t* mask, void* stream) {
+  TMP_REQUIRE(kv_len && mask && B > 0 && T > 0, "materialize_mask: bad argument");
+  const size_t total = (size_t)B * T * T;
+  materialize_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kv_len, B, T, mask);
+  return tmp::check_launch("materialize_mask_kernel");
+}
+
+extern "C" int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
+                                 void* sum_out, void* y, void* stream) {
+  TMP_REQUIRE(x && gamma && beta && y && rows >= 0, "layernorm_fwd: bad argument");
+  TMP_REQUIRE(!add || sum_out, "layernorm_fwd: fused add needs sum_out");
+  if (rows == 0) return TMP_OK;
+  const int grid = rows_grid(rows);
+  if (add)
+    layernorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)add, gamma, beta,
+                                                                        rows, (bf16*)sum_out, (bf16*)y);
+  else
+    layernorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, nullptr, gamma, beta, rows,
+                                                                         nullptr, (bf16*)y);
+  return tmp::check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
+                                 void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, float* dgamma,
+                                 float* dbeta, void* stream) {
+  TMP_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && rows >= 0, "layernorm_bwd: bad argument");
+  TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: dropout p out of range");
+  if (rows == 0) return TMP_OK;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 2LL * tmp::num_sms()) blocks = 2LL * tmp::num_sms();
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
+  const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  layernorm_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)dres, gamma, rows, (bf16*)dx, thr ? (bf16*)dx_drop : nullptr, thr,
+      scale, seed, salt, dgamma, dbeta);
+  return tmp::check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing,
+                                      int B, void* stream) {
+  TMP_REQUIRE(Yv && Yi && Yt && missing && B > 0 && Tv >= 4 && Ti >= 4 && Tt >= 4, "bottleneck_mix_fwd: bad argument");
+  bottleneck_mix_fwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>((bf16*)Yv, (bf16*)Yi, (bf16*)Yt, Tv, Ti,
+                                                                              Tt, missing, B);
+  return tmp::check_launch("bottleneck_mix_fwd_kernel");
+}
+
+extern "C" int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
+                                      const long long* missing, int B, void* stream) {
+  TMP_REQUIRE(dYv && dYi && dYt && missing && B > 0, "bottleneck_mix_bwd: bad argument");
+  bottleneck_mix_bwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      (bf16*)dYv, (bf16*)dYi, (bf16*)dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B);
+  return tmp::check_launch("bottleneck_mix_bwd_kernel");
+}
+
+extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream) {
+  TMP_REQUIRE(dY && out && M >= 0 && N > 0 && N % 8 == 0 && N <= 2048 && ld % 8 == 0, "colsum: bad argument");
+  if (M == 0) return TMP_OK;
+  const int groups = N / 8;
+  TMP_REQUIRE(groups <= 256, "colsum: N too large");
+  long long blocks = 2LL * tmp::num_sms();
+  long long rpb = (M + blocks - 1) / blocks;
+  if (rpb < 32) rpb = 32;
+  blocks = (M + rpb - 1) / rpb;
+  colsum_kernel<<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>((const bf16*)dY, ld, M, N, rpb, out);
+  return tmp::check_launch("colsum_kernel");
+}
+
+extern "C" int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                                 void* stream) {
+  TMP_REQUIRE(in && out && n >= 0 && n % 8 == 0 && drop_p >= 0.f && drop_p < 1.f, "dropout_apply: bad argument");
+  if (n == 0) return TMP_OK;
+  const uint32_t thr = (uint32_t)(drop_p * 65536.f + 0.5f);
+  const long long n8 = n / 8;
+  dropout_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)in, (bf16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt);
+  return tmp::check_launch("dropout_apply_kernel");
+}
+
+// descs: device array of n_desc {const float* src; bf16* dst; bf16* dst_t; int R; int C}; max_R/max_C bound the grid
+extern "C" int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* stream) {
+  TMP_REQUIRE(descs && n_desc > 0 && max_R > 0 && max_C > 0, "cast_weights: bad argument");
+  dim3 grid((max_C + 31) / 32, (max_R + 31) / 32, n_desc);
+  cast_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const CastDesc*)descs);
+  return tmp::check_launch("cast_weights_kernel");
+}

@@ -1,0 +1,45 @@
+// rowwise.cuh -- helpers for the "one warp = one 256-wide token row" kernels (lane l owns channels 8l..8l+7).
+#pragma once
+#include "tc05.cuh"
+
+namespace rw {
+
+constexpr int D = 256;  // --transformer-dim (reference control/config.py:97); kernels are specialised for it
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+
+__device__ __forceinline__ void load8_f32(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8_bf16(const tc05::bf16* __restrict__ p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[2 * t] = tc05::bf16lo_to_f32(w[t]);
+    v[2 * t + 1] = tc05::bf16hi_to_f32(w[t]);
+  }
+}
+__device__ __forceinline__ void store8_bf16(tc05::bf16* __restrict__ p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(tc05::pack_bf16x2(v[0], v[1]), tc05::pack_bf16x2(v[2], v[3]),
+                                            tc05::pack_bf16x2(v[4], v[5]), tc05::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void store8_f32(float* __restrict__ p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+}  // namespace rw

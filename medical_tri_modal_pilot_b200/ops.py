@@ -1,0 +1,152 @@
+"""Tensor-level wrappers over the C ABI (include/tmp_b200.h). Every function launches hand-written sm_100a
+kernels on the current CUDA stream; nothing here computes with PyTorch ops."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, ptr_array, stream_ptr
+
+D = 256
+H = 4
+BF16 = torch.bfloat16
+
+
+def _cuda_contig(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CUDA tensor required (no CPU fallback on this path)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: must be contiguous")
+    return t
+
+
+def lse_len(T: int) -> int:
+    return (T + 127) // 128 * 128
+
+
+def build_lengths(input_lengths, txt_lengths, img_time, n_img, multiimages, missing, skip_missing, T_v, T_i, T_t):
+    """kv_len[3,B] int32. img_time: fp32 [B,n_img] or None."""
+    B = input_lengths.numel()
+    _cuda_contig(input_lengths, torch.int64, "input_lengths")
+    _cuda_contig(txt_lengths, torch.int64, "txt_lengths")
+    if img_time is not None:
+        _cuda_contig(img_time, torch.float32, "img_time")
+    if missing is not None:
+        _cuda_contig(missing, torch.int64, "missing")
+    out = torch.empty(3, B, dtype=torch.int32, device=input_lengths.device)
+    check(_lib.load().tmp_build_lengths(ptr(input_lengths), ptr(txt_lengths), ptr(img_time), int(n_img),
+                                        int(multiimages), ptr(missing), int(skip_missing), B, T_v, T_i, T_t, ptr(out),
+                                        stream_ptr()), "tmp_build_lengths")
+    return out
+
+
+def materialize_mask(kv_len, T):
+    B = kv_len.numel()
+    _cuda_contig(kv_len, torch.int32, "kv_len")
+    out = torch.empty(B, T, T, dtype=torch.uint8, device=kv_len.device)
+    check(_lib.load().tmp_debug_materialize_mask(ptr(kv_len), B, T, ptr(out), stream_ptr()), "tmp_debug_materialize_mask")
+    return out.bool()
+
+
+def umse_embed(x, val4, tim4, Wfeat, out_dtype=torch.float32):
+    """x [..., 3] fp32 -> E [..., 256]. val4/tim4: (Linear.weight, Linear.bias, LN.weight, LN.bias) fp32 tensors."""
+    _cuda_contig(x, torch.float32, "x")
+    n_tok = x.numel() // 3
+    out = torch.empty(*x.shape[:-1], D, dtype=out_dtype, device=x.device)
+    check(_lib.load().tmp_umse_embed_fwd(ptr(x), n_tok, ptr_array(val4), ptr_array(tim4), ptr(Wfeat), ptr(out),
+                                         int(out_dtype == BF16), stream_ptr()), "tmp_umse_embed_fwd")
+    return out
+
+
+def stream_prologue_fwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
+                        pe, drop_p, seed, salt, X0):
+    check(_lib.load().tmp_stream_prologue_fwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
+                                              ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
+                                              ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
+                                              salt, ptr(X0), stream_ptr()), "tmp_stream_prologue_fwd")
+
+
+def stream_prologue_bwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
+                        pe, drop_p, seed, salt, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln, dproj):
+    check(_lib.load().tmp_stream_prologue_bwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
+                                              ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
+                                              ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
+                                              salt, ptr(dX0), ptr(g_val), ptr(g_tim), ptr(g_feat), ptr(g_cls),
+                                              ptr(g_bott), ptr(g_ln), ptr(dproj), stream_ptr()),
+          "tmp_stream_prologue_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, y, add=None, sum_out=None):
+    rows = x.numel() // D
+    check(_lib.load().tmp_layernorm_fwd(ptr(x), ptr(add), ptr(gamma), ptr(beta), rows, ptr(sum_out), ptr(y),
+                                        stream_ptr()), "tmp_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, dres, gamma, dx, dgamma, dbeta, dx_drop=None, drop_p=0.0, seed=0, salt=0):
+    rows = x.numel() // D
+    check(_lib.load().tmp_layernorm_bwd(ptr(dy), ptr(x), ptr(dres), ptr(gamma), rows, ptr(dx), ptr(dx_drop),
+                                        float(drop_p), seed, salt, ptr(dgamma), ptr(dbeta), stream_ptr()),
+          "tmp_layernorm_bwd")
+
+
+def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
+         salt=0, M=None):
+    """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K] bf16, Bw [N,K] bf16."""
+    K = A.shape[-1]
+    M = A.numel() // K if M is None else M
+    N = Bw.shape[0]
+    ld_out = (out if out is not None else out_f32).shape[-1]
+    check(_lib.load().tmp_gemm_bias_act_fwd(ptr(A), A.stride(-2) if A.dim() > 1 else K, ptr(Bw), Bw.stride(0), M, N, K,
+                                            float(alpha), ptr(bias), int(relu), ptr(gate),
+                                            gate.shape[-1] if gate is not None else 0, ptr(residual),
+                                            residual.shape[-1] if residual is not None else 0, float(drop_p), seed,
+                                            salt, ptr(out), ptr(out_f32), ld_out, stream_ptr()),
+          "tmp_gemm_bias_act_fwd")
+
+
+def gemm_wgrad(dY, X, dW, M=None):
+    """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]"""
+    N, K = dY.shape[-1], X.shape[-1]
+    M = dY.numel() // N if M is None else M
+    check(_lib.load().tmp_gemm_wgrad(ptr(dY), N, ptr(X), K, M, N, K, ptr(dW), stream_ptr()), "tmp_gemm_wgrad")
+
+
+def colsum(dY, out, M=None):
+    N = dY.shape[-1]
+    M = dY.numel() // N if M is None else M
+    check(_lib.load().tmp_colsum(ptr(dY), N, M, N, ptr(out), stream_ptr()), "tmp_colsum")
+
+
+def attn_fwd(qkv, kv_len, B, T, O, lse2):
+    check(_lib.load().tmp_mma_attn_fwd(ptr(qkv), ptr(kv_len), B, T, H, ptr(O), O.shape[-1], ptr(lse2), lse2.shape[-1],
+                                       stream_ptr()), "tmp_mma_attn_fwd")
+
+
+def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV):
+    check(_lib.load().tmp_mma_attn_bwd(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),
+                                       lse2.shape[-1], ptr(delta), ptr(dQ_acc), ptr(dQKV), stream_ptr()),
+          "tmp_mma_attn_bwd")
+
+
+def bottleneck_mix_fwd(Yv, Yi, Yt, missing):
+    B = Yv.shape[0]
+    check(_lib.load().tmp_bottleneck_mix_fwd(ptr(Yv), ptr(Yi), ptr(Yt), Yv.shape[1], Yi.shape[1], Yt.shape[1],
+                                             ptr(missing), B, stream_ptr()), "tmp_bottleneck_mix_fwd")
+
+
+def bottleneck_mix_bwd(dYv, dYi, dYt, upper_has_img_txt, missing):
+    B = dYv.shape[0]
+    check(_lib.load().tmp_bottleneck_mix_bwd(ptr(dYv), ptr(dYi), ptr(dYt), dYv.shape[1], dYi.shape[1], dYt.shape[1],
+                                             int(upper_has_img_txt), ptr(missing), B, stream_ptr()),
+          "tmp_bottleneck_mix_bwd")
+
+
+def dropout_apply(inp, out, drop_p, seed, salt):
+    check(_lib.load().tmp_dropout_apply(ptr(inp), ptr(out), inp.numel(), float(drop_p), seed, salt, stream_ptr()),
+          "tmp_dropout_apply")
+
+
+def cast_weights(descs_dev, n_desc, max_R, max_C):
+    check(_lib.load().tmp_cast_weights(ptr(descs_dev), n_desc, max_R, max_C, stream_ptr()), "tmp_cast_weights")
