@@ -1,0 +1,34 @@
+"""Helpers shared by the golden-fixture tests (fixtures are produced by tools/make_golden.py from the reference)."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_fixture(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+
+
+def fixture_inputs(fx):
+    """Regenerate (state_dict, batch, cfg) of a fixture from its seeds."""
+    from oracle import synth, weights
+    from oracle.tri_mbt_oracle import OracleConfig
+    nl, multi, B, L, bseed, wseed = (int(v) for v in fx["config"])
+    sd = weights.make_state_dict(nl, wseed)
+    batch = synth.make_batch(B, L, n_img=3 if multi else 1, seed=bseed, missing_mode=str(fx["missing_mode"]))
+    return sd, batch, OracleConfig(n_layers=nl, multiimages=multi)
+
+
+def grad_probe(name, g):
+    """Same seeded samples / projection as tools/make_golden.py."""
+    g = np.asarray(g, dtype=np.float64).ravel()
+    rng = np.random.Generator(np.random.PCG64(len(name) * 7919 + g.size))
+    idx = rng.integers(0, g.size, 32)
+    proj = rng.standard_normal(g.size)
+    return np.linalg.norm(g), g[idx], float(g @ proj)
