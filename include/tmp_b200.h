@@ -4,8 +4,12 @@
  * (SURVEY.md 8b). Each entry point below names the reference code it replaces (file:line under the reference
  * root). The Python host (medical_tri_modal_pilot_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
  *
- * Conventions: every pointer is a DEVICE pointer unless stated; tensors are row-major contiguous; `bf16`
- * buffers are passed as void*; every call is asynchronous on `stream` (a cudaStream_t), allocates nothing,
+ * Conventions: every pointer is a DEVICE pointer unless stated; tensors are row-major contiguous; 16-bit buffers
+ * are passed as void*. PRECISION: every 16-bit tensor on the product path is IEEE fp16 (the reference's autocast
+ * dtype, trainer.py:126; tcgen05 kind::f16 needs both MMA operands in one format); gradient tensors carry a
+ * caller-chosen power-of-two scale (the kernels are linear in it); accumulation, parameters and parameter
+ * gradients are fp32. The GEMM entry points also accept bf16 x bf16 through their `*_fmt` arguments
+ * (TMP_FMT_F16 = 0, TMP_FMT_BF16 = 1; A and B must use the same format). Every call is asynchronous on `stream` (a cudaStream_t), allocates nothing,
  * keeps no global state and never synchronises. Return 0 on success, >0 = cudaError_t, <0 = argument/driver
  * error; tmp_last_error() returns the message (thread-local). D = 256 channels, H = 4 heads of 64 everywhere
  * (control/config.py:97,99 defaults; the kernels are specialised for them).
@@ -16,6 +20,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define TMP_FMT_F16 0
+#define TMP_FMT_BF16 1
 
 int tmp_abi_version(void);
 const char* tmp_last_error(void);
@@ -33,22 +40,22 @@ int tmp_build_lengths(const long long* input_lengths, const long long* txt_lengt
 int tmp_debug_materialize_mask(const int32_t* kv_len, int B, int T, uint8_t* mask, void* stream);
 
 /* ---- a1: UMSE / TIE embedding (tri_mbt_vsltcls.py:183-190) -------------------------------------------------
- * x[n_tok,3] fp32 (time, value, feature-id-as-float) -> E[n_tok,256] (fp32 or bf16).
+ * x[n_tok,3] fp32 (time, value, feature-id-as-float) -> E[n_tok,256] (fp32 or fp16).
  * val4/tim4: HOST arrays of 4 device pointers {Linear.weight[256], Linear.bias, LayerNorm.weight, LayerNorm.bias}
  * of ie_vslt / ie_time; Wfeat = ie_feat.weight[20,256]. */
 int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* const* val4, const float* const* tim4,
-                       const float* Wfeat, void* out, int out_is_bf16, void* stream);
+                       const float* Wfeat, void* out, int out_is_fp16, void* stream);
 
 /* ---- a1+a2+a5: stream prologue --------------------------------------------------------------------------
- * X0[B, 5+n, 256] bf16 = [bottlenecks(4); Dropout(LN_in([CLS; E]) (+PE))]   (mbt_encoder.py:697-699, 719-729)
- * kind 0 (vslt): E from x[B,n,3] as above.  kind 1 (img/txt): E = proj[B*n,256] + ie_time(times[b, j / (n/n_slots)])
+ * X0[B, 5+n, 256] fp16 = [bottlenecks(4); Dropout(LN_in([CLS; E]) (+PE))]   (mbt_encoder.py:697-699, 719-729)
+ * kind 0 (vslt): E from x[B,n,3] as above.  kind 1 (img/txt): E = proj[B*n,256] (fp16) + ie_time(times[b, j / (n/n_slots)])
  * + ie_feat[feat_id]   (tri_mbt_vsltcls.py:216-224).  pe = positional_encoding.pe rows (txt only) or NULL. */
 int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
                             const float* pe, float drop_p, uint32_t seed, uint32_t salt, void* X0, void* stream);
 /* gradient accumulators are fp32 and ADDED to: g_val/g_tim [4,256] (dW, db, dLN.w, dLN.b), g_feat[20,256],
- * g_cls[256], g_bott[4,256], g_ln[2,256]; dproj[B*n,256] bf16 is written (kind 1). */
+ * g_cls[256], g_bott[4,256], g_ln[2,256]; dX0[B,5+n,256] and dproj[B*n,256] (written, kind 1) are fp16. */
 int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
@@ -58,7 +65,8 @@ int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float*
 
 /* ---- a9: LayerNorm (module.py:130-144: unbiased std, eps on std) ------------------------------------------
  * fwd: if add != NULL: sum_out = x + add, y = LN(sum_out) (encoder.py:27-30 residual fused); else y = LN(x).
- * bwd: dx = dres + dLN(dy; x); dgamma/dbeta fp32 += ; optional dx_drop = dropout(seed,salt)(dx). rows of 256. */
+ * bwd: dx = dres + dLN(dy; x); dgamma/dbeta fp32 += ; optional dx_drop = dropout(seed,salt)(dx). rows of 256.
+ * All 16-bit tensors fp16. */
 int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
                       void* sum_out, void* y, void* stream);
 int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows, void* dx,
@@ -67,27 +75,31 @@ int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const flo
 
 /* ---- a10/a11: tcgen05 GEMMs -------------------------------------------------------------------------------
  * out[M,N] = residual + dropout( gate>0 ? relu?(alpha * A[M,K].B[N,K]^T + bias) : 0 )
- * A, B bf16 K-major (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70, module.py:74-80).
- * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out_bf16 and/or out_f32 receive the result. */
-int tmp_gemm_bias_act_fwd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
-                          const float* bias, int relu, const void* gate, int ld_gate, const void* residual, int ld_res,
-                          float drop_p, uint32_t seed, uint32_t salt, void* out_bf16, float* out_f32, int ld_out,
-                          void* stream);
-/* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0) */
-int tmp_gemm_wgrad(const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW, void* stream);
-/* out[N] fp32 += column sums of dY[M,N] bf16 (bias gradient) */
+ * A, B 16-bit K-major, both fp16 or both bf16 (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70,
+ * module.py:74-80; dgrad passes the gradient as A and the transposed weight copy as B).
+ * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out16 (in out_fmt) and/or out_f32 get the result. */
+int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N, int K,
+                          float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
+                          const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
+                          void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
+/* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X) */
+int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
+                   float* dW, void* stream);
+/* out[N] fp32 += column sums of dY[M,N] fp16 (bias gradient) */
 int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream);
 
 /* ---- a10: modality-aware attention (attention.py:24-49, 65-84) ----------------------------------------------
- * qkv[B*T,768] bf16 = Q|K|V with head h at columns h*64; kv_len[B] (or NULL = unmasked);
- * O[B*T,ld_o] bf16; lse2[B,H,T_lse] fp32 (log2-domain logsumexp of the scaled scores, kept for backward). */
+ * qkv[B*T,768] fp16 = Q|K|V with head h at columns h*64; kv_len[B] (or NULL = unmasked);
+ * O[B*T,ld_o] fp16; lse2[B,H,T_lse] fp32 (log2-domain logsumexp of the scaled scores, kept for backward). */
 int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, int T, int H, void* O, int ld_o, float* lse2,
                      int T_lse, void* stream);
-/* delta[B,H,T_lse] and dQ_acc[B*T,256] fp32 are workspaces; dQKV[B*T,768] bf16 receives dQ|dK|dV. T_lse % 128 == 0. */
+/* qkv, O, dO fp16; delta[B,H,T_lse] and dQ_acc[B*T,256] fp32 are workspaces; dQKV[B*T,768] fp16 receives
+ * dQ|dK|dV. T_lse % 128 == 0. */
 int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B, int T, int H,
                      const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV, void* stream);
 
-/* ---- a7: bottleneck exchange (mbt_encoder.py:764-776), in place on rows 0..3 of Y_m[B,T_m,256] bf16 -------- */
+/* ---- a7: bottleneck exchange (mbt_encoder.py:764-776), in place on rows 0..3 of Y_m[B,T_m,256]
+ * (fp16) ---------------------------------------------------------------------------------------------------- */
 int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
                            void* stream);
 int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
@@ -95,7 +107,9 @@ int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int 
 
 /* ---- helpers ---------------------------------------------------------------------------------------------- */
 int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt, void* stream);
-/* descs: device array of n_desc records {const float* src; bf16* dst; bf16* dst_t; int R; int C} (24+8 bytes) */
+/* fp16 gradient tensors, n % 8 == 0.
+ * tmp_cast_weights: descs = device array of n_desc records {const float* src; fp16* dst; fp16* dst_t; int R; int C}
+ * (32 bytes): dst[R,C] = fp16(src), dst_t[C,R] = fp16(src)^T (either may be NULL). */
 int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* stream);
 
 #ifdef __cplusplus

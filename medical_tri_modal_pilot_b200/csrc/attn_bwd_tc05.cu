@@ -2,7 +2,7 @@
 // as a tcgen05/TMEM kernel. One CTA owns a 128-key tile of one (sample, head) and sweeps the live query tiles:
 //
 //   S^T  = K_j Q_i^T            dP^T = V_j dO_i^T                      (2 MMAs into TMEM)
-//   P^T  = exp2(S^T*c - LSE_i)  dS^T = P^T o (dP^T - delta_i) / 8      (registers -> swizzled smem, bf16)
+//   P^T  = exp2(S^T*c - LSE_i)  dS^T = P^T o (dP^T - delta_i) / 8      (registers -> swizzled smem, fp16)
 //   dV_j += P^T dO_i            dK_j += dS^T Q_i       dQ_i = dS K_j   (3 MMAs; dQ -> fp32 atomics)
 //
 // dS^T is written to shared memory once and read twice: as a K-major A operand (dK) and as an MN-major
@@ -57,7 +57,7 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const int32_t* __restrict__ kv_len, int T, const float* __restrict__ lse2,
-                const float* __restrict__ delta, int T_lse, float* __restrict__ dQ_acc, bf16* __restrict__ dQKV,
+                const float* __restrict__ delta, int T_lse, float* __restrict__ dQ_acc, uint16_t* __restrict__ dQKV,
                 float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -131,9 +131,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_kk = make_idesc_bf16(BT, BT, 0, 0);  // S^T, dP^T : both K-major, N=128
-      constexpr uint32_t idesc_kn = make_idesc_bf16(BT, HD, 0, 1);  // dV, dK   : A K-major, B MN-major, N=64
-      constexpr uint32_t idesc_nn = make_idesc_bf16(BT, HD, 1, 1);  // dQ       : A MN-major, B MN-major
+      // all operands fp16 (kind::f16 needs A and B in the same format; gradients are fp16 with a host-side scale)
+      constexpr uint32_t idesc_st = make_idesc(BT, BT, 0, 0, FMT_F16, FMT_F16);  // S^T  = K Q^T
+      constexpr uint32_t idesc_dp = make_idesc(BT, BT, 0, 0, FMT_F16, FMT_F16);  // dP^T = V dO^T
+      constexpr uint32_t idesc_dv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV  += P^T dO   (B MN-major)
+      constexpr uint32_t idesc_dk = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dK  += dS^T Q   (B MN-major)
+      constexpr uint32_t idesc_dq = make_idesc(BT, HD, 1, 1, FMT_F16, FMT_F16);  // dQ   = dS K     (A, B MN-major)
       const uint32_t sK = smem_u32(smem + kSmemK), sV = smem_u32(smem + kSmemV);
       const uint32_t sPT = smem_u32(smem + kSmemPT), sDST = smem_u32(smem + kSmemDST);
       mbar_wait(&bars->kv_full, 0);
@@ -146,11 +149,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_ST, make_sdesc_sw128(sK + k * 32, 16, 1024), make_sdesc_sw128(sQ + k * 32, 16, 1024), idesc_kk,
+          umma_ss(tm_ST, make_sdesc_sw128(sK + k * 32, 16, 1024), make_sdesc_sw128(sQ + k * 32, 16, 1024), idesc_st,
                   k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_DPT, make_sdesc_sw128(sV + k * 32, 16, 1024), make_sdesc_sw128(sDO + k * 32, 16, 1024), idesc_kk,
+          umma_ss(tm_DPT, make_sdesc_sw128(sV + k * 32, 16, 1024), make_sdesc_sw128(sDO + k * 32, 16, 1024), idesc_dp,
                   k != 0);
         umma_commit(&bars->sdp_full);
 
@@ -159,17 +162,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k) {  // dV += P^T dO_i   (reduction over the 128 queries)
           const uint64_t adesc = make_sdesc_sw128(sPT + (k >> 2) * (BT * 128) + (k & 3) * 32, 16, 1024);
-          umma_ss(tm_DV, adesc, make_sdesc_sw128(sDO + k * 2048, BT * 128, 1024), idesc_kn, (i | k) != 0);
+          umma_ss(tm_DV, adesc, make_sdesc_sw128(sDO + k * 2048, BT * 128, 1024), idesc_dv, (i | k) != 0);
         }
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k) {  // dK += dS^T Q_i
           const uint64_t adesc = make_sdesc_sw128(sDST + (k >> 2) * (BT * 128) + (k & 3) * 32, 16, 1024);
-          umma_ss(tm_DK, adesc, make_sdesc_sw128(sQ + k * 2048, BT * 128, 1024), idesc_kn, (i | k) != 0);
+          umma_ss(tm_DK, adesc, make_sdesc_sw128(sQ + k * 2048, BT * 128, 1024), idesc_dk, (i | k) != 0);
         }
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k) {  // dQ_i = dS K_j    (reduction over the 128 keys; A = dS^T read MN-major)
           umma_ss(tm_DQ, make_sdesc_sw128(sDST + k * 2048, BT * 128, 1024),
-                  make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_nn, k != 0);
+                  make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
         }
         umma_commit(&bars->dq_full);
         umma_commit(&bars->qdo_empty[st]);
@@ -208,10 +211,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const bool ok = key_ok && (i * BT + qc) < len;
             const float pv = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -st_lse[qc]));
             p[u] = ok ? pv : 0.f;
-            d[u] = p[u] * (__uint_as_float(dp[t + u]) - st_dl[qc]) * 0.125f;
+            d[u] = ok ? pv * (__uint_as_float(dp[t + u]) - st_dl[qc]) * 0.125f : 0.f;
           }
-          pp[t >> 1] = pack_bf16x2(p[0], p[1]);
-          dd[t >> 1] = pack_bf16x2(d[0], d[1]);
+          pp[t >> 1] = pack_f16x2(p[0], p[1]);
+          dd[t >> 1] = pack_f16x2(d[0], d[1]);
         }
         const uint32_t sub = (c >> 1) * (BT * 128);
 #pragma unroll
@@ -249,7 +252,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t src = which == 0 ? tm_DK : tm_DV;
-      bf16* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD;
+      uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -259,10 +262,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           uint4* dst = reinterpret_cast<uint4*>(dst_row + c * 32);
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            dst[t] = make_uint4(pack_bf16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
-                                pack_bf16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
-                                pack_bf16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
-                                pack_bf16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
+            dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
+                                pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
+                                pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
+                                pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
         }
       }
     }
@@ -278,7 +281,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h*64+d] * O[b,q,h*64+d]   (one warp per row; rows past T_lse padding are zeroed)
-__global__ void attn_bwd_delta_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, int ld, int B, int T,
+__global__ void attn_bwd_delta_kernel(const uint16_t* __restrict__ O, const uint16_t* __restrict__ dO, int ld, int B, int T,
                                       int H, float* __restrict__ delta, int T_lse) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -291,7 +294,11 @@ __global__ void attn_bwd_delta_kernel(const bf16* __restrict__ O, const bf16* __
     const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      acc += bf16lo_to_f32(ow[t]) * bf16lo_to_f32(gw[t]) + bf16hi_to_f32(ow[t]) * bf16hi_to_f32(gw[t]);
+    {
+      const float2 of = unpack2<FMT_F16>(ow[t]);
+      const float2 gf = unpack2<FMT_F16>(gw[t]);
+      acc += of.x * gf.x + of.y * gf.y;
+    }
   }
   // 8 lanes per head (8 lanes x 8 columns = 64)
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -300,8 +307,8 @@ __global__ void attn_bwd_delta_kernel(const bf16* __restrict__ O, const bf16* __
   if ((lane & 7) == 0) delta[((size_t)b * H + (lane >> 3)) * T_lse + q] = acc;
 }
 
-// dQKV[:, 0:256] = bf16(dQ_acc)
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dQ_acc, bf16* __restrict__ dQKV, size_t rows) {
+// dQKV[:, 0:256] = fp16(dQ_acc)
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dQ_acc, uint16_t* __restrict__ dQKV, size_t rows) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread = 8 columns
   if (idx >= rows * 32) return;
   const size_t row = idx >> 5;
@@ -309,13 +316,13 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dQ_acc, bf1
   const float4 a = *reinterpret_cast<const float4*>(dQ_acc + row * 256 + c8);
   const float4 b2 = *reinterpret_cast<const float4*>(dQ_acc + row * 256 + c8 + 4);
   *reinterpret_cast<uint4*>(dQKV + row * 768 + c8) =
-      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b2.x, b2.y), pack_bf16x2(b2.z, b2.w));
+      make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b2.x, b2.y), pack_f16x2(b2.z, b2.w));
 }
 
 }  // namespace
 
-// qkv [B*T,768], O/dO [B*T,ld] bf16; lse2 from the forward; delta [B,H,T_lse] and dQ_acc [B*T,256] fp32 are
-// workspaces (dQ_acc is zeroed here); dQKV [B*T,768] bf16 receives dQ|dK|dV.
+// qkv [B*T,768] and O [B*T,ld] fp16 (forward quantities), dO [B*T,ld] fp16 (scaled gradient); lse2 from the forward; delta [B,H,T_lse] and dQ_acc [B*T,256] fp32 are
+// workspaces (dQ_acc is zeroed here); dQKV [B*T,768] fp16 receives dQ|dK|dV.
 extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B,
                                 int T, int H, const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV,
                                 void* stream) {
@@ -339,7 +346,7 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   if (rc) return rc;
   {
     const int rows = B * T_lse;
-    attn_bwd_delta_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const bf16*)O, (const bf16*)dO, ld, B, T, H, delta, T_lse);
+    attn_bwd_delta_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const uint16_t*)O, (const uint16_t*)dO, ld, B, T, H, delta, T_lse);
     rc = tmp::check_launch("attn_bwd_delta_kernel");
     if (rc) return rc;
   }
@@ -349,11 +356,11 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     return (int)e;
   }
   dim3 grid((T + BT - 1) / BT, H, B);
-  attn_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, kv_len, T, lse2, delta, T_lse, dQ_acc, (bf16*)dQKV,
+  attn_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, kv_len, T, lse2, delta, T_lse, dQ_acc, (uint16_t*)dQKV,
                                                       kLog2e / 8.0f);
   rc = tmp::check_launch("attn_bwd_kernel");
   if (rc) return rc;
   const size_t rows = (size_t)B * T;
-  attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (bf16*)dQKV, rows);
+  attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (uint16_t*)dQKV, rows);
   return tmp::check_launch("attn_bwd_dq_convert_kernel");
 }

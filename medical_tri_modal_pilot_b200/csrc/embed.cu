@@ -8,7 +8,7 @@
 // polynomials of the scalar (no cross-lane reduction): mean = s*wbar + bbar, var = s^2*A + 2s*C + Dv.
 //
 // One warp per token row, lane l owns channels 8l..8l+7: every global access is a 16 B vector per lane,
-// 512 B contiguous per warp (bf16 rows).
+// 512 B contiguous per warp (16-bit rows). Forward tensors are fp16, gradient tensors bf16.
 #include "common.cuh"
 #include "rowwise.cuh"
 
@@ -69,9 +69,9 @@ __device__ __forceinline__ void branch_add(const BranchLane& L, float s, float r
 
 // ------------------------------------------------------------------------------------------------
 // raw UMSE/TIE embedding (a1): x[n_tok,3] (time,value,feat) -> E[n_tok,256]; used for the bit-exact gather
-// parity test and the HBM-roofline measurement (12 B in + 512 B bf16 out per token).
+// parity test and the HBM-roofline measurement (12 B in + 512 B fp16 out per token).
 // ------------------------------------------------------------------------------------------------
-template <bool OUT_BF16>
+template <bool OUT_16>
 __global__ void __launch_bounds__(256) umse_embed_fwd_kernel(const float* __restrict__ x, long long n_tok, Branch val,
                                                              Branch tim, const float* __restrict__ Wfeat,
                                                              void* __restrict__ out) {
@@ -113,14 +113,14 @@ __global__ void __launch_bounds__(256) umse_embed_fwd_kernel(const float* __rest
       e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w;
       e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
       const long long row = grp * 32 + j;
-      if (OUT_BF16) store8_bf16((bf16*)out + row * D + lane * 8, e);
+      if (OUT_16) store8<ACT>((h16*)out + row * D + lane * 8, e);
       else store8_f32((float*)out + row * D + lane * 8, e);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// stream prologue: builds the layer-0 input of one modality stream, X0[B, T=5+n, 256] bf16.
+// stream prologue: builds the layer-0 input of one modality stream, X0[B, T=5+n, 256] fp16.
 // KIND 0 = vslt (UMSE triples), KIND 1 = img/txt (projected rows + shared time branch + constant feature id).
 // ------------------------------------------------------------------------------------------------
 struct PrologueParams {
@@ -129,7 +129,7 @@ struct PrologueParams {
   const float* x;              // [B, n, 3]
   Branch val;
   // KIND 1
-  const bf16* proj;            // [B*n, 256]
+  const h16* proj;             // [B*n, 256] fp16
   const float* times;          // [B * n_slots]
   int n_slots, rows_per_slot;  // n = n_slots * rows_per_slot
   int feat_id;
@@ -142,7 +142,7 @@ struct PrologueParams {
   const float* ln_b;
   const float* pe;             // [>=T-4, 256] or null
   uint32_t drop_thr16; float drop_scale; uint32_t seed, salt;
-  bf16* X0;                    // [B, T, 256]
+  h16* X0;                     // [B, T, 256] fp16
 };
 
 template <int KIND>
@@ -164,7 +164,7 @@ __device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, cons
     fid = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19);
     branch_add(V, s_val, branch_rstd(V, s_val), e);
   } else {
-    load8_bf16(p.proj + ((size_t)b * p.n + j) * D + lane * 8, e);
+    load8<ACT>(p.proj + ((size_t)b * p.n + j) * D + lane * 8, e);
     s_time = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
     fid = p.feat_id;
   }
@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
   const long long rows = (long long)p.B * p.T;
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     const int b = (int)(row / p.T), t = (int)(row % p.T);
-    bf16* dst = p.X0 + row * D + lane * 8;
+    h16* dst = p.X0 + row * D + lane * 8;
     float e[8], sv = 0.f, st = 0.f;
     int fid = 0;
     if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
       load8_f32(p.bottlenecks + t * D + lane * 8, e);
-      store8_bf16(dst, e);
+      store8<ACT>(dst, e);
       continue;
     }
     float s1 = 0.f;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
       for (int i = 0; i < 8; ++i)
         y[i] = dropout_keep(p.seed, p.salt, base + i, p.drop_thr16) ? y[i] * p.drop_scale : 0.f;
     }
-    store8_bf16(dst, y);
+    store8<ACT>(dst, y);
   }
 }
 
@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
 // ------------------------------------------------------------------------------------------------
 struct PrologueBwdParams {
   PrologueParams f;
-  const bf16* dX0;   // [B, T, 256]
+  const h16* dX0;    // [B, T, 256] bf16 (gradient)
   float* g_val; float* g_tim; float* g_feat; float* g_cls; float* g_bott; float* g_ln;
-  bf16* dproj;
+  h16* dproj;        // [B*n, 256] bf16 (gradient)
 };
 
 struct BranchAcc { float dw[8], db[8], dg[8], dbe[8]; };
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     const int b = (int)(row / p.T), t = (int)(row % p.T);
     float g[8];
-    load8_bf16(q.dX0 + row * D + lane * 8, g);
+    load8<GRD>(q.dX0 + row * D + lane * 8, g);
     float e[8], sv = 0.f, st = 0.f;
     int fid = 0;
     if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(&sG[fid * D + lane * 8 + i], de[i]);
     } else {
-      store8_bf16(q.dproj + ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
+      store8<GRD>(q.dproj + ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a_feat[i] += de[i];
     }
@@ -394,7 +394,7 @@ int grid_for_rows(long long rows) {
 
 // branch parameter block: 4 pointers (Linear.weight[256,1], Linear.bias, LayerNorm.weight, LayerNorm.bias)
 extern "C" int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* const* val4, const float* const* tim4,
-                                  const float* Wfeat, void* out, int out_is_bf16, void* stream) {
+                                  const float* Wfeat, void* out, int out_is_fp16, void* stream) {
   TMP_REQUIRE(x && val4 && tim4 && Wfeat && out && n_tok >= 0, "umse_embed_fwd: bad argument");
   if (n_tok == 0) return TMP_OK;
   Branch v{val4[0], val4[1], val4[2], val4[3]}, t{tim4[0], tim4[1], tim4[2], tim4[3]};
@@ -402,7 +402,7 @@ extern "C" int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* 
   long long blocks = (grp + 7) / 8;
   const long long cap = (long long)tmp::num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (out_is_bf16)
+  if (out_is_fp16)
     umse_embed_fwd_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_tok, v, t, Wfeat, out);
   else
     umse_embed_fwd_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n_tok, v, t, Wfeat, out);
@@ -422,7 +422,7 @@ static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float*
   p.B = B; p.n = n; p.T = 5 + n;
   p.x = x;
   if (val4) p.val = Branch{val4[0], val4[1], val4[2], val4[3]}; else p.val = Branch{nullptr, nullptr, nullptr, nullptr};
-  p.proj = (const bf16*)proj; p.times = times; p.n_slots = n_slots > 0 ? n_slots : 1;
+  p.proj = (const h16*)proj; p.times = times; p.n_slots = n_slots > 0 ? n_slots : 1;
   p.rows_per_slot = n_slots > 0 ? n / n_slots : n; if (p.rows_per_slot < 1) p.rows_per_slot = 1;
   p.feat_id = feat_id;
   p.tim = Branch{tim4[0], tim4[1], tim4[2], tim4[3]};
@@ -430,7 +430,7 @@ static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float*
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.salt = salt;
-  p.X0 = (bf16*)X0;
+  p.X0 = (h16*)X0;
   return TMP_OK;
 }
 
@@ -464,9 +464,9 @@ extern "C" int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, c
   TMP_REQUIRE(dX0 && g_tim && g_feat && g_cls && g_bott && g_ln, "prologue_bwd: null gradient buffer");
   TMP_REQUIRE(kind == 1 || g_val, "prologue_bwd: vslt needs g_val");
   TMP_REQUIRE(kind == 0 || dproj, "prologue_bwd: img/txt needs dproj");
-  q.dX0 = (const bf16*)dX0;
+  q.dX0 = (const h16*)dX0;
   q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
-  q.dproj = (bf16*)dproj;
+  q.dproj = (h16*)dproj;
   const int smem = (20 + 20 + 15) * D * 4;
   static bool attr_set = false;
   if (!attr_set) {

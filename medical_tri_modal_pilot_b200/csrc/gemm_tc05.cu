@@ -23,14 +23,16 @@ struct EpiParams {
   float alpha;            // scale on the accumulator
   const float* bias;      // [N] fp32 or null
   int relu;               // apply ReLU after bias
-  const bf16* gate;       // [M, ld_gate] : multiply by (gate > 0)  (ReLU backward) or null
+  const uint16_t* gate;   // [M, ld_gate] 16-bit: multiply by (gate > 0)  (ReLU backward) or null
   int ld_gate;
-  const bf16* residual;   // [M, ld_res] added last, or null
+  const uint16_t* residual;  // [M, ld_res] 16-bit, added last, or null
   int ld_res;
+  int a_fmt, b_fmt;       // operand formats (FMT_F16 / FMT_BF16)
+  int out_fmt, gate_fmt, res_fmt;
   uint32_t drop_thr16;    // 0 = no dropout; else round(p*65536)
   float drop_scale;       // 1/(1-p)
   uint32_t seed, salt;
-  bf16* out;              // [M, ld_out] bf16 (or null)
+  uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null)
   float* out_f32;         // [M, ld_out] fp32 (or null)
   int ld_out;
 };
@@ -105,7 +107,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t idesc = make_idesc(BM, BN, 0, 0, p.a_fmt, p.b_fmt);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -172,8 +174,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                if (!(bf16lo_to_f32(w[t]) > 0.f)) v[q * 8 + t * 2] = 0.f;
-                if (!(bf16hi_to_f32(w[t]) > 0.f)) v[q * 8 + t * 2 + 1] = 0.f;
+                const float2 gv = unpack2_rt(w[t], p.gate_fmt);
+                if (!(gv.x > 0.f)) v[q * 8 + t * 2] = 0.f;
+                if (!(gv.y > 0.f)) v[q * 8 + t * 2 + 1] = 0.f;
               }
             }
           }
@@ -191,8 +194,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                v[q * 8 + t * 2] += bf16lo_to_f32(w[t]);
-                v[q * 8 + t * 2 + 1] += bf16hi_to_f32(w[t]);
+                const float2 rv = unpack2_rt(w[t], p.res_fmt);
+                v[q * 8 + t * 2] += rv.x;
+                v[q * 8 + t * 2 + 1] += rv.y;
               }
             }
           }
@@ -201,10 +205,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 u;
-              u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              u.x = pack2_rt(v[q * 8 + 0], v[q * 8 + 1], p.out_fmt);
+              u.y = pack2_rt(v[q * 8 + 2], v[q * 8 + 3], p.out_fmt);
+              u.z = pack2_rt(v[q * 8 + 4], v[q * 8 + 5], p.out_fmt);
+              u.w = pack2_rt(v[q * 8 + 6], v[q * 8 + 7], p.out_fmt);
               o[q] = u;
             }
           }
@@ -249,7 +253,7 @@ struct WgradSmem {
 template <int BNW>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int ldw,
-                  float* __restrict__ dW, int rows_per_split) {
+                  float* __restrict__ dW, int rows_per_split, int y_fmt, int x_fmt) {
   using L = WgradSmem<BNW>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -303,7 +307,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
+        const uint32_t idesc = make_idesc(128, BNW, 1, 1, y_fmt, x_fmt);
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < k_blks; ++kb) {
@@ -369,7 +373,8 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p
 }
 
 template <int BNW>
-int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, cudaStream_t st) {
+int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, int y_fmt, int x_fmt,
+                 cudaStream_t st) {
   using L = WgradSmem<BNW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -388,7 +393,7 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, i
   if (rows_per_split < BK) rows_per_split = BK;
   splits = (M + rows_per_split - 1) / rows_per_split;
   dim3 grid(N / 128, K / BNW, splits);
-  gemm_wgrad_kernel<BNW><<<grid, kThreads, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split);
+  gemm_wgrad_kernel<BNW><<<grid, kThreads, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split, y_fmt, x_fmt);
   return tmp::check_launch("gemm_wgrad_kernel");
 }
 
@@ -397,11 +402,18 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, i
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-extern "C" int tmp_gemm_bias_act_fwd(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
-                                     const float* bias, int relu, const void* gate, int ld_gate, const void* residual,
-                                     int ld_res, float drop_p, uint32_t seed, uint32_t salt, void* out_bf16,
-                                     float* out_f32, int ld_out, void* stream) {
+static bool fmt_ok(int f) { return f == FMT_F16 || f == FMT_BF16; }
+
+extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N,
+                                     int K, float alpha, const float* bias, int relu, const void* gate, int gate_fmt,
+                                     int ld_gate, const void* residual, int res_fmt, int ld_res, float drop_p,
+                                     uint32_t seed, uint32_t salt, void* out16, int out_fmt, float* out_f32, int ld_out,
+                                     void* stream) {
+  void* out_bf16 = out16;
   TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
+  TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok(gate_fmt)) &&
+                  (!residual || fmt_ok(res_fmt)), "gemm: formats must be 0 (fp16) or 1 (bf16)");
+  TMP_REQUIRE(a_fmt == b_fmt, "gemm: tcgen05 kind::f16 needs A and B in the same 16-bit format");
   TMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   TMP_REQUIRE(N % 128 == 0 && K % BK == 0, "gemm: N must be a multiple of 128 and K of 64 (N=%d K=%d)", N, K);
   TMP_REQUIRE(ld_out % 8 == 0 && (!gate || ld_gate % 8 == 0) && (!residual || ld_res % 8 == 0),
@@ -418,27 +430,29 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int lda, const void* B, int 
   if (rc) return rc;
   EpiParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.bias = bias; p.relu = relu;
-  p.gate = (const bf16*)gate; p.ld_gate = ld_gate;
-  p.residual = (const bf16*)residual; p.ld_res = ld_res;
+  p.gate = (const uint16_t*)gate; p.ld_gate = ld_gate;
+  p.residual = (const uint16_t*)residual; p.ld_res = ld_res;
+  p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.out_fmt = out_fmt; p.gate_fmt = gate_fmt; p.res_fmt = res_fmt;
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.salt = salt;
-  p.out = (bf16*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
+  p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   const int tiles = m_blks * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
   if (BN == 256) return launch_tn<256>(tmA, tmB, p, grid, (cudaStream_t)stream);
   return launch_tn<128>(tmA, tmB, p, grid, (cudaStream_t)stream);
 }
 
-extern "C" int tmp_gemm_wgrad(const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
-                              void* stream) {
+extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
+                              float* dW, void* stream) {
   TMP_REQUIRE(dY && X && dW, "wgrad: null operand");
+  TMP_REQUIRE(fmt_ok(y_fmt) && fmt_ok(x_fmt) && y_fmt == x_fmt, "wgrad: dY and X must share one 16-bit format");
   TMP_REQUIRE(M > 0 && N % 128 == 0 && K % 128 == 0, "wgrad: need N,K multiples of 128 (M=%d N=%d K=%d)", M, N, K);
   CUtensorMap tmY, tmX;
   int rc = tmp::encode_tmap_2d_bf16(&tmY, dY, (uint64_t)N, (uint64_t)M, (uint64_t)ldy * 2, 64, BK);
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
   if (rc) return rc;
-  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, (cudaStream_t)stream);
-  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, (cudaStream_t)stream);
+  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, y_fmt, x_fmt, (cudaStream_t)stream);
+  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, y_fmt, x_fmt, (cudaStream_t)stream);
 }

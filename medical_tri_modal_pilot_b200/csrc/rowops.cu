@@ -4,7 +4,7 @@
 //   * tmp_layernorm_fwd / bwd : the reference's hand-written LayerNorm (module.py:130-144: unbiased std,
 //     eps added to std) with the residual add / residual gradient fused, one warp per row
 //   * tmp_bottleneck_mix_fwd / bwd : modality-aware bottleneck exchange (mbt_encoder.py:764-776)
-//   * tmp_colsum : bias gradients; tmp_dropout_apply; tmp_cast_weights : fp32 master -> bf16 (+transposed) copies
+//   * tmp_colsum : bias gradients; tmp_dropout_apply; tmp_cast_weights : fp32 master -> fp16 (+transposed) copies
 #include "common.cuh"
 #include "rowwise.cuh"
 
@@ -70,12 +70,12 @@ __device__ __forceinline__ void ln_stats(float (&c)[8], float& r, float& s_std) 
   r = 1.f / (s_std + 1e-6f);
 }
 
-// ADD: h = x + o written to `sum_out`, then normalised.  x,o,sum_out,y: [rows,256] bf16
+// ADD: h = x + o written to `sum_out`, then normalised.  x,o,sum_out,y: [rows,256] fp16
 template <bool ADD>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const h16* __restrict__ x, const h16* __restrict__ o,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows,
-                                                            bf16* __restrict__ sum_out, bf16* __restrict__ y) {
+                                                            h16* __restrict__ sum_out, h16* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   float g[8], be[8];
   load8_f32(gamma + lane * 8, g);
@@ -83,31 +83,31 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     float c[8];
-    load8_bf16(x + row * D + lane * 8, c);
+    load8<ACT>(x + row * D + lane * 8, c);
     if (ADD) {
       float a[8];
-      load8_bf16(o + row * D + lane * 8, a);
+      load8<ACT>(o + row * D + lane * 8, a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) c[i] += a[i];
-      store8_bf16(sum_out + row * D + lane * 8, c);
-      // normalise the bf16-rounded sum: it is what the backward pass and the residual path see
-      load8_bf16(sum_out + row * D + lane * 8, c);
+      store8<ACT>(sum_out + row * D + lane * 8, c);
+      // normalise the fp16-rounded sum: it is what the backward pass and the residual path see
+      load8<ACT>(sum_out + row * D + lane * 8, c);
     }
     float r, sd;
     ln_stats(c, r, sd);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaf(c[i] * r, g[i], be[i]);
-    store8_bf16(y + row * D + lane * 8, v);
+    store8<ACT>(y + row * D + lane * 8, v);
   }
 }
 
 // dx = dres + LN'(dy; x).  Optionally also writes dx_drop = dropout_mask(seed,salt) * dx / (1-p)
 // (the gradient entering the previous block's FFN2 when its output dropout is active).
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const bf16* __restrict__ dres,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restrict__ dy, const h16* __restrict__ x,
+                                                            const h16* __restrict__ dres,
                                                             const float* __restrict__ gamma, long long rows,
-                                                            bf16* __restrict__ dx, bf16* __restrict__ dx_drop,
+                                                            h16* __restrict__ dx, h16* __restrict__ dx_drop,
                                                             uint32_t drop_thr16, float drop_scale, uint32_t seed,
                                                             uint32_t salt, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta) {
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     float c[8], gy[8];
-    load8_bf16(x + row * D + lane * 8, c);
-    load8_bf16(dy + row * D + lane * 8, gy);
+    load8<ACT>(x + row * D + lane * 8, c);
+    load8<GRD>(dy + row * D + lane * 8, gy);
     float r, sd;
     ln_stats(c, r, sd);
     float gbar = 0.f, gc = 0.f;
@@ -144,17 +144,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
     for (int i = 0; i < 8; ++i) out[i] = r * (gy[i] - gbar) - k2 * c[i];
     if (dres) {
       float a[8];
-      load8_bf16(dres + row * D + lane * 8, a);
+      load8<GRD>(dres + row * D + lane * 8, a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) out[i] += a[i];
     }
-    store8_bf16(dx + row * D + lane * 8, out);
+    store8<GRD>(dx + row * D + lane * 8, out);
     if (dx_drop) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         out[i] = dropout_keep(seed, salt, base + i, drop_thr16) ? out[i] * drop_scale : 0.f;
-      store8_bf16(dx_drop + row * D + lane * 8, out);
+      store8<GRD>(dx_drop + row * D + lane * 8, out);
     }
   }
 #pragma unroll
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// bottleneck exchange (a7). Y_m: [B, T_m, 256] bf16; rows 0..3 of every present stream are replaced by the
+// bottleneck exchange (a7). Y_m: [B, T_m, 256] fp16 (forward) / bf16 (gradients); rows 0..3 of every present stream are replaced by the
 // per-sample mean over the modalities selected by `missing` (0: v,i,t  1: v,i  2: v,t  3: v).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mix_weights(long long code, float (&w)[3]) {
@@ -182,7 +182,7 @@ __device__ __forceinline__ void mix_weights(long long code, float (&w)[3]) {
   }
 }
 
-__global__ void bottleneck_mix_fwd_kernel(bf16* __restrict__ Yv, bf16* __restrict__ Yi, bf16* __restrict__ Yt, int Tv,
+__global__ void bottleneck_mix_fwd_kernel(h16* __restrict__ Yv, h16* __restrict__ Yi, h16* __restrict__ Yt, int Tv,
                                           int Ti, int Tt, const long long* __restrict__ missing, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -190,27 +190,27 @@ __global__ void bottleneck_mix_fwd_kernel(bf16* __restrict__ Yv, bf16* __restric
   const int b = row >> 2, r = row & 3;
   float w[3];
   mix_weights(missing[b], w);
-  bf16* pv = Yv + ((size_t)b * Tv + r) * D + lane * 8;
-  bf16* pi = Yi + ((size_t)b * Ti + r) * D + lane * 8;
-  bf16* pt = Yt + ((size_t)b * Tt + r) * D + lane * 8;
+  h16* pv = Yv + ((size_t)b * Tv + r) * D + lane * 8;
+  h16* pi = Yi + ((size_t)b * Ti + r) * D + lane * 8;
+  h16* pt = Yt + ((size_t)b * Tt + r) * D + lane * 8;
   float acc[8], a[8];
-  load8_bf16(pv, acc);
+  load8<ACT>(pv, acc);
   // sum first, scale once: the reference takes torch.mean over the selected stack (mbt_encoder.py:765-768)
-  if (w[1] != 0.f) { load8_bf16(pi, a);
+  if (w[1] != 0.f) { load8<ACT>(pi, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
-  if (w[2] != 0.f) { load8_bf16(pt, a);
+  if (w[2] != 0.f) { load8<ACT>(pt, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] *= w[0];
-  store8_bf16(pv, acc);
-  store8_bf16(pi, acc);
-  store8_bf16(pt, acc);
+  store8<ACT>(pv, acc);
+  store8<ACT>(pi, acc);
+  store8<ACT>(pt, acc);
 }
 
 // gradient: g = sum over present dY_m rows; dY_m rows <- w_m * g.  A null pointer = stream absent in the upper layer.
-__global__ void bottleneck_mix_bwd_kernel(bf16* __restrict__ dYv, bf16* __restrict__ dYi, bf16* __restrict__ dYt,
+__global__ void bottleneck_mix_bwd_kernel(h16* __restrict__ dYv, h16* __restrict__ dYi, h16* __restrict__ dYt,
                                           int Tv, int Ti, int Tt, int upper_has_it,
                                           const long long* __restrict__ missing, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -219,35 +219,35 @@ __global__ void bottleneck_mix_bwd_kernel(bf16* __restrict__ dYv, bf16* __restri
   const int b = row >> 2, r = row & 3;
   float w[3];
   mix_weights(missing[b], w);
-  bf16* pv = dYv + ((size_t)b * Tv + r) * D + lane * 8;
-  bf16* pi = dYi + ((size_t)b * Ti + r) * D + lane * 8;
-  bf16* pt = dYt + ((size_t)b * Tt + r) * D + lane * 8;
+  h16* pv = dYv + ((size_t)b * Tv + r) * D + lane * 8;
+  h16* pi = dYi + ((size_t)b * Ti + r) * D + lane * 8;
+  h16* pt = dYt + ((size_t)b * Tt + r) * D + lane * 8;
   float g[8], a[8], o[8];
-  load8_bf16(pv, g);
+  load8<GRD>(pv, g);
   if (upper_has_it) {
-    load8_bf16(pi, a);
+    load8<GRD>(pi, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += a[i];
-    load8_bf16(pt, a);
+    load8<GRD>(pt, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += a[i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[0];
-  store8_bf16(pv, o);
+  store8<GRD>(pv, o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[1];
-  store8_bf16(pi, o);
+  store8<GRD>(pi, o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[2];
-  store8_bf16(pt, o);
+  store8<GRD>(pt, o);
 }
 
 // ------------------------------------------------------------------------------------------------
-// column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (bf16 in, fp32 atomics out)
+// column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (bf16 gradients in, fp32 atomics out)
 // block = 256 threads = (N/8 column groups) x (rows in flight)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dY, int ld, long long M, int N,
+__global__ void __launch_bounds__(256) colsum_kernel(const h16* __restrict__ dY, int ld, long long M, int N,
                                                      long long rows_per_block, float* __restrict__ out) {
   extern __shared__ float sacc[];  // [N]
   for (int i = threadIdx.x; i < N; i += blockDim.x) sacc[i] = 0.f;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dY
     const long long r1 = min(M, r0 + rows_per_block);
     for (long long r = r0 + rl; r < r1; r += lanes_r) {
       float v[8];
-      load8_bf16(dY + r * ld + cg * 8, v);
+      load8<GRD>(dY + r * ld + cg * 8, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
@@ -274,22 +274,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dY
   for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&out[i], sacc[i]);
 }
 
-__global__ void dropout_apply_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8,
+__global__ void dropout_apply_kernel(const h16* __restrict__ in, h16* __restrict__ out, long long n8,
                                      uint32_t thr16, float scale, uint32_t seed, uint32_t salt) {
   const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i8 >= n8) return;
   float v[8];
-  load8_bf16(in + i8 * 8, v);
+  load8<GRD>(in + i8 * 8, v);
   const uint32_t base = (uint32_t)(i8 * 8);
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = dropout_keep(seed, salt, base + i, thr16) ? v[i] * scale : 0.f;
-  store8_bf16(out + i8 * 8, v);
+  store8<GRD>(out + i8 * 8, v);
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight refresh: fp32 master [R,C] -> bf16 [R,C] and bf16 transposed [C,R], batched over a descriptor table
+// weight refresh: fp32 master [R,C] -> fp16 [R,C] and fp16 transposed [C,R], batched over a descriptor table
 // ------------------------------------------------------------------------------------------------
-struct CastDesc { const float* src; bf16* dst; bf16* dst_t; int R, C; };
+struct CastDesc { const float* src; __half* dst; __half* dst_t; int R, C; };
 
 __global__ void cast_weights_kernel(const CastDesc* __restrict__ descs) {
   __shared__ float tile[32][33];
@@ -302,7 +302,7 @@ __global__ void cast_weights_kernel(const CastDesc* __restrict__ descs) {
     float v = 0.f;
     if (r < d.R && c < d.C) {
       v = d.src[(size_t)r * d.C + c];
-      if (d.dst) d.dst[(size_t)r * d.C + c] = __float2bfloat16(v);
+      if (d.dst) d.dst[(size_t)r * d.C + c] = __float2half_rn(v);
     }
     tile[i][tx] = v;
   }
@@ -310,7 +310,7 @@ __global__ void cast_weights_kernel(const CastDesc* __restrict__ descs) {
   if (d.dst_t) {
     for (int i = ty; i < 32; i += 8) {
       const int c = c0 + i, r = r0 + tx;
-      if (r < d.R && c < d.C) d.dst_t[(size_t)c * d.R + r] = __float2bfloat16(tile[tx][i]);
+      if (r < d.R && c < d.C) d.dst_t[(size_t)c * d.R + r] = __float2half_rn(tile[tx][i]);
     }
   }
 }
@@ -349,11 +349,11 @@ extern "C" int tmp_layernorm_fwd(const void* x, const void* add, const float* ga
   if (rows == 0) return TMP_OK;
   const int grid = rows_grid(rows);
   if (add)
-    layernorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)add, gamma, beta,
-                                                                        rows, (bf16*)sum_out, (bf16*)y);
+    layernorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const h16*)x, (const h16*)add, gamma, beta,
+                                                                        rows, (h16*)sum_out, (h16*)y);
   else
-    layernorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, nullptr, gamma, beta, rows,
-                                                                         nullptr, (bf16*)y);
+    layernorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const h16*)x, nullptr, gamma, beta, rows,
+                                                                         nullptr, (h16*)y);
   return tmp::check_launch("layernorm_fwd_kernel");
 }
 
@@ -368,7 +368,7 @@ extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   layernorm_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)dres, gamma, rows, (bf16*)dx, thr ? (bf16*)dx_drop : nullptr, thr,
+      (const h16*)dy, (const h16*)x, (const h16*)dres, gamma, rows, (h16*)dx, thr ? (h16*)dx_drop : nullptr, thr,
       scale, seed, salt, dgamma, dbeta);
   return tmp::check_launch("layernorm_bwd_kernel");
 }
@@ -376,7 +376,7 @@ extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres
 extern "C" int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing,
                                       int B, void* stream) {
   TMP_REQUIRE(Yv && Yi && Yt && missing && B > 0 && Tv >= 4 && Ti >= 4 && Tt >= 4, "bottleneck_mix_fwd: bad argument");
-  bottleneck_mix_fwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>((bf16*)Yv, (bf16*)Yi, (bf16*)Yt, Tv, Ti,
+  bottleneck_mix_fwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>((h16*)Yv, (h16*)Yi, (h16*)Yt, Tv, Ti,
                                                                               Tt, missing, B);
   return tmp::check_launch("bottleneck_mix_fwd_kernel");
 }
@@ -385,7 +385,7 @@ extern "C" int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, i
                                       const long long* missing, int B, void* stream) {
   TMP_REQUIRE(dYv && dYi && dYt && missing && B > 0, "bottleneck_mix_bwd: bad argument");
   bottleneck_mix_bwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      (bf16*)dYv, (bf16*)dYi, (bf16*)dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B);
+      (h16*)dYv, (h16*)dYi, (h16*)dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B);
   return tmp::check_launch("bottleneck_mix_bwd_kernel");
 }
 
@@ -398,7 +398,7 @@ extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out
   long long rpb = (M + blocks - 1) / blocks;
   if (rpb < 32) rpb = 32;
   blocks = (M + rpb - 1) / rpb;
-  colsum_kernel<<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>((const bf16*)dY, ld, M, N, rpb, out);
+  colsum_kernel<<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>((const h16*)dY, ld, M, N, rpb, out);
   return tmp::check_launch("colsum_kernel");
 }
 
@@ -409,7 +409,7 @@ extern "C" int tmp_dropout_apply(const void* in, void* out, long long n, float d
   const uint32_t thr = (uint32_t)(drop_p * 65536.f + 0.5f);
   const long long n8 = n / 8;
   dropout_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)in, (bf16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt);
+      (const h16*)in, (h16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt);
   return tmp::check_launch("dropout_apply_kernel");
 }
 

@@ -24,19 +24,30 @@ __device__ __forceinline__ void load8_f32(const float* __restrict__ p, float (&v
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void load8_bf16(const tc05::bf16* __restrict__ p, float (&v)[8]) {
+// 8 consecutive 16-bit elements (16 B) <-> 8 floats; FMT = tc05::FMT_F16 (activations) or FMT_BF16 (gradients)
+typedef uint16_t h16;  // storage type of either 16-bit format
+template <int FMT>
+__device__ __forceinline__ void load8(const h16* __restrict__ p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    v[2 * t] = tc05::bf16lo_to_f32(w[t]);
-    v[2 * t + 1] = tc05::bf16hi_to_f32(w[t]);
+    const float2 f = tc05::unpack2<FMT>(w[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store8_bf16(tc05::bf16* __restrict__ p, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(tc05::pack_bf16x2(v[0], v[1]), tc05::pack_bf16x2(v[2], v[3]),
-                                            tc05::pack_bf16x2(v[4], v[5]), tc05::pack_bf16x2(v[6], v[7]));
+template <int FMT>
+__device__ __forceinline__ void store8(h16* __restrict__ p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(tc05::pack2<FMT>(v[0], v[1]), tc05::pack2<FMT>(v[2], v[3]),
+                                            tc05::pack2<FMT>(v[4], v[5]), tc05::pack2<FMT>(v[6], v[7]));
 }
+// tcgen05 kind::f16 requires both MMA operands in the SAME 16-bit format (mixing fp16 x bf16 is an illegal
+// instruction), and every backward GEMM multiplies a gradient by a forward tensor -> one format everywhere.
+// fp16 is used (8x finer than bf16; the reference's autocast dtype); gradient tensors carry a static
+// power-of-two scale applied by the host at the backward entry (see runtime.py GRAD_SCALE).
+constexpr int ACT = tc05::FMT_F16;  // forward activations / weights
+constexpr int GRD = tc05::FMT_F16;  // gradient tensors (scaled)
 __device__ __forceinline__ void store8_f32(float* __restrict__ p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -116,9 +117,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Instruction descriptor, kind::f16, BF16 x BF16 -> FP32 accumulate, dense.
 //   bits[4,6)=c_format(1=F32) [7,10)=a_format(1=BF16) [10,13)=b_format(1=BF16)
 //   bit15=a_major (0=K,1=MN)  bit16=b_major  [17,23)=N>>3  [24,29)=M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+//   a_fmt / b_fmt: 0 = F16, 1 = BF16 (the two operands may differ: forward activations and weights are fp16,
+//   gradient tensors are bf16 -- see DESIGN.md "precision").
+enum : int { FMT_F16 = 0, FMT_BF16 = 1 };
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // Shared-memory matrix descriptor for 128B-swizzled operand tiles (rows of 128 bytes, 8-row / 1024 B atoms).
 //   bits[0,14)=addr>>4  [16,30)=LBO>>4  [32,46)=SBO>>4  [46,48)=version(1 on sm_100)  [61,64)=layout (2=SW128)
@@ -222,6 +226,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit pair <-> float pair, format chosen at compile time (FMT_F16 / FMT_BF16)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (FMT == FMT_F16) return pack_f16x2(lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if (FMT == FMT_F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return make_float2(bf16lo_to_f32(v), bf16hi_to_f32(v));
+}
+// runtime-format variants (uniform branch) for the GEMM epilogue
+__device__ __forceinline__ uint32_t pack2_rt(float lo, float hi, int fmt) {
+  return fmt == FMT_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack2_rt(uint32_t v, int fmt) {
+  return fmt == FMT_F16 ? __half22float2(*reinterpret_cast<__half2*>(&v))
+                        : make_float2(bf16lo_to_f32(v), bf16hi_to_f32(v));
+}
 
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose rows are
 // 128 bytes (tile base 1024 B aligned). This is the layout TMA SWIZZLE_128B writes and UMMA SW128 reads.

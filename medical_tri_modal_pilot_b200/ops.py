@@ -9,7 +9,19 @@ from ._lib import check, ptr, ptr_array, stream_ptr
 
 D = 256
 H = 4
-BF16 = torch.bfloat16
+ACT = torch.float16     # forward activations + 16-bit weight copies
+GRD = torch.float16     # gradient tensors (carry runtime.GRAD_SCALE)
+_FMT = {torch.float16: 0, torch.bfloat16: 1}
+
+
+def _fmt(t):
+    if t is None:
+        return 0
+    try:
+        return _FMT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"16-bit tensor (fp16 / bf16) required, got {t.dtype}") from None
+
 
 
 def _cuda_contig(t, dtype=None, name="tensor"):
@@ -56,7 +68,7 @@ def umse_embed(x, val4, tim4, Wfeat, out_dtype=torch.float32):
     n_tok = x.numel() // 3
     out = torch.empty(*x.shape[:-1], D, dtype=out_dtype, device=x.device)
     check(_lib.load().tmp_umse_embed_fwd(ptr(x), n_tok, ptr_array(val4), ptr_array(tim4), ptr(Wfeat), ptr(out),
-                                         int(out_dtype == BF16), stream_ptr()), "tmp_umse_embed_fwd")
+                                         int(out_dtype == ACT), stream_ptr()), "tmp_umse_embed_fwd")
     return out
 
 
@@ -93,16 +105,17 @@ def layernorm_bwd(dy, x, dres, gamma, dx, dgamma, dbeta, dx_drop=None, drop_p=0.
 
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
          salt=0, M=None):
-    """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K] bf16, Bw [N,K] bf16."""
+    """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16."""
     K = A.shape[-1]
     M = A.numel() // K if M is None else M
     N = Bw.shape[0]
     ld_out = (out if out is not None else out_f32).shape[-1]
-    check(_lib.load().tmp_gemm_bias_act_fwd(ptr(A), A.stride(-2) if A.dim() > 1 else K, ptr(Bw), Bw.stride(0), M, N, K,
-                                            float(alpha), ptr(bias), int(relu), ptr(gate),
-                                            gate.shape[-1] if gate is not None else 0, ptr(residual),
-                                            residual.shape[-1] if residual is not None else 0, float(drop_p), seed,
-                                            salt, ptr(out), ptr(out_f32), ld_out, stream_ptr()),
+    check(_lib.load().tmp_gemm_bias_act_fwd(ptr(A), _fmt(A), A.stride(-2) if A.dim() > 1 else K, ptr(Bw), _fmt(Bw),
+                                            Bw.stride(0), M, N, K, float(alpha), ptr(bias), int(relu), ptr(gate),
+                                            _fmt(gate), gate.shape[-1] if gate is not None else 0, ptr(residual),
+                                            _fmt(residual), residual.shape[-1] if residual is not None else 0,
+                                            float(drop_p), seed, salt, ptr(out), _fmt(out), ptr(out_f32), ld_out,
+                                            stream_ptr()),
           "tmp_gemm_bias_act_fwd")
 
 
@@ -110,7 +123,8 @@ def gemm_wgrad(dY, X, dW, M=None):
     """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]"""
     N, K = dY.shape[-1], X.shape[-1]
     M = dY.numel() // N if M is None else M
-    check(_lib.load().tmp_gemm_wgrad(ptr(dY), N, ptr(X), K, M, N, K, ptr(dW), stream_ptr()), "tmp_gemm_wgrad")
+    check(_lib.load().tmp_gemm_wgrad(ptr(dY), _fmt(dY), N, ptr(X), _fmt(X), K, M, N, K, ptr(dW), stream_ptr()),
+          "tmp_gemm_wgrad")
 
 
 def colsum(dY, out, M=None):

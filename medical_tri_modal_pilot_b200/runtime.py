@@ -1,0 +1,397 @@
+"""FusedPath -- host-side orchestration of the sm_100a kernels for the UMSE embedding + MBT fusion encoder of
+`tri_mbt_vsltcls` (reference tri_mbt_vsltcls.py:183-240 and mbt_encoder.py:696-784), forward and backward.
+
+Memory plan (all device buffers are allocated once and reused; nothing is allocated inside a step):
+  * every fused-path parameter lives in ONE flat fp32 buffer (`flat_w`, q/k/v of a block adjacent so QKV is a single
+    [768,256] GEMM operand); the nn.Parameters of the model are views into it, so optimizers / state_dict see the
+    reference's names and shapes. Gradients live in a second flat buffer with the same offsets (`flat_g`): the
+    wgrad / reduction kernels accumulate straight into it and `param.grad` are views -> the DDP allreduce walks
+    contiguous ranges of `flat_g` without any flatten/copy.
+  * fp16 copies of the parameters (`flat_w16`) and transposed copies of the GEMM weights (`flat_wT16`, dgrad
+    operands) are refreshed by two kernel launches per step.
+  * activations: stream m keeps X[l] (layer inputs, l = 0..n_layers) plus per-layer xn, qkv, O, h, hn, a, lse as
+    padded [B, T_m, *] fp16 tensors (gradient scratch is fp16 too, scaled by GRAD_SCALE) (T_v = 5+L, T_i = 5+49*n_img, T_t = 133: 4 bottleneck rows, CLS, tokens).
+    Key-padding is never materialised: kv_len[3,B] int32 stays on device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+D = 256
+FF = 1024
+ACT = ops.ACT    # fp16: forward activations and 16-bit weight copies
+GRD = ops.GRD    # fp16: gradient tensors, multiplied by GRAD_SCALE
+# Static power-of-two scale carried by every 16-bit gradient tensor (fp16 has 5 exponent bits; dS ~ P*dP/8 would sit
+# in the subnormal range unscaled). Backward kernels are linear in the incoming gradient, so the scale is applied
+# once to dL/dCLS and removed once from the flat fp32 gradient buffer. The reference itself runs fp16 autocast with
+# NO scaling at all (trainer.py:126,185-188: GradScaler commented out).
+GRAD_SCALE = 4096.0
+
+
+def _is_fused_param(name: str) -> bool:
+    if name.startswith(("ie_vslt.", "ie_time.", "ie_feat.", "txt_embedding.", "linear.")):
+        return True
+    if name.startswith("fusion_transformer.") and "layer_norms_after_concat" not in name:
+        return True
+    return False
+
+
+class _Block:
+    """Flat-buffer views of one (layer, modality) encoder block."""
+    __slots__ = ("ln1_g", "ln1_b", "wqkv", "bqkv", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2")
+
+
+class FusedPath:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.step = 0
+        self._ws_key = None
+        self.comm_hook = None     # optional callable(flat_g_range_start, flat_g_range_end) for DDP bucket overlap
+        self.skip_missing = True
+        self.grad_scale = GRAD_SCALE
+
+    # ------------------------------------------------------------------------------------------------------------
+    # parameter flattening
+    # ------------------------------------------------------------------------------------------------------------
+    def _layout(self):
+        """Ordered list of (state_dict name, param) such that tensors consumed together are adjacent."""
+        m = self.model
+        named = dict(m.named_parameters())
+        order = []
+        for p in ("ie_vslt", "ie_time"):
+            order += [f"{p}.0.weight", f"{p}.0.bias", f"{p}.1.weight", f"{p}.1.bias"]
+        order += ["ie_feat.weight"]
+        F = "fusion_transformer"
+        order += [f"{F}.cls_token_per_modality.{k}" for k in range(3)]
+        order += [f"{F}.bottlenecks"]
+        for k in range(3):
+            order += [f"{F}.layer_norms_in.{k}.weight", f"{F}.layer_norms_in.{k}.bias"]
+        order += ["txt_embedding.weight", "txt_embedding.bias", "linear.weight", "linear.bias"]
+        for l in range(m.num_layers):
+            for k in range(3):
+                p = f"{F}.layer_stacks.{l}.{k}"
+                order += [f"{p}.attention_prenorm.gamma", f"{p}.attention_prenorm.beta"]
+                order += [f"{p}.self_attention.{q}_proj.linear.weight" for q in ("query", "key", "value")]
+                order += [f"{p}.self_attention.{q}_proj.linear.bias" for q in ("query", "key", "value")]
+                order += [f"{p}.feed_forward_prenorm.gamma", f"{p}.feed_forward_prenorm.beta"]
+                order += [f"{p}.feed_forward.w_1.weight", f"{p}.feed_forward.w_1.bias",
+                          f"{p}.feed_forward.w_2.weight", f"{p}.feed_forward.w_2.bias"]
+        fused = {n for n in named if _is_fused_param(n)}
+        assert fused == set(order), sorted(fused ^ set(order))
+        return [(n, named[n]) for n in order]
+
+    def _ensure_params(self, device):
+        m = self.model
+        first = next(iter(m.ie_vslt.parameters()))
+        if self.device == device and getattr(self, "_sig", None) == first.data_ptr():
+            return
+        if device.type != "cuda":
+            raise RuntimeError("FusedPath needs a CUDA device")
+        layout = self._layout()
+        offs, total = {}, 0
+        for n, p in layout:
+            offs[n] = total
+            total += p.numel()
+        assert all(o % 256 == 0 for o in offs.values())
+        flat_w = torch.empty(total, dtype=torch.float32, device=device)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self.gviews = {}
+        with torch.no_grad():
+            for n, p in layout:
+                v = flat_w[offs[n]: offs[n] + p.numel()].view(p.shape)
+                v.copy_(p.data.to(device))
+                p.data = v
+                self.gviews[n] = flat_g[offs[n]: offs[n] + p.numel()].view(p.shape)
+        self.layout, self.offs, self.total = layout, offs, total
+        self.flat_w, self.flat_g = flat_w, flat_g
+        self.flat_w16 = torch.empty(total, dtype=ACT, device=device)
+        W = lambda n, *shape: flat_w[offs[n]:].as_strided(shape, _contig_strides(shape))
+        G = lambda n, *shape: flat_g[offs[n]:].as_strided(shape, _contig_strides(shape))
+        H16 = lambda n, *shape: self.flat_w16[offs[n]:].as_strided(shape, _contig_strides(shape))
+        self.W, self.G, self.H16 = W, G, H16
+        # transposed bf16 copies of the GEMM weights used by dgrad
+        F = "fusion_transformer"
+        t_total = m.num_layers * 3 * (768 * 256 + 1024 * 256 * 2)
+        self.flat_wT16 = torch.empty(t_total, dtype=ACT, device=device)
+        descs = np.zeros(1 + m.num_layers * 9, dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("dst_t", "<u8"),
+                                                               ("R", "<i4"), ("C", "<i4")]))
+        descs[0] = (flat_w.data_ptr(), self.flat_w16.data_ptr(), 0, total // 256, 256)
+        self.wT = {}
+        t_off, k = 0, 1
+        for l in range(m.num_layers):
+            for s in range(3):
+                p = f"{F}.layer_stacks.{l}.{s}"
+                for key, name, R, C in (("qkv", f"{p}.self_attention.query_proj.linear.weight", 768, 256),
+                                        ("w1", f"{p}.feed_forward.w_1.weight", 1024, 256),
+                                        ("w2", f"{p}.feed_forward.w_2.weight", 256, 1024)):
+                    dst_t = self.flat_wT16[t_off: t_off + R * C].view(C, R)
+                    self.wT[(l, s, key)] = dst_t
+                    descs[k] = (flat_w.data_ptr() + 4 * offs[name], 0, dst_t.data_ptr(), R, C)
+                    t_off += R * C
+                    k += 1
+        self.n_desc = k
+        self.cast_descs = torch.from_numpy(descs.view(np.uint8).copy()).to(device)
+        self.blocks = {}
+        for l in range(m.num_layers):
+            for s in range(3):
+                self.blocks[(l, s)] = self._block_views(l, s)
+        self.device = device
+        self._sig = first.data_ptr()
+        self._trigger = torch.zeros(1, device=device, requires_grad=True)
+
+    def _block_views(self, l, s):
+        p = f"fusion_transformer.layer_stacks.{l}.{s}"
+        names = dict(ln1_g=f"{p}.attention_prenorm.gamma", ln1_b=f"{p}.attention_prenorm.beta",
+                     wqkv=f"{p}.self_attention.query_proj.linear.weight",
+                     bqkv=f"{p}.self_attention.query_proj.linear.bias",
+                     ln2_g=f"{p}.feed_forward_prenorm.gamma", ln2_b=f"{p}.feed_forward_prenorm.beta",
+                     w1=f"{p}.feed_forward.w_1.weight", b1=f"{p}.feed_forward.w_1.bias",
+                     w2=f"{p}.feed_forward.w_2.weight", b2=f"{p}.feed_forward.w_2.bias")
+        shapes = dict(ln1_g=(D,), ln1_b=(D,), wqkv=(768, D), bqkv=(768,), ln2_g=(D,), ln2_b=(D,), w1=(FF, D),
+                      b1=(FF,), w2=(D, FF), b2=(D,))
+        w, g, h = _Block(), _Block(), _Block()
+        for k, n in names.items():
+            setattr(w, k, self.W(n, *shapes[k]))
+            setattr(g, k, self.G(n, *shapes[k]))
+            setattr(h, k, self.H16(n, *shapes[k]))
+        return w, g, h
+
+    # ------------------------------------------------------------------------------------------------------------
+    # workspace
+    # ------------------------------------------------------------------------------------------------------------
+    def _ensure_workspace(self, B, L, n_img):
+        key = (B, L, n_img)
+        if self._ws_key == key:
+            return
+        dev = self.device
+        NL = self.model.num_layers
+        T = [5 + L, 5 + 49 * n_img, 5 + 128]
+        self.T = T
+        ws = []
+        for s in range(3):
+            M = B * T[s]
+            Tl = ops.lse_len(T[s])
+            nl_s = NL if (s == 0 or not self.model.vsltonly) else NL - 1      # img/txt skip the last layer
+            e = lambda *shape, dt=ACT: torch.empty(*shape, dtype=dt, device=dev)
+            g = lambda *shape: torch.empty(*shape, dtype=GRD, device=dev)
+            st = {
+                "M": M, "T": T[s], "Tl": Tl, "n_layers": nl_s,
+                "X": [e(B, T[s], D) for _ in range(nl_s + 1)],
+                "xn": [e(M, D) for _ in range(nl_s)], "qkv": [e(M, 768) for _ in range(nl_s)],
+                "O": [e(M, D) for _ in range(nl_s)], "h": [e(M, D) for _ in range(nl_s)],
+                "hn": [e(M, D) for _ in range(nl_s)], "a": [e(M, FF) for _ in range(nl_s)],
+                "lse": [e(B, 4, Tl, dt=torch.float32) for _ in range(nl_s)],
+                # backward scratch (reused by every layer of the stream)
+                "g_y": g(B, T[s], D), "g_x": g(B, T[s], D), "g_yd": g(B, T[s], D), "g_a": g(M, FF), "g_hn": g(M, D),
+                "g_h": g(M, D), "g_qkv": g(M, 768), "g_xn": g(M, D),
+                "dq_acc": e(M, D, dt=torch.float32), "delta": e(B, 4, Tl, dt=torch.float32),
+            }
+            ws.append(st)
+        self.ws = ws
+        self.proj = [None, torch.empty(B * 49 * n_img, D, dtype=ACT, device=dev),
+                     torch.empty(B * 128, D, dtype=ACT, device=dev)]
+        self.g_proj = [None, torch.empty(B * 49 * n_img, D, dtype=GRD, device=dev),
+                       torch.empty(B * 128, D, dtype=GRD, device=dev)]
+        self._ws_key = key
+
+    # ------------------------------------------------------------------------------------------------------------
+    def __call__(self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing):
+        self._ensure_params(x.device)
+        return _FusedFn.apply(self._trigger, self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time,
+                              missing)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _branch(self, prefix, grads=False):
+        src = self.G if grads else self.W
+        return [src(f"{prefix}.0.weight", D), src(f"{prefix}.0.bias", D), src(f"{prefix}.1.weight", D),
+                src(f"{prefix}.1.bias", D)]
+
+    def _prologue_args(self, s, ctx):
+        m = self.model
+        F = "fusion_transformer"
+        B = ctx["B"]
+        n = self.T[s] - 5
+        pe = m.fusion_transformer.positional_encoding.pe[0] if s == 2 else None
+        common = dict(tim4=self._branch("ie_time"), Wfeat=self.W("ie_feat.weight", 20, D),
+                      cls=self.W(f"{F}.cls_token_per_modality.{s}", D), bottlenecks=self.W(f"{F}.bottlenecks", 4, D),
+                      ln_g=self.W(f"{F}.layer_norms_in.{s}.weight", D), ln_b=self.W(f"{F}.layer_norms_in.{s}.bias", D),
+                      pe=pe, drop_p=ctx["p"], seed=ctx["seed"], salt=1000 + s)
+        if s == 0:
+            return dict(kind=0, B=B, n=n, x=ctx["x"], val4=self._branch("ie_vslt"), proj=None, times=None, n_slots=0,
+                        feat_id=0, **common)
+        times = ctx["img_time"] if s == 1 else ctx["txt_time"]
+        return dict(kind=1, B=B, n=n, x=None, val4=None, proj=self.proj[s], times=times,
+                    n_slots=(ctx["n_img"] if s == 1 else 1), feat_id=(18 if s == 1 else 19), **common)
+
+    def forward(self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing, training):
+        m = self.model
+        B, L = x.shape[0], x.shape[1]
+        n_img = 3 if m.multiimages == 1 else 1
+        self._ensure_workspace(B, L, n_img)
+        NL = m.num_layers
+        p = m.dropout if training else 0.0
+        self.step += 1
+        seed = (int(torch.initial_seed()) * 1000003 + self.step) & 0x7FFFFFFF
+        ctx = dict(B=B, L=L, n_img=n_img, p=p, seed=seed)
+        ctx["x"] = x.float().contiguous()
+        ctx["img_time"] = img_time.float().reshape(B, n_img).contiguous()
+        ctx["txt_time"] = txt_time.float().contiguous()
+        ctx["missing"] = missing.to(torch.long).contiguous()
+        T = self.T
+        ctx["kv_len"] = ops.build_lengths(input_lengths.to(torch.long).contiguous(), txt_lengths.to(torch.long).contiguous(),
+                                          ctx["img_time"], n_img, m.multiimages, ctx["missing"], int(self.skip_missing),
+                                          T[0], T[1], T[2])
+        # refresh bf16 (+ transposed) parameter copies
+        ops.cast_weights(self.cast_descs, 1, self.total // 256, 256)              # flat fp32 -> bf16
+        ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
+        # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
+        ctx["txts16"] = txts.reshape(B * 128, 768).to(ACT).contiguous()
+        ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(ACT).contiguous()
+        ops.gemm(ctx["img16"], self.H16("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
+        ops.gemm(ctx["txts16"], self.H16("txt_embedding.weight", D, 768), out=self.proj[2],
+                 bias=self.W("txt_embedding.bias", D))
+        for s in range(3):
+            ops.stream_prologue_fwd(X0=self.ws[s]["X"][0], **self._prologue_args(s, ctx))
+        for l in range(NL):
+            last = m.vsltonly == 1 and l == NL - 1
+            for s in ([0] if last else [0, 1, 2]):
+                self._layer_fwd(l, s, ctx)
+            if l == NL - 1:
+                break
+            ops.bottleneck_mix_fwd(self.ws[0]["X"][l + 1], self.ws[1]["X"][l + 1], self.ws[2]["X"][l + 1], ctx["missing"])
+        self.ctx = ctx
+        return self.ws[0]["X"][NL][:, 4, :].float()
+
+    def _layer_fwd(self, l, s, ctx):
+        st = self.ws[s]
+        w, _, h16 = self.blocks[(l, s)]
+        B, T, M = ctx["B"], st["T"], st["M"]
+        p, seed = ctx["p"], ctx["seed"]
+        x = st["X"][l]
+        ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, st["xn"][l])
+        ops.gemm(st["xn"][l], h16.wqkv, out=st["qkv"][l], bias=w.bqkv)
+        ops.attn_fwd(st["qkv"][l], ctx["kv_len"][s], B, T, st["O"][l], st["lse"][l])
+        ops.layernorm_fwd(x, w.ln2_g, w.ln2_b, st["hn"][l], add=st["O"][l], sum_out=st["h"][l])
+        ops.gemm(st["hn"][l], h16.w1, out=st["a"][l], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3 + s) * 4 + 1)
+        ops.gemm(st["a"][l], h16.w2, out=st["X"][l + 1].view(M, D), bias=w.b2, residual=st["h"][l], drop_p=p,
+                 seed=seed, salt=(l * 3 + s) * 4 + 2)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def backward(self, d_cls):
+        m = self.model
+        ctx = self.ctx
+        NL = m.num_layers
+        B, p, seed = ctx["B"], ctx["p"], ctx["seed"]
+        self.flat_g.zero_()
+        for s in range(3):
+            self.ws[s]["g_y"].zero_()
+        self.ws[0]["g_y"][:, 4, :] = (d_cls * self.grad_scale).to(GRD)
+        for l in range(NL - 1, -1, -1):
+            last = m.vsltonly == 1 and l == NL - 1
+            streams = [0] if last else [0, 1, 2]
+            for s in streams:
+                self._layer_bwd(l, s, ctx)
+            # after _layer_bwd, g_y of each processed stream holds dX[l] (gradient wrt the layer input)
+            if l > 0:
+                upper_has_it = 0 if last else 1
+                ops.bottleneck_mix_bwd(self.ws[0]["g_y"], self.ws[1]["g_y"], self.ws[2]["g_y"], upper_has_it,
+                                       ctx["missing"])
+            if self.comm_hook is not None:
+                self.comm_hook(l)
+        # prologue + projections
+        F = "fusion_transformer"
+        for s in range(3):
+            a = self._prologue_args(s, ctx)
+            ops.stream_prologue_bwd(dX0=self.ws[s]["g_y"], g_val=self.G("ie_vslt.0.weight", 4, D) if s == 0 else None,
+                                    g_tim=self.G("ie_time.0.weight", 4, D), g_feat=self.G("ie_feat.weight", 20, D),
+                                    g_cls=self.G(f"{F}.cls_token_per_modality.{s}", D),
+                                    g_bott=self.G(f"{F}.bottlenecks", 4, D),
+                                    g_ln=self.G(f"{F}.layer_norms_in.{s}.weight", 2, D),
+                                    dproj=self.g_proj[s], **a)
+        ops.gemm_wgrad(self.g_proj[1], ctx["img16"], self.G("linear.weight", D, 768))
+        ops.colsum(self.g_proj[1], self.G("linear.bias", D))
+        ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768))
+        ops.colsum(self.g_proj[2], self.G("txt_embedding.bias", D))
+        self.flat_g.mul_(1.0 / self.grad_scale)
+        if self.comm_hook is not None:
+            self.comm_hook(-1)
+        self._publish_grads()
+
+    def _layer_bwd(self, l, s, ctx):
+        st = self.ws[s]
+        w, g, h16 = self.blocks[(l, s)]
+        B, T, M = ctx["B"], st["T"], st["M"]
+        p, seed = ctx["p"], ctx["seed"]
+        gy = st["g_y"].view(M, D)
+        if p > 0:
+            ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2)
+            gyd = st["g_yd"].view(M, D)
+        else:
+            gyd = gy
+        scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+        # FFN2: y = h + drop2(a W2^T + b2)
+        ops.gemm(gyd, self.wT[(l, s, "w2")], out=st["g_a"], gate=st["a"][l], alpha=scale)
+        ops.gemm_wgrad(gyd, st["a"][l], g.w2)
+        ops.colsum(gyd, g.b2)
+        # FFN1: a = drop1(relu(hn W1^T + b1))
+        ops.gemm(st["g_a"], self.wT[(l, s, "w1")], out=st["g_hn"])
+        ops.gemm_wgrad(st["g_a"], st["hn"][l], g.w1)
+        ops.colsum(st["g_a"], g.b1)
+        # LN2 (+ residual): h = x + O
+        ops.layernorm_bwd(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b)
+        # attention
+        ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"],
+                     st["dq_acc"], st["g_qkv"])
+        ops.gemm(st["g_qkv"], self.wT[(l, s, "qkv")], out=st["g_xn"])
+        ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv)
+        ops.colsum(st["g_qkv"], g.bqkv)
+        # LN1 (+ residual)
+        ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
+        st["g_y"], st["g_x"] = st["g_x"], st["g_y"]
+
+    def _publish_grads(self):
+        """param.grad <- view of flat_g (accumulates if the caller kept older gradients)."""
+        for n, prm in self.layout:
+            gv = self.gviews[n]
+            if prm.grad is None:
+                prm.grad = gv
+            elif prm.grad.data_ptr() != gv.data_ptr():
+                prm.grad.add_(gv)
+
+    # ranges of flat_g per backward stage (used by the DDP bucket plan)
+    def grad_range_of_layer(self, l):
+        F = "fusion_transformer"
+        if l >= 0:
+            a = self.offs[f"{F}.layer_stacks.{l}.0.attention_prenorm.gamma"]
+            nxt = f"{F}.layer_stacks.{l + 1}.0.attention_prenorm.gamma"
+            b = self.offs[nxt] if nxt in self.offs else self.total
+            return a, b
+        return 0, self.offs[f"{F}.layer_stacks.0.0.attention_prenorm.gamma"]
+
+
+def _contig_strides(shape):
+    st, acc = [], 1
+    for d in reversed(shape):
+        st.append(acc)
+        acc *= d
+    return tuple(reversed(st))
+
+
+class _FusedFn(torch.autograd.Function):
+    """Autograd boundary: inputs are data tensors (no gradient) + a dummy trigger; the parameters' gradients are
+    produced by the kernels directly into the flat gradient buffer (see FusedPath._publish_grads)."""
+
+    @staticmethod
+    def forward(ctx, trigger, fp, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing):
+        ctx.fp = fp
+        return fp.forward(x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing,
+                          training=fp.model.training)
+
+    @staticmethod
+    def backward(ctx, d_cls):
+        ctx.fp.backward(d_cls.contiguous())
+        return (torch.zeros(1, device=d_cls.device),) + (None,) * 9

@@ -19,6 +19,10 @@ sys.path.insert(0, ROOT)
 CASES = ["lengths", "umse", "layernorm", "prologue", "mix_colsum", "gemm", "wgrad", "attn_fwd", "attn_bwd"]
 
 
+import torch as _t
+ACT, GRD = _t.float16, _t.float16
+
+
 def _err(a, b):
     import torch
     a = a.float(); b = b.float()
@@ -79,13 +83,13 @@ def case_umse():
     E = ops.umse_embed(x, val4, tim4, W, torch.float32)
     ref = _branch_ref(x[:, 1], *val4) + _branch_ref(x[:, 0], *tim4) + W[x[:, 2].int().long()]
     out = {"fp32": _err(E, ref)}
-    Eb = ops.umse_embed(x, val4, tim4, W, torch.bfloat16)
-    out["bf16"] = _err(Eb, ref)
+    Eb = ops.umse_embed(x, val4, tim4, W, ACT)
+    out["fp16"] = _err(Eb, ref)
     # gather bit-exactness: kill both LN-ReLU branches (gamma = beta = 0 -> relu(0) = 0)
     z4 = [val4[0], val4[1], torch.zeros(256, device=dev), torch.zeros(256, device=dev)]
     Eg = ops.umse_embed(x, z4, z4, W, torch.float32)
     out["gather_bit_exact"] = bool(torch.equal(Eg, W[x[:, 2].int().long()]))
-    out["ok"] = out["fp32"]["max_abs"] < 2e-5 and out["bf16"]["rel_to_max"] < 1e-2 and out["gather_bit_exact"]
+    out["ok"] = out["fp32"]["max_abs"] < 2e-5 and out["fp16"]["rel_to_max"] < 2e-3 and out["gather_bit_exact"]
     return out
 
 
@@ -101,8 +105,8 @@ def case_layernorm():
     torch.manual_seed(1)
     dev = "cuda"
     rows = 3001
-    x = torch.randn(rows, 256, device=dev).bfloat16()
-    o = torch.randn(rows, 256, device=dev).bfloat16()
+    x = torch.randn(rows, 256, device=dev).half()
+    o = torch.randn(rows, 256, device=dev).half()
     g = (1 + 0.1 * torch.randn(256, device=dev)); b = 0.1 * torch.randn(256, device=dev)
     y = torch.empty_like(x)
     ops.layernorm_fwd(x, g, b, y)
@@ -114,15 +118,15 @@ def case_layernorm():
     res["add_fwd"] = _err(y2, _ln_ref(h.float(), g, b))
     # backward
     xf = x.float().requires_grad_(True); gp = g.clone().requires_grad_(True); bp = b.clone().requires_grad_(True)
-    dy = torch.randn(rows, 256, device=dev).bfloat16()
-    dres = torch.randn(rows, 256, device=dev).bfloat16()
+    dy = torch.randn(rows, 256, device=dev).to(GRD)
+    dres = torch.randn(rows, 256, device=dev).to(GRD)
     _ln_ref(xf, gp, bp).backward(dy.float())
-    dx = torch.empty_like(x); dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
+    dx = torch.empty_like(dy); dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
     ops.layernorm_bwd(dy, x, dres, g, dx, dg, db)
     res["bwd_dx"] = _err(dx, xf.grad + dres.float())
     res["bwd_dg"] = _err(dg, gp.grad)
     res["bwd_db"] = _err(db, bp.grad)
-    dxd = torch.empty_like(x); dx2 = torch.empty_like(x)
+    dxd = torch.empty_like(dy); dx2 = torch.empty_like(dy)
     dg.zero_(); db.zero_()
     ops.layernorm_bwd(dy, x, dres, g, dx2, dg, db, dx_drop=dxd, drop_p=0.1, seed=7, salt=3)
     keep = (dxd != 0).float().mean().item()
@@ -161,7 +165,7 @@ def case_prologue():
             proj = times = None; n_slots = 0; feat = 0; use_pe = None
         else:
             x = None
-            proj = torch.randn(B * n, 256, device=dev).bfloat16()
+            proj = torch.randn(B * n, 256, device=dev).half()
             projf = proj.float().requires_grad_(True)
             times = -torch.rand(B, 3, device=dev) * 24
             n_slots = 3; feat = 18; use_pe = pe
@@ -173,16 +177,16 @@ def case_prologue():
         if use_pe is not None:
             y = y + use_pe[: n + 1]
         ref = torch.cat([bo.expand(B, 4, 256), y], 1)
-        X0 = torch.empty(B, T, 256, device=dev, dtype=torch.bfloat16)
+        X0 = torch.empty(B, T, 256, device=dev, dtype=ACT)
         ops.stream_prologue_fwd(kind, B, n, x, val4 if kind == 0 else None, proj, times, n_slots, feat, tim4, W, cls,
                                 bott, lg, lb, use_pe, 0.0, 0, 0, X0)
         res[f"fwd{kind}"] = _err(X0, ref)
-        dX0 = torch.randn(B, T, 256, device=dev).bfloat16()
+        dX0 = torch.randn(B, T, 256, device=dev).to(GRD)
         ref.backward(dX0.float())
         g_val = torch.zeros(4, 256, device=dev); g_tim = torch.zeros(4, 256, device=dev)
         g_feat = torch.zeros(20, 256, device=dev); g_cls = torch.zeros(256, device=dev)
         g_bott = torch.zeros(4, 256, device=dev); g_ln = torch.zeros(2, 256, device=dev)
-        dproj = torch.empty(B * n, 256, device=dev, dtype=torch.bfloat16) if kind == 1 else None
+        dproj = torch.empty(B * n, 256, device=dev, dtype=GRD) if kind == 1 else None
         ops.stream_prologue_bwd(kind, B, n, x, val4 if kind == 0 else None, proj, times, n_slots, feat, tim4, W, cls,
                                 bott, lg, lb, use_pe, 0.0, 0, 0, dX0, g_val if kind == 0 else None, g_tim, g_feat,
                                 g_cls, g_bott, g_ln, dproj)
@@ -205,7 +209,7 @@ def case_mix_colsum():
     torch.manual_seed(3)
     dev = "cuda"
     B = 9
-    Ys = [torch.randn(B, T, 256, device=dev).bfloat16() for T in (45, 152, 133)]
+    Ys = [torch.randn(B, T, 256, device=dev).half() for T in (45, 152, 133)]
     missing = torch.tensor([0, 1, 2, 3, 0, 1, 2, 3, 0], device=dev)
     bo = torch.stack([y[:, :4].float() for y in Ys])
     tri = bo.mean(0); vi = bo[:2].mean(0); vt = (bo[0] + bo[2]) / 2
@@ -216,7 +220,7 @@ def case_mix_colsum():
            "mix_rest_untouched": all(torch.equal(a[:, 4:], b[:, 4:]) for a, b in zip(Yc, Ys))}
     # bwd
     w = torch.tensor([[1 / 3, 1 / 3, 1 / 3], [.5, .5, 0], [.5, 0, .5], [1, 0, 0]], device=dev)[missing]  # [B,3]
-    dY = [torch.randn(B, T, 256, device=dev).bfloat16() for T in (45, 152, 133)]
+    dY = [torch.randn(B, T, 256, device=dev).to(GRD) for T in (45, 152, 133)]
     g = sum(d[:, :4].float() for d in dY)
     dYc = [d.clone() for d in dY]
     ops.bottleneck_mix_bwd(*dYc, 1, missing)
@@ -227,12 +231,12 @@ def case_mix_colsum():
                                for m in range(3))
     for N in (256, 768, 1024):
         M = 4097
-        dy = torch.randn(M, N, device=dev).bfloat16()
+        dy = torch.randn(M, N, device=dev).to(GRD)
         out = torch.zeros(N, device=dev)
         ops.colsum(dy, out)
         res[f"colsum{N}"] = _err(out, dy.float().sum(0))["rel_to_max"]
     # dropout_apply statistics + determinism
-    a = torch.ones(1 << 20, device=dev).bfloat16(); o1 = torch.empty_like(a); o2 = torch.empty_like(a)
+    a = torch.ones(1 << 20, device=dev).to(GRD); o1 = torch.empty_like(a); o2 = torch.empty_like(a)
     ops.dropout_apply(a, o1, 0.1, 11, 5); ops.dropout_apply(a, o2, 0.1, 11, 5)
     res["drop_keep"] = (o1 != 0).float().mean().item(); res["drop_det"] = bool(torch.equal(o1, o2))
     res["ok"] = res["mix_fwd"] < 1e-2 and res["mix_bwd"] < 1e-2 and res["mix_bwd_vonly"] < 1e-2 and \
@@ -247,35 +251,38 @@ def case_gemm():
     torch.manual_seed(4)
     dev = "cuda"
     res = {}
-    for (M, N, K) in [(128, 128, 64), (300, 256, 256), (4096, 768, 256), (1000, 1024, 256), (1001, 256, 1024),
-                      (20000, 256, 768)]:
-        A = torch.randn(M, K, device=dev).bfloat16()
-        Bw = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
-        bias = torch.randn(N, device=dev)
-        ref = A.float() @ Bw.float().t()
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        ops.gemm(A, Bw, out=out)
-        res[f"plain_{M}x{N}x{K}"] = _err(out, ref)
-        ops.gemm(A, Bw, out=out, bias=bias, relu=True)
-        res[f"bias_relu_{M}x{N}x{K}"] = _err(out, torch.relu(ref + bias))
-        resid = torch.randn(M, N, device=dev).bfloat16()
-        of = torch.empty(M, N, device=dev)
-        ops.gemm(A, Bw, out=out, out_f32=of, bias=bias, residual=resid)
-        res[f"bias_res_{M}x{N}x{K}"] = _err(out, ref + bias + resid.float())
-        res[f"f32out_{M}x{N}x{K}"] = _err(of, ref + bias + resid.float())
-        gate = torch.randn(M, N, device=dev).bfloat16()
-        ops.gemm(A, Bw, out=out, gate=gate, alpha=0.5)
-        res[f"gate_{M}x{N}x{K}"] = _err(out, 0.5 * ref * (gate.float() > 0))
+    # (A dtype, B dtype, out dtype): the product uses fp16 everywhere; bf16 x bf16 stays supported by the kernel
+    for tag, (da, db_, do) in {"fwd": (ACT, ACT, ACT), "bf16": (_t.bfloat16,) * 3}.items():
+        for (M, N, K) in [(128, 128, 64), (300, 256, 256), (4096, 768, 256), (1000, 1024, 256), (1001, 256, 1024),
+                          (20000, 256, 768)]:
+            A = torch.randn(M, K, device=dev).to(da)
+            Bw = (torch.randn(N, K, device=dev) / K ** 0.5).to(db_)
+            bias = torch.randn(N, device=dev)
+            ref = A.float() @ Bw.float().t()
+            out = torch.empty(M, N, device=dev, dtype=do)
+            ops.gemm(A, Bw, out=out)
+            res[f"{tag}_plain_{M}x{N}x{K}"] = _err(out, ref)
+            ops.gemm(A, Bw, out=out, bias=bias, relu=True)
+            res[f"{tag}_bias_relu_{M}x{N}x{K}"] = _err(out, torch.relu(ref + bias))
+            resid = torch.randn(M, N, device=dev).to(ACT)
+            of = torch.empty(M, N, device=dev)
+            ops.gemm(A, Bw, out=out, out_f32=of, bias=bias, residual=resid)
+            res[f"{tag}_bias_res_{M}x{N}x{K}"] = _err(out, ref + bias + resid.float())
+            res[f"{tag}_f32out_{M}x{N}x{K}"] = _err(of, ref + bias + resid.float())
+            gate = torch.randn(M, N, device=dev).to(ACT)
+            ops.gemm(A, Bw, out=out, gate=gate, alpha=0.5)
+            res[f"{tag}_gate_{M}x{N}x{K}"] = _err(out, 0.5 * ref * (gate.float() > 0))
     M, N, K = 2048, 1024, 256
-    A = torch.randn(M, K, device=dev).bfloat16(); Bw = (torch.randn(N, K, device=dev) / 16).bfloat16()
-    o0 = torch.empty(M, N, device=dev, dtype=torch.bfloat16); o1 = torch.empty_like(o0); o2 = torch.empty_like(o0)
+    A = torch.randn(M, K, device=dev).half(); Bw = (torch.randn(N, K, device=dev) / 16).half()
+    o0 = torch.empty(M, N, device=dev, dtype=ACT); o1 = torch.empty_like(o0); o2 = torch.empty_like(o0)
     ops.gemm(A, Bw, out=o0)
     ops.gemm(A, Bw, out=o1, drop_p=0.1, seed=3, salt=9); ops.gemm(A, Bw, out=o2, drop_p=0.1, seed=3, salt=9)
     kept = o1 != 0
     res["drop_keep"] = kept.float().mean().item()
     res["drop_det"] = bool(torch.equal(o1, o2))
     res["drop_scale"] = _err(o1[kept], (o0.float() / 0.9)[kept])
-    res["ok"] = all(v["rel_to_max"] < 1.5e-2 and v["finite"] for k, v in res.items() if isinstance(v, dict)) and \
+    tol = lambda k: 2.5e-3 if k.startswith("fwd") else 1.5e-2
+    res["ok"] = all(v["rel_to_max"] < tol(k) and v["finite"] for k, v in res.items() if isinstance(v, dict)) and \
         abs(res["drop_keep"] - 0.9) < 5e-3 and res["drop_det"]
     return res
 
@@ -287,8 +294,8 @@ def case_wgrad():
     dev = "cuda"
     res = {}
     for (M, N, K) in [(64, 128, 128), (1000, 256, 1024), (5000, 768, 256), (4097, 1024, 256), (333, 256, 768)]:
-        dY = torch.randn(M, N, device=dev).bfloat16()
-        X = torch.randn(M, K, device=dev).bfloat16()
+        dY = torch.randn(M, N, device=dev).to(GRD)
+        X = torch.randn(M, K, device=dev).half()
         dW = torch.zeros(N, K, device=dev)
         ops.gemm_wgrad(dY, X, dW)
         res[f"{M}x{N}x{K}"] = _err(dW, dY.float().t() @ X.float())
@@ -313,16 +320,16 @@ def case_attn_fwd():
     dev = "cuda"
     res = {}
     for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (2, 54, [54, 54])]:
-        qkv = (torch.randn(B * T, 768, device=dev) * 1.5).bfloat16()
+        qkv = (torch.randn(B * T, 768, device=dev) * 1.5).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
-        O = torch.full((B * T, 256), 7.0, device=dev, dtype=torch.bfloat16)
+        O = torch.full((B * T, 256), 7.0, device=dev, dtype=ACT)
         lse = torch.zeros(B, 4, ops.lse_len(T), device=dev)
         ops.attn_fwd(qkv, kv, B, T, O, lse)
         ref = _attn_ref(qkv, kv, B, T)
         live = (torch.arange(T, device=dev)[None, :] < kv[:, None])  # only live query rows are defined by parity
         e = _err(O.view(B, T, 256)[live], ref[live])
         res[f"B{B}_T{T}"] = e
-    res["ok"] = all(v["rel_to_max"] < 2e-2 and v["finite"] for v in res.values() if isinstance(v, dict))
+    res["ok"] = all(v["rel_to_max"] < 3e-3 and v["finite"] for v in res.values() if isinstance(v, dict))
     return res
 
 
@@ -333,26 +340,26 @@ def case_attn_bwd():
     dev = "cuda"
     res = {}
     for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600])]:
-        qkv = (torch.randn(B * T, 768, device=dev)).bfloat16()
+        qkv = (torch.randn(B * T, 768, device=dev)).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
         live = (torch.arange(T, device=dev)[None, :] < kv[:, None])
         qf = qkv.float().requires_grad_(True)
         ref = _attn_ref(qf, kv, B, T)
-        dO = torch.randn(B, T, 256, device=dev).bfloat16()
+        dO = torch.randn(B, T, 256, device=dev).to(GRD)
         dO = (dO * live[..., None]).contiguous()  # padding query rows carry exactly zero gradient
         ref.backward(dO.float())
-        O = torch.empty(B * T, 256, device=dev, dtype=torch.bfloat16)
+        O = torch.empty(B * T, 256, device=dev, dtype=ACT)
         Tl = ops.lse_len(T)
         lse = torch.zeros(B, 4, Tl, device=dev)
         ops.attn_fwd(qkv, kv, B, T, O, lse)
         delta = torch.empty(B, 4, Tl, device=dev); dq_acc = torch.empty(B * T, 256, device=dev)
-        dQKV = torch.full((B * T, 768), 3.0, device=dev, dtype=torch.bfloat16)
+        dQKV = torch.full((B * T, 768), 3.0, device=dev, dtype=GRD)
         ops.attn_bwd(qkv, O, dO.view(B * T, 256), kv, B, T, lse, delta, dq_acc, dQKV)
         g = qf.grad.view(B * T, 768)
         res[f"dQ_B{B}_T{T}"] = _err(dQKV[:, :256], g[:, :256])
         res[f"dK_B{B}_T{T}"] = _err(dQKV[:, 256:512], g[:, 256:512])
         res[f"dV_B{B}_T{T}"] = _err(dQKV[:, 512:], g[:, 512:])
-    res["ok"] = all(v["rel_to_max"] < 3e-2 and v["finite"] for v in res.values() if isinstance(v, dict))
+    res["ok"] = all(v["rel_to_max"] < 5e-3 and v["finite"] for v in res.values() if isinstance(v, dict))
     return res
 
 

@@ -23,14 +23,17 @@ sys.path.insert(0, ROOT)
 
 CASES = {
     # name: (n_layers, multiimages, B, L, batch seed, weight seed, missing_mode)
-    "tri_nl2_multi_B6_L40": (2, 1, 6, 40, 11, 1, "mixed"),
-    "tri_nl2_single_B5_L33": (2, 0, 5, 33, 12, 2, "mixed"),
-    "tri_nl3_multi_B4_L150": (3, 1, 4, 150, 13, 3, "none"),
+    # batches are >= 16 so that the head's BatchNorm1d (batch statistics) is well conditioned, as at the real B=64
+    "tri_nl2_multi_B32_L40": (2, 1, 32, 40, 11, 1, "mixed"),
+    "tri_nl2_single_B24_L33": (2, 0, 24, 33, 12, 2, "mixed"),
+    "tri_nl3_multi_B16_L150": (3, 1, 16, 150, 13, 3, "none"),
 }
 
 
 def import_reference():
-    sys.path.insert(0, REF)
+    # The repo ships its own `builder/` drop-in shim (a regular package), which would shadow the reference's
+    # namespace package `builder/` whatever the sys.path order: keep the repo root off sys.path while importing.
+    sys.path[:] = [REF] + [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
     sys.argv = ["x", "--model", "tri_mbt_vsltcls", "--input-types", "vslt_img_txt", "--vslt-type", "TIE",
                 "--imgtxt-time", "1", "--mbt-only-vslt", "1", "--multiimages", "1", "--transformer-num-layers", "2",
                 "--batch-size", "4", "--dropout", "0", "--img-pretrain", "No",
@@ -46,6 +49,8 @@ def import_reference():
     orig = mod.swin_t_m
     mod.swin_t_m = lambda weights=None, **k: orig(weights=None, **k)
     enc_mod = importlib.import_module("builder.models.src.transformer.mbt_encoder")
+    assert mod.__file__.startswith(REF), mod.__file__
+    sys.path.append(ROOT)
     return args, mod, enc_mod
 
 
@@ -54,6 +59,7 @@ def main():
     from oracle import synth, weights
     from oracle import tri_mbt_oracle as O
 
+    os.chdir("/tmp")
     args, mod, enc_mod = import_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
