@@ -112,6 +112,12 @@ int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint
  * (32 bytes): dst[R,C] = fp16(src), dst_t[C,R] = fp16(src)^T (either may be NULL). */
 int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* stream);
 
+
+/* ---- a13 (optimizer tail): torch.optim.AdamW semantics (reference 2_train.py:110) over the
+ * flat fp32 parameter / gradient buffers of the fused path: w,g,m,v fp32 [n], n % 4 == 0; step >= 1. ---------- */
+int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

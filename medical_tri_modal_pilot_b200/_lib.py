@@ -38,6 +38,7 @@ SIGNATURES = {
     "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp],
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
+    "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
 }
 _RESTYPES = {"tmp_last_error": C.c_char_p}
 
@@ -67,9 +68,16 @@ def last_error() -> str:
     return (load().tmp_last_error() or b"").decode()
 
 
+# kernels launched per C-ABI call (tmp_mma_attn_bwd = delta + main + dQ convert); bench.py reports the total
+_KERNELS_PER_CALL = {"tmp_mma_attn_bwd": 3}
+launch_count = 0
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+    launch_count += _KERNELS_PER_CALL.get(what, 1)
 
 
 def ptr(t) -> int | None:

@@ -135,7 +135,8 @@ class TRI_MBT_VSLTCLS(nn.Module):
         # The reference only runs with vslt_img_txt; the 1- and 2-modal input types are served
         # by the exactly equivalent constant `missing` code.
         self.input_types = getattr(args, "input_types", "vslt_img_txt")
-        self.forced_missing = {"vslt": 3, "vslt_txt": 2, "vslt_img": 1, "vslt_img_txt": None}[self.input_types]
+        if self.input_types not in ("vslt", "vslt_txt", "vslt_img", "vslt_img_txt"):
+            raise ValueError(f"unknown --input-types {self.input_types}")
         self.bottlenecks_n = 4
 
         mk_ie = lambda k: nn.Sequential(nn.Linear(k, D), nn.LayerNorm(D), nn.ReLU(inplace=True))
@@ -166,8 +167,7 @@ class TRI_MBT_VSLTCLS(nn.Module):
         B = x.shape[0]
         demographic = torch.cat([age.unsqueeze(1), gen.unsqueeze(1)], dim=1).float()
         demo_embedding = self.ie_demo(demographic)
-        if self.forced_missing is not None:
-            missing = torch.full((B,), self.forced_missing, dtype=torch.long, device=x.device)
+        missing = self.tri_missing_code(missing, B, x.device)
         img_feats = self.encode_images(img, missing)
         cls_out = self._fused(x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing)
         classInput = self.layer_norms_after_concat(cls_out)
@@ -178,6 +178,18 @@ class TRI_MBT_VSLTCLS(nn.Module):
             output2 = None
         output1 = self.fc_list(classInput)
         return output1, output2, None
+
+    def tri_missing_code(self, missing, B, device):
+        """Map the trainer's `missing_num` of a 1-/2-modal run onto the tri-modal code (0 all present, 1 txt missing,
+        2 img missing, 3 both; reference trainer.py:68-84 and its remap :99-105, inverted -- SURVEY.md 8c):
+        vslt -> 3; vslt_txt {0,1} -> {2,3}; vslt_img {0,1} -> {1,3}."""
+        if self.input_types == "vslt_img_txt":
+            return missing.to(torch.long)
+        if self.input_types == "vslt" or missing is None:
+            code = {"vslt": 3, "vslt_txt": 2, "vslt_img": 1}[self.input_types]
+            return torch.full((B,), code, dtype=torch.long, device=device)
+        m = (missing.to(torch.long) != 0).to(torch.long)
+        return 2 + m if self.input_types == "vslt_txt" else 1 + 2 * m
 
     def encode_images(self, img, missing):
         """Frozen image encoder (reference tri_mbt_vsltcls.py:205-209: reshape(-1,1,224,224), torch.no_grad).

@@ -164,3 +164,11 @@ def dropout_apply(inp, out, drop_p, seed, salt):
 
 def cast_weights(descs_dev, n_desc, max_R, max_C):
     check(_lib.load().tmp_cast_weights(ptr(descs_dev), n_desc, max_R, max_C, stream_ptr()), "tmp_cast_weights")
+
+
+def adamw_step(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    """torch.optim.AdamW update of the flat fp32 buffers w (in place), with moments m, v (in place)."""
+    for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v")):
+        _cuda_contig(t, torch.float32, nm)
+    check(_lib.load().tmp_adamw_step(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), float(lr), float(beta1), float(beta2),
+                                     float(eps), float(weight_decay), int(step), stream_ptr()), "tmp_adamw_step")

@@ -50,8 +50,9 @@ class FusedPath:
         self.device = None
         self.step = 0
         self._ws_key = None
-        self.comm_hook = None     # optional callable(flat_g_range_start, flat_g_range_end) for DDP bucket overlap
+        self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
         self.skip_missing = True
+        self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
         self.grad_scale = GRAD_SCALE
 
     # ------------------------------------------------------------------------------------------------------------
@@ -300,8 +301,7 @@ class FusedPath:
                 upper_has_it = 0 if last else 1
                 ops.bottleneck_mix_bwd(self.ws[0]["g_y"], self.ws[1]["g_y"], self.ws[2]["g_y"], upper_has_it,
                                        ctx["missing"])
-            if self.comm_hook is not None:
-                self.comm_hook(l)
+            self._range_done(*self.grad_range_of_layer(l))
         # prologue + projections
         F = "fusion_transformer"
         for s in range(3):
@@ -316,10 +316,15 @@ class FusedPath:
         ops.colsum(self.g_proj[1], self.G("linear.bias", D))
         ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768))
         ops.colsum(self.g_proj[2], self.G("txt_embedding.bias", D))
-        self.flat_g.mul_(1.0 / self.grad_scale)
-        if self.comm_hook is not None:
-            self.comm_hook(-1)
+        self._range_done(*self.grad_range_of_layer(-1))
         self._publish_grads()
+
+    def _range_done(self, a, b):
+        """flat_g[a:b] is complete: remove the fp16 gradient scale and hand the range to the data-parallel hook
+        (trainer.GradSync launches its all-reduce on the communication stream while the backward continues)."""
+        self.flat_g[a:b].mul_(1.0 / self.grad_scale)
+        if self.comm_hook is not None:
+            self.comm_hook(a, b)
 
     def _layer_bwd(self, l, s, ctx):
         st = self.ws[s]
@@ -353,9 +358,22 @@ class FusedPath:
         ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
         st["g_y"], st["g_x"] = st["g_x"], st["g_y"]
 
+    def live_end(self):
+        """flat_w[:live_end()] / flat_g[:live_end()] are the parameters that receive gradients. With --mbt-only-vslt 1
+        the img/txt blocks of the last layer are never run (mbt_encoder.py:757-763): they are the tail of the flat
+        layout and keep `grad = None` like in the reference (torch.optim.AdamW skips them)."""
+        m = self.model
+        if m.vsltonly == 1:
+            return self.offs[f"fusion_transformer.layer_stacks.{m.num_layers - 1}.1.attention_prenorm.gamma"]
+        return self.total
+
     def _publish_grads(self):
         """param.grad <- view of flat_g (accumulates if the caller kept older gradients)."""
+        self.grads_fresh = True
+        end = self.live_end()
         for n, prm in self.layout:
+            if self.offs[n] >= end:
+                continue
             gv = self.gviews[n]
             if prm.grad is None:
                 prm.grad = gv
@@ -368,7 +386,7 @@ class FusedPath:
         if l >= 0:
             a = self.offs[f"{F}.layer_stacks.{l}.0.attention_prenorm.gamma"]
             nxt = f"{F}.layer_stacks.{l + 1}.0.attention_prenorm.gamma"
-            b = self.offs[nxt] if nxt in self.offs else self.total
+            b = self.offs[nxt] if nxt in self.offs else self.live_end()
             return a, b
         return 0, self.offs[f"{F}.layer_stacks.0.0.attention_prenorm.gamma"]
 

@@ -1,0 +1,174 @@
+"""Training / evaluation step with the reference's trainer contract (reference builder/trainer/trainer.py:20-241,
+builder/trainer/__init__.py:14-47) plus the one thing the reference does not have: data-parallel gradient exchange.
+
+`missing_trainer` / `get_trainer` take exactly the reference's arguments (host or device tensors as `2_train.py:141-200`
+passes them) and return `(model, loss.item())`. Differences, all deliberate and documented in DESIGN.md:
+  * no hidden device->host round trips: the `missing` -> `missing_num` code (trainer.py:68-84, a `torch.unique` over
+    rows) is computed arithmetically on device (`2*img_missing + txt_missing`, bit-identical on 0/1 rows);
+  * `train_x` is NOT truncated to `max(input_lengths)` (trainer.py:41-42 needs a host sync); rows past each sample's
+    length are dead in the fused path (kv_len masks them), so the result is identical;
+  * `torch.cuda.amp.autocast()` is not entered: the fused path has its own fp16 tensor-core precision plan and the
+    tiny classifier head stays fp32.
+
+`GradSync` is the data-parallel part: one process per GPU, the flat fp32 gradient buffer of the fused
+path is all-reduced range by range (one range per encoder layer, launched from the backward as soon as that layer's
+weight gradients are complete) on a dedicated communication stream, so NCCL over NVLink overlaps the rest of the
+backward; the few head parameters go in one extra flat bucket.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def missing_to_num(missing: torch.Tensor) -> torch.Tensor:
+    """[B,3] rows (0, img_missing, txt_missing) -> code 0..3 (reference trainer.py:68-84: rank among the 4 canonical
+    rows after torch.unique(sorted) == 2*img_missing + txt_missing)."""
+    m = missing.to(torch.long)
+    return 2 * m[:, 1] + m[:, 2]
+
+
+class GradSync:
+    """Bucketed gradient all-reduce overlapped with the fused backward (NCCL, or gloo in the CPU tests).
+
+    Attach with `GradSync(model, process_group)`; `missing_trainer` calls `finish()` between backward and
+    optimizer.step(). Averaging: every range is pre-divided by world_size on the compute stream, then summed."""
+
+    def __init__(self, model, group=None, broadcast_from: int | None = 0, overlap: bool = True):
+        self.model = model
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.fp = model._fused
+        self.overlap = overlap
+        self.comm_stream = None
+        self.head_params = [p for n, p in model.named_parameters()
+                            if p.requires_grad and not n.startswith("img_encoder.") and not self._is_fused(n)]
+        self._head_flat = None
+        self.n_collectives = 0
+        self.fp.comm_hook = self._on_range_ready
+        object.__setattr__(model, "grad_sync", self)      # found by train_step; not a submodule / state_dict entry
+        if broadcast_from is not None:
+            self.broadcast_parameters(broadcast_from)
+
+    def _is_fused(self, name):
+        from .runtime import _is_fused_param
+        return _is_fused_param(name)
+
+    def broadcast_parameters(self, src=0):
+        """Identical initial weights on every rank. Buffers (BatchNorm statistics) included."""
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src, group=self.group)
+
+    # called by FusedPath.backward on the compute stream once flat_g[a:b] is final (already unscaled)
+    def _on_range_ready(self, a: int, b: int):
+        g = self.fp.flat_g[a:b]
+        if self.world == 1:
+            return
+        g.mul_(1.0 / self.world)
+        if g.is_cuda and self.overlap:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(device=g.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        self.n_collectives += 1
+
+    def finish(self):
+        """Head bucket + join the communication stream. Call after loss.backward(), before optimizer.step()."""
+        if self.world == 1:
+            return
+        live = [p for p in self.head_params if p.grad is not None]
+        if live:
+            flat = torch.cat([p.grad.reshape(-1) for p in live]).mul_(1.0 / self.world)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.n_collectives += 1
+            off = 0
+            for p in live:
+                n = p.numel()
+                p.grad.copy_(flat[off: off + n].view_as(p.grad))
+                off += n
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
+def prepare_batch(args, device, train_x, static_x, input_lengths, train_y, x_img, x_txt, txt_lengths, imgtxt_time,
+                  missing):
+    """Host->device moves and casts of reference 2_train.py:143-169 + trainer.py:25-105 (no-ops for tensors that are
+    already resident). Returns the dict `train_step` consumes."""
+    nb = dict(device=device, non_blocking=True)
+    img_time, txt_time = imgtxt_time
+    missing_num = missing_to_num(missing.to(**nb))
+    if args.input_types == "vslt_txt":                           # trainer.py:99-105 remap (the model maps it back)
+        missing_num = torch.where(missing_num >= 2, missing_num - 2, missing_num)
+    elif args.input_types == "vslt_img":
+        missing_num = torch.where(missing_num == 3, torch.ones_like(missing_num), torch.zeros_like(missing_num))
+    static_x = static_x.to(**nb)
+    return dict(
+        x=train_x.to(**nb), y=train_y.to(dtype=torch.float32, **nb),
+        age=static_x[:, 1].float(), gender=static_x[:, 0].float(),           # trainer.py:92-95
+        input_lengths=input_lengths.to(**nb), txts=x_txt.to(**nb), txt_lengths=txt_lengths.to(**nb),
+        img=x_img.to(**nb), missing_num=missing_num,
+        img_time=img_time.to(dtype=torch.float32, **nb),                     # reference: HalfTensor (:26-27)
+        txt_time=txt_time.to(dtype=torch.float32, **nb))
+
+
+def forward_loss(args, model, criterion, b, flow_type):
+    mean = getattr(args, "feature_means", None)
+    output, _, _ = model(b["x"], None, None, None, mean, b["age"], b["gender"], b["input_lengths"], b["txts"],
+                         b["txt_lengths"], b["img"], b["missing_num"], None, b["img_time"], b["txt_time"], flow_type,
+                         None, None)
+    output = output.squeeze()
+    return output, criterion(output, b["y"])
+
+
+def train_step(args, model, optimizer, criterion, b, scheduler=None, iteration=0, logger=None):
+    """One optimisation step on a prepared (device-resident) batch; returns the loss as a DEVICE tensor (no sync).
+    reference trainer.py:124-191."""
+    optimizer.zero_grad()
+    _, loss = forward_loss(args, model, criterion, b, "train")
+    loss.backward()
+    sync = getattr(model, "grad_sync", None)
+    if sync is not None:
+        sync.finish()
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step(iteration)
+        if logger is not None:
+            logger.log_lr(scheduler.get_lr()[0], iteration)
+    return loss.detach()
+
+
+def missing_trainer(args, iteration, train_x, static_x, input_lengths, train_y, model, logger, device, scheduler=None,
+                    optimizer=None, criterion=None, scaler=None, flow_type=None, output_lengths=None, seq_lengths=None,
+                    x_img=None, x_txt=None, txt_lengths=None, imgtxt_time=None, missing=None, reports_tokens=None,
+                    reports_lengths=None, criterion_aux=None):
+    """Same signature and return value as reference builder/trainer/trainer.py:20-241 (TIE branch)."""
+    if getattr(args, "vslt_type", "TIE") != "TIE":
+        raise NotImplementedError("B200 trainer implements --vslt-type TIE")
+    b = prepare_batch(args, device, train_x, static_x, input_lengths, train_y, x_img, x_txt, txt_lengths, imgtxt_time,
+                      missing)
+    if flow_type == "train":
+        loss = train_step(args, model, optimizer, criterion, b, scheduler, iteration, logger)
+    else:
+        with torch.no_grad():
+            output, loss = forward_loss(args, model, criterion, b, flow_type)
+            output = torch.sigmoid(output)
+        if logger is not None:
+            logger.evaluator.add_batch(b["y"], output)
+    return model, loss.item()
+
+
+def get_trainer(args, iteration, x, static, input_lengths, y, output_lengths, model, logger, device, scheduler,
+                optimizer, criterion, x_txt=None, x_img=None, txt_lengths=None, seq_lengths=None, imgtxt_time=None,
+                scaler=None, missing=None, flow_type=None, reports_tokens=None, reports_lengths=None,
+                criterion_aux=None):
+    """reference builder/trainer/__init__.py:14-47"""
+    return missing_trainer(args, iteration, x, static, input_lengths, y, model, logger, device, scheduler, optimizer,
+                           criterion, scaler, flow_type, output_lengths, seq_lengths=seq_lengths, x_img=x_img,
+                           x_txt=x_txt, txt_lengths=txt_lengths, imgtxt_time=imgtxt_time, missing=missing,
+                           reports_tokens=reports_tokens, reports_lengths=reports_lengths, criterion_aux=criterion_aux)

@@ -66,17 +66,21 @@ def test_logits_and_grads(name):
     assert worst[0] >= GRAD_COS_MIN, worst
 
 
-def test_input_types_map_to_constant_missing_code():
-    """--input-types vslt / vslt_txt / vslt_img == tri model with constant missing code 3 / 2 / 1."""
+def test_input_types_map_to_tri_missing_code():
+    """--input-types vslt / vslt_txt / vslt_img == tri model with missing code 3 / {2,3} / {1,3} (the
+    2-modal codes {0,1} are the trainer's remap, reference trainer.py:99-105)."""
     from oracle import tri_mbt_oracle as O
     fx = load_fixture(fixture_names()[0])
     sd, batch, cfg = fixture_inputs(fx)
     B = batch["x"].shape[0]
-    for it, code in (("vslt", 3), ("vslt_txt", 2), ("vslt_img", 1)):
+    two = (torch.arange(B) % 2).to(torch.long)                       # per-sample "second modality missing" flag
+    for it, tri in (("vslt", torch.full((B,), 3)), ("vslt_txt", 2 + two), ("vslt_img", 1 + 2 * two)):
         model = build_model(cfg, sd, B, input_types=it).train()
-        out, _ = run_model(model, batch)
+        b1 = dict(batch)
+        b1["missing"] = two
+        out, _ = run_model(model, b1)
         b2 = dict(batch)
-        b2["missing"] = torch.full((B,), code, dtype=torch.long)
+        b2["missing"] = tri.to(torch.long)
         ref = O.forward(sd, b2, cfg)
         rel = ((out.detach().cpu() - ref).abs().max() / ref.abs().max()).item()
         assert rel < LOGIT_RTOL_BF16, (it, rel)
