@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtmp_b200.so")
+LIB_PATH = os.environ.get("TMP_B200_LIB") or os.path.join(_PKG, "libtmp_b200.so")   # env override: A/B debugging only
 
 _vp, _i, _ll, _f, _u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint32
 _pp = C.POINTER(C.c_void_p)

@@ -1,14 +1,19 @@
 // attn_bwd_tc05.cu -- backward of the modality-aware attention (reference attention.py:24-49 under autograd)
 // as a tcgen05/TMEM kernel. One CTA owns a 128-key tile of one (sample, head) and sweeps the live query tiles:
 //
-//   S^T  = K_j Q_i^T            dP^T = V_j dO_i^T                      (2 MMAs into TMEM)
+//   S^T  = K_j Q_i^T            dP^T = V_j dO_i^T                      (MMAs into TMEM, in two 64-query halves)
 //   P^T  = exp2(S^T*c - LSE_i)  dS^T = P^T o (dP^T - delta_i) / 8      (registers -> swizzled smem, fp16)
-//   dV_j += P^T dO_i            dK_j += dS^T Q_i       dQ_i = dS K_j   (3 MMAs; dQ -> fp32 atomics)
+//   dV_j += P^T dO_i            dK_j += dS^T Q_i       dQ_i = dS K_j   (MMAs; dQ leaves through a TMA reduce-add)
 //
-// dS^T is written to shared memory once and read twice: as a K-major A operand (dK) and as an MN-major
-// A operand (dQ = dS.K needs the transpose). Q_i / dO_i / K_j are consumed as MN-major B operands straight
-// from their natural [row, d] layout. The key-padding mask is kv_len[b] applied in-register (P^T rows of
-// masked keys are exactly 0, so dK/dV of pad rows are exactly 0, as in the reference).
+// Pipeline: every 128x128 score tile is processed as two 64-query halves with separate TMEM buffers, so the
+// S^T/dP^T MMAs of the next half run while the 8 compute warps do the exponentials of the current one, and the
+// dV/dK/dQ MMAs of half h overlap the compute of half h+1 (TMEM: 2x64 S^T + 2x64 dP^T + dV 64 + dK 64 + dQ 64 = 448
+// columns). dS^T is written to shared memory once and read twice: as a K-major A operand (dK) and as an MN-major
+// A operand (dQ = dS.K needs the transpose). Q_i / dO_i / K_j are consumed as MN-major B operands straight from
+// their natural [row, d] layout; LSE_i / delta_i ride in the same TMA ring stage as Q_i / dO_i (bulk copies).
+// dQ_i (fp32, 128x64) is staged in swizzled smem per warp and added into the fp32 accumulator with
+// cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b] applied in-register, only in
+// boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly 0, as in the reference).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -16,12 +21,14 @@ using namespace tc05;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kComputeWarps = 8;
+constexpr int kThreads = 64 + 32 * kComputeWarps;
 constexpr int BT = 128;  // tile rows (keys per CTA, queries per iteration)
 constexpr int HD = 64;
 constexpr int kStages = 2;
-constexpr int kTile = BT * HD * 2;   // 16 KB : [128 rows x 64 bf16]
-constexpr int kSq = BT * BT * 2;     // 32 KB : [128 x 128] bf16 as two 64-column sub-tiles
+constexpr int kTile = BT * HD * 2;   // 16 KB : [128 rows x 64 fp16]
+constexpr int kSq = BT * BT * 2;     // 32 KB : [128 x 128] fp16 as two 64-column sub-tiles
+constexpr int kStatBytes = 2 * BT * 4;  // lse[128] | delta[128] fp32 per ring stage
 
 constexpr int kSmemK = 0;
 constexpr int kSmemV = kSmemK + kTile;
@@ -29,9 +36,10 @@ constexpr int kSmemQ = kSmemV + kTile;
 constexpr int kSmemDO = kSmemQ + kStages * kTile;
 constexpr int kSmemPT = kSmemDO + kStages * kTile;
 constexpr int kSmemDST = kSmemPT + kSq;
-constexpr int kSmemStat = kSmemDST + kSq;                 // [2 buffers][lse 128 | delta 128] fp32
-constexpr int kSmemBar = kSmemStat + 2 * 2 * BT * 4;
-constexpr int kSmemTotal = kSmemBar + 128 + 1024;
+constexpr int kSmemDQ = kSmemDST + kSq;                   // per compute warp: [32 rows x 32 fp32], 128B swizzle
+constexpr int kSmemStat = kSmemDQ + kComputeWarps * 4096;
+constexpr int kSmemBar = kSmemStat + kStages * kStatBytes;
+constexpr int kSmemTotal = kSmemBar + 256 + 1024;
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -44,25 +52,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct Bars {
   uint64_t kv_full;
   uint64_t qdo_full[kStages], qdo_empty[kStages];
-  uint64_t sdp_full;  // MMA -> compute : S^T and dP^T in TMEM
-  uint64_t pds_full;  // compute -> MMA : P^T and dS^T in smem
-  uint64_t dq_full;   // MMA -> compute : dQ tile in TMEM, all MMAs of this iteration retired
+  uint64_t sdp_full[2];  // MMA -> compute : S^T and dP^T of half h in TMEM
+  uint64_t pds_full[2];  // compute -> MMA : P^T and dS^T of half h in smem (and the TMEM half is drained)
+  uint64_t dq_full;      // MMA -> compute : dQ tile in TMEM, all MMAs of this iteration retired
+  uint64_t dq_empty;     // compute -> MMA : dQ TMEM drained
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const int32_t* __restrict__ kv_len, int T, const float* __restrict__ lse2,
-                const float* __restrict__ delta, int T_lse, float* __restrict__ dQ_acc, uint16_t* __restrict__ dQKV,
-                float scale_log2) {
+                const __grid_constant__ CUtensorMap tmDQ, const int32_t* __restrict__ kv_len, int T,
+                const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
+                uint16_t* __restrict__ dQKV, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   Bars* bars = (Bars*)(smem + kSmemBar);
-  float* stat = (float*)(smem + kSmemStat);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,7 +78,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (k0 >= len) {
     // masked / padding keys: dK = dV = 0
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int r = (warp - 2) * 32 + lane;
       if (k0 + r < T) {
         uint4* dk = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + k0 + r) * 768 + 256 + h * HD);
@@ -93,14 +97,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmDQ);
     mbar_init(&bars->kv_full, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->qdo_full[s], 1);
       mbar_init(&bars->qdo_empty[s], 1);
     }
-    mbar_init(&bars->sdp_full, 1);
-    mbar_init(&bars->pds_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->sdp_full[s], 1);
+      mbar_init(&bars->pds_full[s], kComputeWarps);
+    }
     mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_empty, kComputeWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
@@ -108,11 +116,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
-  const uint32_t tm_ST = tmem_base + 0;
-  const uint32_t tm_DPT = tmem_base + 128;
+  const uint32_t tm_ST = tmem_base + 0;     // [2] x 64 columns
+  const uint32_t tm_DPT = tmem_base + 128;  // [2] x 64 columns
   const uint32_t tm_DV = tmem_base + 256;
   const uint32_t tm_DK = tmem_base + 320;
   const uint32_t tm_DQ = tmem_base + 384;
+  const size_t stat_base = ((size_t)b * H + h) * T_lse;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -123,152 +132,212 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t ph = 0;
       for (int i = 0; i < n_q; ++i) {
         mbar_wait(&bars->qdo_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->qdo_full[st], 2 * kTile);
+        mbar_expect_tx(&bars->qdo_full[st], 2 * kTile + kStatBytes);
         tma_load_2d(smem + kSmemQ + st * kTile, &tmQKV, &bars->qdo_full[st], h * HD, row_base + i * BT);
         tma_load_2d(smem + kSmemDO + st * kTile, &tmDO, &bars->qdo_full[st], h * HD, row_base + i * BT);
+        bulk_load_1d(smem + kSmemStat + st * kStatBytes, lse2 + stat_base + i * BT, BT * 4, &bars->qdo_full[st]);
+        bulk_load_1d(smem + kSmemStat + st * kStatBytes + BT * 4, delta + stat_base + i * BT, BT * 4,
+                     &bars->qdo_full[st]);
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // all operands fp16 (kind::f16 needs A and B in the same format; gradients are fp16 with a host-side scale)
-      constexpr uint32_t idesc_st = make_idesc(BT, BT, 0, 0, FMT_F16, FMT_F16);  // S^T  = K Q^T
-      constexpr uint32_t idesc_dp = make_idesc(BT, BT, 0, 0, FMT_F16, FMT_F16);  // dP^T = V dO^T
-      constexpr uint32_t idesc_dv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV  += P^T dO   (B MN-major)
-      constexpr uint32_t idesc_dk = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dK  += dS^T Q   (B MN-major)
+      constexpr uint32_t idesc_s = make_idesc(BT, 64, 0, 0, FMT_F16, FMT_F16);   // S^T_h / dP^T_h : [128 keys x 64 q]
+      constexpr uint32_t idesc_kv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV += P^T dO, dK += dS^T Q (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(BT, HD, 1, 1, FMT_F16, FMT_F16);  // dQ   = dS K     (A, B MN-major)
       const uint32_t sK = smem_u32(smem + kSmemK), sV = smem_u32(smem + kSmemV);
       const uint32_t sPT = smem_u32(smem + kSmemPT), sDST = smem_u32(smem + kSmemDST);
-      mbar_wait(&bars->kv_full, 0);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < n_q; ++i) {
+      auto issue_sdp = [&](int i, int hh) {   // S^T_hh(i), dP^T_hh(i)
+        const int st = i & 1;
+        const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile) + hh * 8192;    // 64 query rows = 8192 B
+        const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile) + hh * 8192;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_ss(tm_ST + hh * 64, make_sdesc_sw128(sK + k * 32, 16, 1024), make_sdesc_sw128(sQ + k * 32, 16, 1024),
+                  idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_ss(tm_DPT + hh * 64, make_sdesc_sw128(sV + k * 32, 16, 1024), make_sdesc_sw128(sDO + k * 32, 16, 1024),
+                  idesc_s, k != 0);
+        umma_commit(&bars->sdp_full[hh]);
+      };
+      auto issue_dvdk = [&](int i, int hh) {  // dV += P^T_hh dO_i[hh], dK += dS^T_hh Q_i[hh]  (reduction over 64 queries)
+        const int st = i & 1;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile);
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile);
-        mbar_wait(&bars->qdo_full[st], ph);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tm_DV, make_sdesc_sw128(sPT + hh * (BT * 128) + k * 32, 16, 1024),
+                  make_sdesc_sw128(sDO + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv, (i | hh | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tm_DK, make_sdesc_sw128(sDST + hh * (BT * 128) + k * 32, 16, 1024),
+                  make_sdesc_sw128(sQ + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv, (i | hh | k) != 0);
+      };
+      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(&bars->qdo_full[0], 0);
+      tc_fence_after();
+      issue_sdp(0, 0);
+      issue_sdp(0, 1);
+      for (int i = 0; i < n_q; ++i) {
+        const uint32_t ph = i & 1;
+        const bool more = i + 1 < n_q;
+        // ---- half 0 ----
+        mbar_wait(&bars->pds_full[0], ph);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_ST, make_sdesc_sw128(sK + k * 32, 16, 1024), make_sdesc_sw128(sQ + k * 32, 16, 1024), idesc_st,
-                  k != 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_DPT, make_sdesc_sw128(sV + k * 32, 16, 1024), make_sdesc_sw128(sDO + k * 32, 16, 1024), idesc_dp,
-                  k != 0);
-        umma_commit(&bars->sdp_full);
-
-        mbar_wait(&bars->pds_full, i & 1);
+        issue_dvdk(i, 0);
+        if (more) {
+          mbar_wait(&bars->qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_sdp(i + 1, 0);
+        }
+        // ---- half 1 ----
+        mbar_wait(&bars->pds_full[1], ph);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < BT / 16; ++k) {  // dV += P^T dO_i   (reduction over the 128 queries)
-          const uint64_t adesc = make_sdesc_sw128(sPT + (k >> 2) * (BT * 128) + (k & 3) * 32, 16, 1024);
-          umma_ss(tm_DV, adesc, make_sdesc_sw128(sDO + k * 2048, BT * 128, 1024), idesc_dv, (i | k) != 0);
+        issue_dvdk(i, 1);
+        if (i > 0) {
+          mbar_wait(&bars->dq_empty, (i - 1) & 1);
+          tc_fence_after();
         }
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k) {  // dK += dS^T Q_i
-          const uint64_t adesc = make_sdesc_sw128(sDST + (k >> 2) * (BT * 128) + (k & 3) * 32, 16, 1024);
-          umma_ss(tm_DK, adesc, make_sdesc_sw128(sQ + k * 2048, BT * 128, 1024), idesc_dk, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < BT / 16; ++k) {  // dQ_i = dS K_j    (reduction over the 128 keys; A = dS^T read MN-major)
+        for (int k = 0; k < BT / 16; ++k)  // dQ_i = dS K_j  (reduction over the 128 keys; A = dS^T read MN-major)
           umma_ss(tm_DQ, make_sdesc_sw128(sDST + k * 2048, BT * 128, 1024),
                   make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
-        }
         umma_commit(&bars->dq_full);
-        umma_commit(&bars->qdo_empty[st]);
-        if (++st == kStages) { st = 0; ph ^= 1; }
+        umma_commit(&bars->qdo_empty[i & 1]);
+        if (more) issue_sdp(i + 1, 1);
       }
     }
   } else {
-    const int quarter = warp & 3;
+    // ===================== compute warps =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int colhalf = cw >> 2;        // which 32 of the 64 columns of a half-step / of the 64 dQ,dK,dV columns
     const int r = quarter * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dK/dV, query row for dQ
-    const int tid = (warp - 2) * 32 + lane;
     const bool key_ok = (k0 + r) < len;
+    const bool key_tile_partial = (k0 + BT) > len;
     uint8_t* sPT = smem + kSmemPT;
     uint8_t* sDST = smem + kSmemDST;
-    const size_t stat_base = ((size_t)b * H + h) * T_lse;
-    for (int i = 0; i < n_q; ++i) {
-      float* st_lse = stat + (i & 1) * 2 * BT;
-      float* st_dl = st_lse + BT;
-      st_lse[tid] = lse2[stat_base + i * BT + tid];
-      st_dl[tid] = delta[stat_base + i * BT + tid];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&bars->sdp_full, i & 1);
+    uint8_t* sDQ = smem + kSmemDQ + cw * 4096;
+
+    auto dq_flush = [&](int i) {   // dQ(i): TMEM -> swizzled smem box -> TMA reduce-add into the fp32 accumulator
+      mbar_wait(&bars->dq_full, i & 1);
       tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_addr(tm_DQ, quarter * 32, colhalf * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->dq_empty);
+        tma_store_wait_read0();   // previous reduce of this warp has finished reading the staging box
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
+        tma_store_commit();
+      }
+    };
+
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      const float* st_lse = (const float*)(smem + kSmemStat + st * kStatBytes);
+      const float* st_dl = st_lse + BT;
+      const bool need_mask = key_tile_partial || (i * BT + BT > len);
+      if (i == 0 || true) {
+        // the ring stage (Q_i, dO_i, lse_i, delta_i) is complete before the MMA warp could issue S^T(i); observing
+        // it here orders our generic-proxy reads of lse/delta after the bulk copies.
+        mbar_wait(&bars->qdo_full[st], (i >> 1) & 1);
+      }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {  // 32 queries per chunk
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_wait(&bars->sdp_full[hh], i & 1);
+        tc_fence_after();
         uint32_t s[32], dp[32];
-        tmem_ld32(tmem_addr(tm_ST, quarter * 32, c * 32), s);
-        tmem_ld32(tmem_addr(tm_DPT, quarter * 32, c * 32), dp);
+        tmem_ld32(tmem_addr(tm_ST + hh * 64, quarter * 32, colhalf * 32), s);
+        tmem_ld32(tmem_addr(tm_DPT + hh * 64, quarter * 32, colhalf * 32), dp);
         tmem_ld_wait();
+        const int qc0 = hh * 64 + colhalf * 32;   // first query column (within the 128-query tile) of this thread's run
         uint32_t pp[16], dd[16];
+        if (!need_mask) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float p[2], d[2];
+          for (int t = 0; t < 32; t += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
+            const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float p[4], d[4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int qc = c * 32 + t + u;
-            const bool ok = key_ok && (i * BT + qc) < len;
-            const float pv = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -st_lse[qc]));
-            p[u] = ok ? pv : 0.f;
-            d[u] = ok ? pv * (__uint_as_float(dp[t + u]) - st_dl[qc]) * 0.125f : 0.f;
+            for (int u = 0; u < 4; ++u) {
+              // p/8 straight from the exponential (lse + 3 in log2 units), p = 8 * (p/8) is exact
+              const float p8 = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -(lv[u] + 3.f)));
+              p[u] = p8 * 8.f;
+              d[u] = p8 * (__uint_as_float(dp[t + u]) - dv[u]);
+            }
+            pp[t >> 1] = pack_f16x2(p[0], p[1]); pp[(t >> 1) + 1] = pack_f16x2(p[2], p[3]);
+            dd[t >> 1] = pack_f16x2(d[0], d[1]); dd[(t >> 1) + 1] = pack_f16x2(d[2], d[3]);
           }
-          pp[t >> 1] = pack_f16x2(p[0], p[1]);
-          dd[t >> 1] = pack_f16x2(d[0], d[1]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            float p[2], d[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int qc = qc0 + t + u;
+              const bool ok = key_ok && (i * BT + qc) < len;
+              const float p8 = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -(st_lse[qc] + 3.f)));
+              p[u] = ok ? p8 * 8.f : 0.f;
+              d[u] = ok ? p8 * (__uint_as_float(dp[t + u]) - st_dl[qc]) : 0.f;
+            }
+            pp[t >> 1] = pack_f16x2(p[0], p[1]);
+            dd[t >> 1] = pack_f16x2(d[0], d[1]);
+          }
         }
-        const uint32_t sub = (c >> 1) * (BT * 128);
+        if (hh == 0 && i > 0) {
+          // P^T / dS^T smem (both halves) may be overwritten only after the MMAs of iteration i-1 have retired
+          mbar_wait(&bars->dq_full, (i - 1) & 1);
+        }
+        const uint32_t sub = hh * (BT * 128);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = sub + sw128_offset(r, (c & 1) * 4 + q4);
+          const uint32_t off = sub + sw128_offset(r, colhalf * 4 + q4);
           *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
           *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
         }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->pds_full[hh]);
+        if (hh == 0 && i > 0) dq_flush(i - 1);
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->pds_full);
-
-      mbar_wait(&bars->dq_full, i & 1);
-      tc_fence_after();
-      const int q = i * BT + r;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tm_DQ, quarter * 32, c * 32), v);
-        tmem_ld_wait();
-        if (q < len) {
-          float* dst = dQ_acc + (size_t)(row_base + q) * 256 + h * HD + c * 32;
-#pragma unroll
-          for (int t = 0; t < 32; t += 4)
-            red_add_v4(dst + t, __uint_as_float(v[t]), __uint_as_float(v[t + 1]), __uint_as_float(v[t + 2]),
-                       __uint_as_float(v[t + 3]));
-        }
-      }
-      tc_fence_before();
     }
-    // dK_j, dV_j (all MMAs retired: last dq_full)
+    dq_flush(n_q - 1);
+    // dK_j, dV_j (all MMAs retired: last dq_full). Each warp: 32 key rows x 32 of the 64 columns of each.
     const int kr = k0 + r;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t src = which == 0 ? tm_DK : tm_DV;
-      uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(src, quarter * 32, c * 32), v);
-        tmem_ld_wait();
-        if (kr < T) {
-          uint4* dst = reinterpret_cast<uint4*>(dst_row + c * 32);
+      uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD + colhalf * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem_addr(src, quarter * 32, colhalf * 32), v);
+      tmem_ld_wait();
+      if (kr < T) {
+        uint4* dst = reinterpret_cast<uint4*>(dst_row);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
-                                pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
-                                pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
-                                pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
-        }
+        for (int t = 0; t < 4; ++t)
+          dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
       }
     }
+    if (lane == 0) tma_store_wait_read0();
   }
 
   tc_fence_before();
@@ -339,10 +408,12 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     }
     attr_set = true;
   }
-  CUtensorMap tmQKV, tmDO;
+  CUtensorMap tmQKV, tmDO, tmDQ;
   int rc = tmp::encode_tmap_2d_bf16(&tmQKV, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BT);
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmDO, dO, 256, (uint64_t)B * T, (uint64_t)ld * 2, HD, BT);
+  if (rc) return rc;
+  rc = tmp::encode_tmap_2d_f32(&tmDQ, dQ_acc, 256, (uint64_t)B * T, 256 * 4, 32, 32);   // reduce-add boxes [32 rows x 32 fp32]
   if (rc) return rc;
   {
     const int rows = B * T_lse;
@@ -356,7 +427,7 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     return (int)e;
   }
   dim3 grid((T + BT - 1) / BT, H, B);
-  attn_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, kv_len, T, lse2, delta, T_lse, dQ_acc, (uint16_t*)dQKV,
+  attn_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, kv_len, T, lse2, delta, T_lse, (uint16_t*)dQKV,
                                                       kLog2e / 8.0f);
   rc = tmp::check_launch("attn_bwd_kernel");
   if (rc) return rc;

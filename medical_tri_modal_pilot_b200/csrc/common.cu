@@ -30,8 +30,20 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* gaddr, uint64_t inner, uint64_t outer,
+                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer);
+}
+int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer);
+}
+
+static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* gaddr, uint64_t inner, uint64_t outer,
+                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   auto fn = get_encode();
   if (!fn) return TMP_ERR_DRIVER;
   if (((uintptr_t)gaddr & 15) || (row_stride_bytes & 15)) {
@@ -42,7 +54,7 @@ int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uin
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gaddr), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 2, const_cast<void*>(gaddr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -19,6 +19,10 @@ void set_error(const char* fmt, ...);
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer);
 
+// fp32 elements, 128B swizzle (box_inner <= 32 floats): used for TMA reduce-add of fp32 accumulators.
+int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer);
+
 int num_sms();
 
 inline int check_launch(const char* what) {

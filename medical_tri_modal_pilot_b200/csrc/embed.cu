@@ -219,9 +219,7 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
     }
     if (p.drop_thr16) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        y[i] = dropout_keep(p.seed, p.salt, base + i, p.drop_thr16) ? y[i] * p.drop_scale : 0.f;
+      dropout_apply_run<8>(y, dropout_key(p.seed, p.salt), base, p.drop_thr16, p.drop_scale);
     }
     store8<ACT>(dst, y);
   }
@@ -310,9 +308,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
     }
     if (p.drop_thr16) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        g[i] = dropout_keep(p.seed, p.salt, base + i, p.drop_thr16) ? g[i] * p.drop_scale : 0.f;
+      dropout_apply_run<8>(g, dropout_key(p.seed, p.salt), base, p.drop_thr16, p.drop_scale);
     }
     float s1 = 0.f;
 #pragma unroll

@@ -15,8 +15,11 @@ using namespace tc05;
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kThreadsW = 192;                  // wgrad kernel: 4 epilogue warps
+constexpr int kBiasSmemFloats = 1024;
 
 struct EpiParams {
   int M, N, K;
@@ -31,25 +34,91 @@ struct EpiParams {
   int out_fmt, gate_fmt, res_fmt;
   uint32_t drop_thr16;    // 0 = no dropout; else round(p*65536)
   float drop_scale;       // 1/(1-p)
-  uint32_t seed, salt;
-  uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null)
-  float* out_f32;         // [M, ld_out] fp32 (or null)
+  uint32_t drop_key;      // dropout_key(seed, salt)
+  uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
+  float* out_f32;         // [M, ld_out] fp32 (or null) -- direct stores
   int ld_out;
 };
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kOutOffset = kStages * kStageBytes;            // per epilogue warp: 2 x [32 rows x 128 B]
+  static constexpr int kOutBytes = kEpiWarps * 2 * 4096;
+  static constexpr int kBiasOffset = kOutOffset + kOutBytes;
+  static constexpr int kBarOffset = kBiasOffset + kBiasSmemFloats * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
 
+// Epilogue of one 32-column chunk held by one thread (= one output row): v <- fused epilogue of the accumulators.
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p, const float* sbias, int row, bool row_ok,
+                                              int col0) {
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
+  if (p.bias) {
+    if (sbias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + j);   // smem broadcast
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.gate && row_ok) {
+    const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = __ldg(g + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 gv = unpack2_rt(w[t], p.gate_fmt);
+        if (!(gv.x > 0.f)) v[q * 8 + t * 2] = 0.f;
+        if (!(gv.y > 0.f)) v[q * 8 + t * 2 + 1] = 0.f;
+      }
+    }
+  }
+  if (p.drop_thr16)
+    dropout_apply_run<32>(v, p.drop_key, (uint32_t)row * (uint32_t)p.N + (uint32_t)col0, p.drop_thr16, p.drop_scale);
+  if (p.residual && row_ok) {
+    const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = __ldg(g + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 rv = unpack2_rt(w[t], p.res_fmt);
+        v[q * 8 + t * 2] += rv.x;
+        v[q * 8 + t * 2 + 1] += rv.y;
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, EpiParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -59,6 +128,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  float* sbias = (float*)(smem + L::kBiasOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,20 +136,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_blks = p.N / BN;
   const int k_blks = p.K / BK;
   const int num_tiles = m_blks * n_blks;
+  const bool bias_in_smem = p.bias && p.N <= kBiasSmemFloats;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.out) prefetch_tmap(&tmOut);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i];
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
@@ -135,8 +209,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // warp -> (TMEM lane quarter it may access, column half of the tile). Each thread owns one output row and walks
+    // BN/2 columns in 32-column chunks; TMEM loads are software-pipelined one chunk ahead; 16-bit results are staged in
+    // 128B-swizzled smem boxes of [32 rows x 64 cols] and written with TMA stores (coalesced, asynchronous, M-tail
+    // clipped by the tensor map), double-buffered per warp.
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int half = e >> 2;
+    constexpr int kChunks = BN / 64;   // 32-column chunks per warp
+    uint8_t* stage_buf = smem + L::kOutOffset + e * 8192;
+    const float* sb_ptr = bias_in_smem ? sbias : nullptr;
+    int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -145,85 +229,60 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tmem_base, quarter * 32, acc * BN + c * 32), r);
+      const int colw = n0 + half * (BN / 2);
+      const uint32_t taddr = tmem_addr(tmem_base, quarter * 32, acc * BN + half * (BN / 2));
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
+        if (c + 1 < kChunks) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        if (c == kChunks - 1) {
+          // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
+        const int col0 = colw + c * 32;
+        epilogue_math(v, p, sb_ptr, row, row_ok, col0);
+        if (p.out_f32 && row_ok) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
+          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
-        if (p.relu) {
+        if (p.out) {
+          uint8_t* sbox = stage_buf + sbuf * 4096;
+          if ((c & 1) == 0) {
+            // the TMA store issued two boxes ago must have finished reading this buffer
+            if (lane == 0) tma_store_wait_read1();
+            __syncwarp();
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (row_ok) {
-          if (p.gate) {
-            const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = __ldg(g + q);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 gv = unpack2_rt(w[t], p.gate_fmt);
-                if (!(gv.x > 0.f)) v[q * 8 + t * 2] = 0.f;
-                if (!(gv.y > 0.f)) v[q * 8 + t * 2 + 1] = 0.f;
-              }
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack2_rt(v[q * 8 + 0], v[q * 8 + 1], p.out_fmt);
+            u.y = pack2_rt(v[q * 8 + 2], v[q * 8 + 3], p.out_fmt);
+            u.z = pack2_rt(v[q * 8 + 4], v[q * 8 + 5], p.out_fmt);
+            u.w = pack2_rt(v[q * 8 + 6], v[q * 8 + 7], p.out_fmt);
+            *reinterpret_cast<uint4*>(sbox + sw128_offset(lane, (c & 1) * 4 + q)) = u;
+          }
+          if ((c & 1) == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, sbox, colw + (c - 1) * 32, m0 + quarter * 32);
+              tma_store_commit();
             }
-          }
-          if (p.drop_thr16) {
-            const uint32_t base = (uint32_t)row * (uint32_t)p.N + (uint32_t)col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = dropout_keep(p.seed, p.salt, base + j, p.drop_thr16) ? v[j] * p.drop_scale : 0.f;
-          }
-          if (p.residual) {
-            const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = __ldg(g + q);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 rv = unpack2_rt(w[t], p.res_fmt);
-                v[q * 8 + t * 2] += rv.x;
-                v[q * 8 + t * 2 + 1] += rv.y;
-              }
-            }
-          }
-          if (p.out) {
-            uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)row * p.ld_out + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack2_rt(v[q * 8 + 0], v[q * 8 + 1], p.out_fmt);
-              u.y = pack2_rt(v[q * 8 + 2], v[q * 8 + 3], p.out_fmt);
-              u.z = pack2_rt(v[q * 8 + 4], v[q * 8 + 5], p.out_fmt);
-              u.w = pack2_rt(v[q * 8 + 6], v[q * 8 + 7], p.out_fmt);
-              o[q] = u;
-            }
-          }
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            sbuf ^= 1;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_read0();
   }
 
   tc_fence_before();
@@ -251,7 +310,7 @@ struct WgradSmem {
 };
 
 template <int BNW>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsW, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int ldw,
                   float* __restrict__ dW, int rows_per_split, int y_fmt, int x_fmt) {
   using L = WgradSmem<BNW>;
@@ -357,7 +416,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 }
 
 template <int BN>
-int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, int grid, cudaStream_t st) {
+int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const EpiParams& p, int grid,
+              cudaStream_t st) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -368,7 +428,7 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p
     }
     attr_set = true;
   }
-  gemm_tn_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, p);
+  gemm_tn_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmOut, p);
   return tmp::check_launch("gemm_tn_kernel");
 }
 
@@ -393,7 +453,7 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, i
   if (rows_per_split < BK) rows_per_split = BK;
   splits = (M + rows_per_split - 1) / rows_per_split;
   dim3 grid(N / 128, K / BNW, splits);
-  gemm_wgrad_kernel<BNW><<<grid, kThreads, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split, y_fmt, x_fmt);
+  gemm_wgrad_kernel<BNW><<<grid, kThreadsW, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split, y_fmt, x_fmt);
   return tmp::check_launch("gemm_wgrad_kernel");
 }
 
@@ -435,12 +495,20 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.out_fmt = out_fmt; p.gate_fmt = gate_fmt; p.res_fmt = res_fmt;
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.seed = seed; p.salt = salt;
+  p.drop_key = dropout_key(seed, salt);
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
+  CUtensorMap tmOut;
+  if (out_bf16) {
+    // 16-bit output written by TMA: boxes of [32 rows x 64 cols], 128B swizzle; rows >= M are clipped
+    rc = tmp::encode_tmap_2d_bf16(&tmOut, out_bf16, (uint64_t)N, (uint64_t)M, (uint64_t)ld_out * 2, 64, 32);
+    if (rc) return rc;
+  } else {
+    tmOut = tmA;
+  }
   const int tiles = m_blks * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
-  if (BN == 256) return launch_tn<256>(tmA, tmB, p, grid, (cudaStream_t)stream);
-  return launch_tn<128>(tmA, tmB, p, grid, (cudaStream_t)stream);
+  if (BN == 256) return launch_tn<256>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+  return launch_tn<128>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
 }
 
 extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,

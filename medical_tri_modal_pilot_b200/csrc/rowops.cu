@@ -151,9 +151,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restric
     store8<GRD>(dx + row * D + lane * 8, out);
     if (dx_drop) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        out[i] = dropout_keep(seed, salt, base + i, drop_thr16) ? out[i] * drop_scale : 0.f;
+      dropout_apply_run<8>(out, dropout_key(seed, salt), base, drop_thr16, drop_scale);
       store8<GRD>(dx_drop + row * D + lane * 8, out);
     }
   }
@@ -281,8 +279,7 @@ __global__ void dropout_apply_kernel(const h16* __restrict__ in, h16* __restrict
   float v[8];
   load8<GRD>(in + i8 * 8, v);
   const uint32_t base = (uint32_t)(i8 * 8);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = dropout_keep(seed, salt, base + i, thr16) ? v[i] * scale : 0.f;
+  dropout_apply_run<8>(v, dropout_key(seed, salt), base, thr16, scale);
   store8<GRD>(out + i8 * 8, v);
 }
 

@@ -84,6 +84,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both addresses 16 B aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
@@ -266,11 +273,48 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-// returns 1 if the element is kept. thr16 = round(p * 65536).
+// Dropout keep-mask: one 32-bit hash per PAIR of consecutive elements, 16 bits each (thr16 = round(p * 65536)).
+//   key  = dropout_key(seed, salt)                        (uniform per launch)
+//   bits = dropout_bits(key, idx >> 1)                    (IMAD + xorshift + multiply + xorshift)
+//   keep(idx) = 16-bit lane (idx & 1) of bits >= thr16
+// Forward and backward kernels evaluate the same function of (seed, salt, element index), so no mask is stored.
+__host__ __device__ __forceinline__ uint32_t dropout_key(uint32_t seed, uint32_t salt) {
+  return mix32(seed) ^ (salt * 0x85ebca6bU);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t pair_idx) {
+  uint32_t h = pair_idx * 0x9E3779B1U + key;
+  h ^= h >> 16;
+  h *= 0x7feb352dU;
+  h ^= h >> 15;
+  return h;
+}
+__host__ __device__ __forceinline__ bool dropout_keep_lo(uint32_t bits, uint32_t thr16) { return (bits & 0xffffu) >= thr16; }
+__host__ __device__ __forceinline__ bool dropout_keep_hi(uint32_t bits, uint32_t thr16) { return bits >= (thr16 << 16); }
+// per-element form (elementwise kernels)
 __host__ __device__ __forceinline__ uint32_t dropout_keep(uint32_t seed, uint32_t salt, uint32_t idx, uint32_t thr16) {
-  uint32_t h = mix32(idx * 0x9E3779B9U + seed) ^ (salt * 0x85ebca6bU);
-  h = mix32(h);
-  return (h & 0xffffu) >= thr16;
+  const uint32_t bits = dropout_bits(dropout_key(seed, salt), idx >> 1);
+  return (idx & 1u) ? dropout_keep_hi(bits, thr16) : dropout_keep_lo(bits, thr16);
+}
+// `v[0..n)` holds n consecutive elements starting at even index `idx0`: zero the dropped ones, scale the kept ones.
+template <int N>
+__device__ __forceinline__ void dropout_apply_run(float (&v)[N], uint32_t key, uint32_t idx0, uint32_t thr16,
+                                                  float scale) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const uint32_t bits = dropout_bits(key, (idx0 + j) >> 1);
+    v[j] = dropout_keep_lo(bits, thr16) ? v[j] * scale : 0.f;
+    v[j + 1] = dropout_keep_hi(bits, thr16) ? v[j + 1] * scale : 0.f;
+  }
+}
+
+__device__ __forceinline__ void tma_store_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+// TMA reduce-add (fp32) of a smem box into global memory
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 
 }  // namespace tc05

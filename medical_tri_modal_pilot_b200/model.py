@@ -157,7 +157,7 @@ class TRI_MBT_VSLTCLS(nn.Module):
         self.layer_norms_after_concat = nn.LayerNorm(D)
         self.fc_list = nn.Sequential(nn.Linear(2 * D, D), nn.BatchNorm1d(D), self.activations["relu"], nn.Linear(D, 1))
         self._fused = FusedPath(self)
-        self.img_autocast = True     # run the frozen Swin under bf16 autocast (its output feeds a bf16 GEMM anyway)
+        self.img_autocast = True     # run the frozen Swin in bf16 (its output feeds an fp16 tensor-core GEMM anyway)
 
     # -- reference forward contract (tri_mbt_vsltcls.py:167) ----------------------------------------------------
     def forward(self, x, h, m, d, x_m, age, gen, input_lengths, txts, txt_lengths, img, missing, f_indices, img_time,
@@ -200,8 +200,23 @@ class TRI_MBT_VSLTCLS(nn.Module):
             img = img.reshape(-1, 1, 224, 224)
         with torch.no_grad():
             if self.img_autocast:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    f = self.img_encoder(img)
+                f = self._img_encoder_bf16()(img.to(torch.bfloat16))
             else:
                 f = self.img_encoder(img)
         return f.reshape(f.shape[0], 49, 768).to(torch.float16).contiguous()
+
+    def _img_encoder_bf16(self):
+        """bf16 shadow of the frozen image encoder (the fp32 module stays the state_dict master). Pure-bf16 weights
+        avoid autocast's per-op casts and fp32 LayerNorm traffic; rebuilt when the master weights change."""
+        first = self.img_encoder.features[0][0].weight
+        last = self.img_encoder.norm.weight
+        sig = (first.data_ptr(), first._version, last.data_ptr(), last._version, first.device)
+        cached = self.__dict__.get("_img_lp")
+        if cached is None or cached[0] != sig:
+            import copy
+            lp = copy.deepcopy(self.img_encoder).to(device=first.device, dtype=torch.bfloat16).eval()
+            for p in lp.parameters():
+                p.requires_grad_(False)
+            cached = (sig, lp)
+            self.__dict__["_img_lp"] = cached
+        return cached[1]

@@ -15,6 +15,9 @@ Memory plan (all device buffers are allocated once and reused; nothing is alloca
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import numpy as np
 import torch
 
@@ -53,6 +56,9 @@ class FusedPath:
         self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
         self.skip_missing = True
         self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
+        self.debug_trace = None   # dict -> backward() records per-layer input gradients (debugging aid)
+        # img / txt modality streams on side CUDA streams (TMP_B200_SINGLE_STREAM=1 serialises them: debugging aid)
+        self.multi_stream = os.environ.get("TMP_B200_SINGLE_STREAM", "0") != "1"
         self.grad_scale = GRAD_SCALE
 
     # ------------------------------------------------------------------------------------------------------------
@@ -252,20 +258,64 @@ class FusedPath:
         # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
         ctx["txts16"] = txts.reshape(B * 128, 768).to(ACT).contiguous()
         ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(ACT).contiguous()
-        ops.gemm(ctx["img16"], self.H16("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
-        ops.gemm(ctx["txts16"], self.H16("txt_embedding.weight", D, 768), out=self.proj[2],
-                 bias=self.W("txt_embedding.bias", D))
-        for s in range(3):
-            ops.stream_prologue_fwd(X0=self.ws[s]["X"][0], **self._prologue_args(s, ctx))
+        # The three modality streams of a layer are independent until the bottleneck exchange (mbt_encoder.py:744-776):
+        # vslt runs on the caller's stream, img / txt on two side streams, joined at every exchange.
+        self._fork()
+        with self._lane(1):
+            ops.gemm(ctx["img16"], self.H16("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
+            ops.stream_prologue_fwd(X0=self.ws[1]["X"][0], **self._prologue_args(1, ctx))
+        with self._lane(2):
+            ops.gemm(ctx["txts16"], self.H16("txt_embedding.weight", D, 768), out=self.proj[2],
+                     bias=self.W("txt_embedding.bias", D))
+            ops.stream_prologue_fwd(X0=self.ws[2]["X"][0], **self._prologue_args(2, ctx))
+        ops.stream_prologue_fwd(X0=self.ws[0]["X"][0], **self._prologue_args(0, ctx))
         for l in range(NL):
             last = m.vsltonly == 1 and l == NL - 1
-            for s in ([0] if last else [0, 1, 2]):
-                self._layer_fwd(l, s, ctx)
+            if not last:
+                for s in (1, 2):
+                    with self._lane(s):
+                        self._layer_fwd(l, s, ctx)
+            self._layer_fwd(l, 0, ctx)
+            self._join()
             if l == NL - 1:
                 break
             ops.bottleneck_mix_fwd(self.ws[0]["X"][l + 1], self.ws[1]["X"][l + 1], self.ws[2]["X"][l + 1], ctx["missing"])
+            self._fork()
         self.ctx = ctx
         return self.ws[0]["X"][NL][:, 4, :].float()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # stream lanes: lane 0 = the caller's stream, lanes 1/2 = side streams for the img / txt modality streams
+    # ------------------------------------------------------------------------------------------------------------
+    def _lanes_init(self):
+        if getattr(self, "_side", None) is None or self._side_dev != self.device:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._ev_main = torch.cuda.Event()
+            self._ev_side = [torch.cuda.Event() for _ in range(2)]
+            self._side_dev = self.device
+
+    def _lane(self, s):
+        if s == 0 or not self.multi_stream:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self._side[s - 1])
+
+    def _fork(self):
+        """side lanes wait for everything issued so far on the caller's stream"""
+        if not self.multi_stream:
+            return
+        self._lanes_init()
+        self._ev_main.record()
+        for st in self._side:
+            st.wait_event(self._ev_main)
+
+    def _join(self):
+        """the caller's stream waits for everything issued so far on the side lanes"""
+        if not self.multi_stream:
+            return
+        cur = torch.cuda.current_stream()
+        for st, ev in zip(self._side, self._ev_side):
+            ev.record(st)
+            cur.wait_event(ev)
 
     def _layer_fwd(self, l, s, ctx):
         st = self.ws[s]
@@ -293,9 +343,17 @@ class FusedPath:
         self.ws[0]["g_y"][:, 4, :] = (d_cls * self.grad_scale).to(GRD)
         for l in range(NL - 1, -1, -1):
             last = m.vsltonly == 1 and l == NL - 1
-            streams = [0] if last else [0, 1, 2]
-            for s in streams:
-                self._layer_bwd(l, s, ctx)
+            if not last:
+                self._fork()
+                for s in (1, 2):
+                    with self._lane(s):
+                        self._layer_bwd(l, s, ctx)
+            self._layer_bwd(l, 0, ctx)
+            if not last:
+                self._join()
+            if self.debug_trace is not None:       # tools/gpu_grad_trace.py: dL/dX[l] per stream (scaled fp16)
+                for s in ([0] if last else [0, 1, 2]):
+                    self.debug_trace[("dX", l, s)] = self.ws[s]["g_y"].float().div(self.grad_scale).cpu()
             # after _layer_bwd, g_y of each processed stream holds dX[l] (gradient wrt the layer input)
             if l > 0:
                 upper_has_it = 0 if last else 1
@@ -304,18 +362,24 @@ class FusedPath:
             self._range_done(*self.grad_range_of_layer(l))
         # prologue + projections
         F = "fusion_transformer"
-        for s in range(3):
-            a = self._prologue_args(s, ctx)
-            ops.stream_prologue_bwd(dX0=self.ws[s]["g_y"], g_val=self.G("ie_vslt.0.weight", 4, D) if s == 0 else None,
-                                    g_tim=self.G("ie_time.0.weight", 4, D), g_feat=self.G("ie_feat.weight", 20, D),
-                                    g_cls=self.G(f"{F}.cls_token_per_modality.{s}", D),
-                                    g_bott=self.G(f"{F}.bottlenecks", 4, D),
-                                    g_ln=self.G(f"{F}.layer_norms_in.{s}.weight", 2, D),
-                                    dproj=self.g_proj[s], **a)
-        ops.gemm_wgrad(self.g_proj[1], ctx["img16"], self.G("linear.weight", D, 768))
-        ops.colsum(self.g_proj[1], self.G("linear.bias", D))
-        ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768))
-        ops.colsum(self.g_proj[2], self.G("txt_embedding.bias", D))
+        self._fork()
+        for s in (1, 2, 0):
+            with self._lane(s):
+                a = self._prologue_args(s, ctx)
+                ops.stream_prologue_bwd(dX0=self.ws[s]["g_y"],
+                                        g_val=self.G("ie_vslt.0.weight", 4, D) if s == 0 else None,
+                                        g_tim=self.G("ie_time.0.weight", 4, D), g_feat=self.G("ie_feat.weight", 20, D),
+                                        g_cls=self.G(f"{F}.cls_token_per_modality.{s}", D),
+                                        g_bott=self.G(f"{F}.bottlenecks", 4, D),
+                                        g_ln=self.G(f"{F}.layer_norms_in.{s}.weight", 2, D),
+                                        dproj=self.g_proj[s], **a)
+                if s == 1:
+                    ops.gemm_wgrad(self.g_proj[1], ctx["img16"], self.G("linear.weight", D, 768))
+                    ops.colsum(self.g_proj[1], self.G("linear.bias", D))
+                elif s == 2:
+                    ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768))
+                    ops.colsum(self.g_proj[2], self.G("txt_embedding.bias", D))
+        self._join()
         self._range_done(*self.grad_range_of_layer(-1))
         self._publish_grads()
 

@@ -32,3 +32,23 @@ def grad_probe(name, g):
     idx = rng.integers(0, g.size, 32)
     proj = rng.standard_normal(g.size)
     return np.linalg.norm(g), g[idx], float(g @ proj)
+
+
+GEMM_WEIGHT_KEYS = ("_proj.linear.weight", "feed_forward.w_1.weight", "feed_forward.w_2.weight")
+
+
+def fp16_representable(sd):
+    """Copy of a state_dict whose tensor-core GEMM weights (QKV, FFN, the two 768->256 projections) are rounded to
+    fp16-representable values. The B200 path feeds fp16 copies of exactly these tensors to tcgen05 (fp32 masters, fp32
+    biases / LayerNorm parameters), so with such a state_dict the oracle (fp32 math) and the kernels see IDENTICAL
+    weights. Why it matters: on the random-init fixtures the fp32 oracle's own gradients move by up to cos 0.975
+    (layer_stacks.1.0.feed_forward_prenorm.beta) when only these weights are rounded to fp16 -- the sums over tokens
+    cancel heavily, and a weight perturbation is coherent across tokens -- so a gradient comparison at non-identical
+    weights measures that sensitivity, not the kernels."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(GEMM_WEIGHT_KEYS) or k in ("txt_embedding.weight", "linear.weight"):
+            out[k] = v.half().float()
+        else:
+            out[k] = v
+    return out

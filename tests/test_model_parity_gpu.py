@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import fixture_inputs, fixture_names, load_fixture
+from golden_util import fixture_inputs, fixture_names, fp16_representable, load_fixture
 
 pytestmark = pytest.mark.gpu
 LOGIT_RTOL_BF16 = 2e-2
@@ -37,11 +37,12 @@ def test_logits_and_grads(name):
     from oracle import tri_mbt_oracle as O
     fx = load_fixture(name)
     sd, batch, cfg = fixture_inputs(fx)
+    sd = fp16_representable(sd)          # identical weights on both sides (see golden_util.fp16_representable)
     B = batch["x"].shape[0]
     model = build_model(cfg, sd, B)
     model.train()
     out, b = run_model(model, batch)
-    ref = torch.from_numpy(fx["logits"])
+    ref = torch.from_numpy(fx["logits"])  # the reference's own fp32 logits (at the unrounded weights)
     rel = ((out.detach().cpu() - ref).abs().max() / ref.abs().max()).item()
     assert rel < LOGIT_RTOL_BF16, f"logits rel err {rel}"
     loss = torch.nn.BCEWithLogitsLoss()(out.squeeze(), b["y"])

@@ -5,7 +5,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
-from golden_util import fixture_inputs, fixture_names, load_fixture
+from golden_util import fixture_inputs, fixture_names, fp16_representable, load_fixture
 from test_model_parity_gpu import build_model, run_model
 from oracle import tri_mbt_oracle as O
 
@@ -13,9 +13,13 @@ names = sys.argv[1:] or fixture_names()
 for name in names:
     fx = load_fixture(name)
     sd, batch, cfg = fixture_inputs(fx)
+    if os.environ.get("RAW_WEIGHTS") != "1":
+        sd = fp16_representable(sd)
     B = batch["x"].shape[0]
     if torch.cuda.is_available():
         model = build_model(cfg, sd, B).train()
+        if os.environ.get("GRAD_SCALE"):
+            model._fused.grad_scale = float(os.environ["GRAD_SCALE"])
     # oracle with grads wrt cls
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k and "positional" not in k}
     full = dict(sd); full.update(leaves)
@@ -41,7 +45,7 @@ for name in names:
         if np.linalg.norm(r) < 1e-6: continue
         rows.append((float(a @ r / (np.linalg.norm(a) * np.linalg.norm(r) + 1e-30)), k, np.linalg.norm(a), np.linalg.norm(r)))
     rows.sort()
-    for c, k, na, nr in rows[:8]:
+    for c, k, na, nr in rows[:int(os.environ.get("NROWS", "8"))]:
         print(f"   cos {c:.5f} |g| {na:.3e} ref {nr:.3e} {k}")
     print(f"   injected-dCLS grads: min cos {rows[0][0]:.5f} median {np.median([r[0] for r in rows]):.5f} n={len(rows)}")
     model.zero_grad(set_to_none=True)

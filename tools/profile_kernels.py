@@ -1,0 +1,128 @@
+"""Stand-alone launches of every hot kernel at the bench workload's shapes (B=64, T_v=1005, ...), for
+`ncu --set full` captures (two launches per kernel) and for CUDA-event timing tables (--time).
+
+    ncu --set full --clock-control none --import-source on -k regex:'attn|gemm|layernorm|umse|prologue|colsum' \
+        -o gpurun_out/prof python tools/profile_kernels.py
+    python tools/profile_kernels.py --time        # prints a JSON table: kernel, shape, ms, TFLOP/s or GB/s
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from medical_tri_modal_pilot_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--time", action="store_true")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_times.json"))
+    a = ap.parse_args()
+    dev = "cuda"
+    torch.manual_seed(0)
+    B = a.B
+    only = [s for s in a.only.split(",") if s]
+    cases = []
+
+    def add(name, fn, flops=None, bytes_=None, shape=""):
+        if only and not any(s in name for s in only):
+            return
+        cases.append((name, fn, flops, bytes_, shape))
+
+    for T in (1005, 2005, 152, 133):
+        M = B * T
+        Tl = ops.lse_len(T)
+        qkv = (torch.randn(M, 768, device=dev)).half()
+        kv = torch.full((B,), T, device=dev, dtype=torch.int32)
+        O = torch.empty(M, 256, device=dev, dtype=torch.float16)
+        lse = torch.zeros(B, 4, Tl, device=dev)
+        dO = (torch.randn(M, 256, device=dev) * 0.1).half()
+        delta = torch.empty(B, 4, Tl, device=dev)
+        dq = torch.empty(M, 256, device=dev)
+        dqkv = torch.empty(M, 768, device=dev, dtype=torch.float16)
+        f_fwd = 4.0 * T * T * 64 * 4 * B
+        add(f"attn_fwd_T{T}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse: ops.attn_fwd(qkv, kv, B, T, O, lse), f_fwd, None,
+            f"B={B} H=4 T={T} d=64")
+        add(f"attn_bwd_T{T}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, dO=dO, delta=delta, dq=dq, dqkv=dqkv:
+            ops.attn_bwd(qkv, O, dO, kv, B, T, lse, delta, dq, dqkv), 2.5 * f_fwd, None, f"B={B} H=4 T={T} d=64")
+        if T == 2005:
+            continue
+        # GEMMs of one encoder block at this stream length
+        for (nm, N, K, relu) in (("qkv", 768, 256, False), ("ffn1", 1024, 256, True), ("ffn2", 256, 1024, False)):
+            A = torch.randn(M, K, device=dev).half()
+            W = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+            bias = torch.randn(N, device=dev)
+            out = torch.empty(M, N, device=dev, dtype=torch.float16)
+            res = torch.randn(M, N, device=dev).half() if nm == "ffn2" else None
+            add(f"gemm_{nm}_T{T}", lambda A=A, W=W, out=out, bias=bias, relu=relu, res=res:
+                ops.gemm(A, W, out=out, bias=bias, relu=relu, residual=res, drop_p=0.1, seed=1, salt=2),
+                2.0 * M * N * K, None, f"M={M} N={N} K={K}")
+            dY = torch.randn(M, N, device=dev).half()
+            dW = torch.zeros(N, K, device=dev)
+            add(f"wgrad_{nm}_T{T}", lambda dY=dY, A=A, dW=dW: ops.gemm_wgrad(dY, A, dW), 2.0 * M * N * K, None,
+                f"M={M} N={N} K={K}")
+            cs = torch.zeros(N, device=dev)
+            add(f"colsum_{nm}_T{T}", lambda dY=dY, cs=cs: ops.colsum(dY, cs), None, M * N * 2.0, f"M={M} N={N}")
+        x = torch.randn(M, 256, device=dev).half()
+        y = torch.empty_like(x)
+        g = torch.ones(256, device=dev); b = torch.zeros(256, device=dev)
+        add(f"layernorm_fwd_T{T}", lambda x=x, y=y: ops.layernorm_fwd(x, g, b, y), None, M * 256 * 2 * 2.0, f"rows={M}")
+        h = torch.empty_like(x)
+        add(f"layernorm_fwd_add_T{T}", lambda x=x, y=y, h=h: ops.layernorm_fwd(x, g, b, y, add=x, sum_out=h), None,
+            M * 256 * 2 * 4.0, f"rows={M}")
+        dx = torch.empty_like(x); dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
+        add(f"layernorm_bwd_T{T}", lambda x=x, dx=dx: ops.layernorm_bwd(x, x, x, g, dx, dg, db), None,
+            M * 256 * 2 * 4.0, f"rows={M}")
+    # UMSE embedding at >= 512k tokens (stable HBM figure), 12 B in + 512 B fp16 out per token
+    n_tok = 1 << 20
+    xt = torch.empty(n_tok, 3, device=dev)
+    xt[:, 0] = -torch.rand(n_tok, device=dev) * 24; xt[:, 1] = torch.rand(n_tok, device=dev)
+    xt[:, 2] = torch.randint(0, 18, (n_tok,), device=dev).float()
+    mk = lambda: [torch.randn(256, device=dev), torch.randn(256, device=dev), torch.ones(256, device=dev),
+                  torch.zeros(256, device=dev)]
+    v4, t4 = mk(), mk()
+    Wf = torch.randn(20, 256, device=dev)
+    add("umse_embed_fwd_1M", lambda: ops.umse_embed(xt, v4, t4, Wf, torch.float16), None, n_tok * 524.0,
+        f"tokens={n_tok}")
+
+    results = []
+    for name, fn, flops, bytes_, shape in cases:
+        fn()
+        if not a.time:
+            fn()
+            continue
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        r = {"kernel": name, "shape": shape, "ms": round(ms, 4)}
+        if flops:
+            r["tflops"] = round(flops / ms / 1e9, 1)
+        if bytes_:
+            r["gbs"] = round(bytes_ / ms / 1e6, 1)
+        results.append(r)
+        print(json.dumps(r), flush=True)
+    torch.cuda.synchronize()
+    if a.time:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        with open(a.out, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
