@@ -74,7 +74,7 @@ int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const flo
                       void* stream);
 
 /* ---- a10/a11: tcgen05 GEMMs -------------------------------------------------------------------------------
- * out[M,N] = residual + dropout( gate>0 ? relu?(alpha * A[M,K].B[N,K]^T + bias) : 0 )
+ * out[M,N] = residual + dropout( gate>0 ? act(alpha * A[M,K].B[N,K]^T + bias) : 0 ),  act = relu: 0 none, 1 ReLU, 2 GELU(erf)
  * A, B 16-bit K-major, both fp16 or both bf16 (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70,
  * module.py:74-80; dgrad passes the gradient as A and the transposed weight copy as B).
  * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out16 (in out_fmt) and/or out_f32 get the result. */
@@ -117,6 +117,27 @@ int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* 
  * flat fp32 parameter / gradient buffers of the fused path: w,g,m,v fp32 [n], n % 4 == 0; step >= 1. ---------- */
 int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, void* stream);
+
+/* ---- image-encoder feed: the glue of the frozen Swin-T forward around the tcgen05 GEMMs
+ * (reference builder/models/src/swin_transformer.py: patch embedding :541-551, SwinTransformerBlock.forward :447-450,
+ * shifted_window_attention :115-214, PatchMerging :34-46,75-86). Activations fp16 [tokens, Cp] (Cp = padded channel
+ * stride, pad channels zero); LayerNorm parameters fp32; n_img images; H x W token map; C real channels. -------------- */
+/* img fp32 [n_img,224,224]; Wt [16,96] = conv weight transposed (pixel-major); out [n_img*56*56, Cp] */
+int tmp_swin_patch_embed_ln(const float* img, int n_img, const float* Wt, const float* bconv, const float* g,
+                            const float* b, void* out, int Cp, void* stream);
+/* out[window order] = LayerNorm(x[natural order]) after torch.roll(-shift) and window partition (7x7 windows) */
+int tmp_swin_ln_window(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp, int shift,
+                       void* out, void* stream);
+/* qkv [tokens(window order), ld_qkv] = q|k|v (head h at h*32 inside each C-wide part); rel_bias fp32 [heads,49,49];
+ * out [tokens(window order), ld_out] */
+int tmp_swin_window_attn(const void* qkv, int ld_qkv, const float* rel_bias, int n_img, int H, int W, int C, int heads,
+                         int shift, void* out, int ld_out, void* stream);
+/* x[natural] += y[window order] (window reverse + reverse shift); hn = LayerNorm(x) unless hn == NULL */
+int tmp_swin_unwindow_add_ln(const void* y, void* x, const float* g, const float* b, int n_img, int H, int W, int C,
+                             int Cp, int shift, void* hn, void* stream);
+/* out[(n,i,j), 4C] = LayerNorm(x0|x1|x2|x3) of the 2x2 neighbourhood (PatchMerging), out stride 4C */
+int tmp_swin_merge_ln(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp, void* out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

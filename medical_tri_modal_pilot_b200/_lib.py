@@ -39,6 +39,11 @@ SIGNATURES = {
     "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp],
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
+    "tmp_swin_patch_embed_ln": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "tmp_swin_ln_window": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "tmp_swin_window_attn": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "tmp_swin_unwindow_add_ln": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "tmp_swin_merge_ln": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"tmp_last_error": C.c_char_p}
 

@@ -25,7 +25,7 @@ struct EpiParams {
   int M, N, K;
   float alpha;            // scale on the accumulator
   const float* bias;      // [N] fp32 or null
-  int relu;               // apply ReLU after bias
+  int relu;               // activation after bias: 0 none, 1 ReLU, 2 GELU (erf)
   const uint16_t* gate;   // [M, ld_gate] 16-bit: multiply by (gate > 0)  (ReLU backward) or null
   int ld_gate;
   const uint16_t* residual;  // [M, ld_res] 16-bit, added last, or null
@@ -75,9 +75,12 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
       }
     }
   }
-  if (p.relu) {
+  if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (p.relu == 2) {   // exact (erf) GELU: nn.GELU() of the Swin MLP
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
   }
   if (p.gate && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);

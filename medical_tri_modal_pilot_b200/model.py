@@ -157,6 +157,7 @@ class TRI_MBT_VSLTCLS(nn.Module):
         self.layer_norms_after_concat = nn.LayerNorm(D)
         self.fc_list = nn.Sequential(nn.Linear(2 * D, D), nn.BatchNorm1d(D), self.activations["relu"], nn.Linear(D, 1))
         self._fused = FusedPath(self)
+        self.native_swin = True      # frozen image encoder through swin_feed.SwinFeed (False: stock torchvision forward)
         self.img_autocast = True     # run the frozen Swin in bf16 (its output feeds an fp16 tensor-core GEMM anyway)
 
     # -- reference forward contract (tri_mbt_vsltcls.py:167) ----------------------------------------------------
@@ -199,11 +200,28 @@ class TRI_MBT_VSLTCLS(nn.Module):
         if self.multiimages == 1:
             img = img.reshape(-1, 1, 224, 224)
         with torch.no_grad():
+            if self.native_swin:
+                return self._swin_feed()(img)                  # sm_100a kernels (swin_feed.py), fp16 [N,49,768]
             if self.img_autocast:
                 f = self._img_encoder_bf16()(img.to(torch.bfloat16))
             else:
                 f = self.img_encoder(img)
         return f.reshape(f.shape[0], 49, 768).to(torch.float16).contiguous()
+
+    def _swin_sig(self):
+        first = self.img_encoder.features[0][0].weight
+        last = self.img_encoder.norm.weight
+        return (first.data_ptr(), first._version, last.data_ptr(), last._version, first.device)
+
+    def _swin_feed(self):
+        """B200-native forward of the frozen image encoder; fp16 weight copies rebuilt when the master weights change."""
+        sig = self._swin_sig()
+        cached = self.__dict__.get("_swin_native")
+        if cached is None or cached[0] != sig:
+            from .swin_feed import SwinFeed
+            cached = (sig, SwinFeed(self.img_encoder))
+            self.__dict__["_swin_native"] = cached
+        return cached[1]
 
     def _img_encoder_bf16(self):
         """bf16 shadow of the frozen image encoder (the fp32 module stays the state_dict master). Pure-bf16 weights

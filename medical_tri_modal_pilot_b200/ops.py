@@ -172,3 +172,31 @@ def adamw_step(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
         _cuda_contig(t, torch.float32, nm)
     check(_lib.load().tmp_adamw_step(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), float(lr), float(beta1), float(beta2),
                                      float(eps), float(weight_decay), int(step), stream_ptr()), "tmp_adamw_step")
+
+
+# ---- image-encoder feed (csrc/swin.cu) -------------------------------------------------------------------------
+def swin_patch_embed_ln(img, Wt, bconv, g, b, out, Cp):
+    n_img = img.numel() // (224 * 224)
+    _cuda_contig(img, torch.float32, "img")
+    check(_lib.load().tmp_swin_patch_embed_ln(ptr(img), n_img, ptr(Wt), ptr(bconv), ptr(g), ptr(b), ptr(out), Cp,
+                                              stream_ptr()), "tmp_swin_patch_embed_ln")
+
+
+def swin_ln_window(x, g, b, n_img, H, C, Cp, shift, out):
+    check(_lib.load().tmp_swin_ln_window(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, shift, ptr(out), stream_ptr()),
+          "tmp_swin_ln_window")
+
+
+def swin_window_attn(qkv, rel_bias, n_img, H, C, heads, shift, out):
+    check(_lib.load().tmp_swin_window_attn(ptr(qkv), qkv.shape[-1], ptr(rel_bias), n_img, H, H, C, heads, shift, ptr(out),
+                                           out.shape[-1], stream_ptr()), "tmp_swin_window_attn")
+
+
+def swin_unwindow_add_ln(y, x, g, b, n_img, H, C, Cp, shift, hn):
+    check(_lib.load().tmp_swin_unwindow_add_ln(ptr(y), ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, shift, ptr(hn),
+                                               stream_ptr()), "tmp_swin_unwindow_add_ln")
+
+
+def swin_merge_ln(x, g, b, n_img, H, C, Cp, out):
+    check(_lib.load().tmp_swin_merge_ln(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, ptr(out), stream_ptr()),
+          "tmp_swin_merge_ln")

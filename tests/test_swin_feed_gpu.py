@@ -1,0 +1,149 @@
+"""GPU parity of the B200-native image-encoder feed (swin_feed.SwinFeed + csrc/swin.cu) against the stock torchvision
+Swin-T module the reference uses (builder/models/src/swin_transformer.py is a patched torchvision copy), fp32 eval mode,
+identical weights. Tolerance: 16-bit activations through 12 blocks -> 2e-2 of the output range, rmse 1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _randomised_swin(seed=0):
+    from medical_tri_modal_pilot_b200.model import build_swin_t_m
+    torch.manual_seed(seed)
+    m = build_swin_t_m().cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(seed + 1)
+    with torch.no_grad():                      # make every bias / LayerNorm / rel-pos term matter
+        for n, p in m.named_parameters():
+            if n.endswith("relative_position_bias_table"):
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda") * 0.5)
+            elif p.dim() == 1 and "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g, device="cuda"))
+            elif p.dim() == 1:
+                p.copy_(0.2 * torch.randn(p.shape, generator=g, device="cuda"))
+            elif p.dim() == 2:
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda") / p.shape[1] ** 0.5)
+    return m
+
+
+def _err(a, r):
+    a, r = a.float(), r.float()
+    return ((a - r).abs().max() / r.abs().max()).item(), ((a - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
+
+
+def test_glue_kernels_match_torch():
+    from medical_tri_modal_pilot_b200 import ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    for (C, Cp, H, shift) in [(96, 128, 56, 3), (96, 128, 56, 0), (192, 256, 28, 3), (384, 384, 14, 3), (768, 768, 7, 0)]:
+        N = 3
+        x = torch.zeros(N, H, H, Cp, device=dev, dtype=torch.float16)
+        x[..., :C] = torch.randn(N, H, H, C, device=dev).half()
+        g = 1 + 0.1 * torch.randn(C, device=dev); b = 0.1 * torch.randn(C, device=dev)
+        out = torch.full((N * H * H, Cp), 7.0, device=dev, dtype=torch.float16)
+        ops.swin_ln_window(x, g, b, N, H, C, Cp, shift, out)
+        ref = F.layer_norm(x[..., :C].float(), (C,), g, b, 1e-5)
+        if shift:
+            ref = torch.roll(ref, shifts=(-shift, -shift), dims=(1, 2))
+        nW = H // 7
+        ref = ref.view(N, nW, 7, nW, 7, C).permute(0, 1, 3, 2, 4, 5).reshape(N * H * H, C)
+        assert _err(out[:, :C], ref)[0] < 2e-3, (C, H, shift)
+        assert (out[:, C:] == 0).all()
+        # inverse: window reverse + unshift + residual (+ LN)
+        y = torch.zeros(N * H * H, Cp, device=dev, dtype=torch.float16)
+        y[:, :C] = torch.randn(N * H * H, C, device=dev).half()
+        x2 = x.clone(); hn = torch.empty_like(out)
+        ops.swin_unwindow_add_ln(y, x2, g, b, N, H, C, Cp, shift, hn)
+        yr = y[:, :C].float().view(N, nW, nW, 7, 7, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H, H, C)
+        if shift:
+            yr = torch.roll(yr, shifts=(shift, shift), dims=(1, 2))
+        xr = x[..., :C].float() + yr
+        assert _err(x2[..., :C], xr)[0] < 2e-3
+        assert _err(hn[:, :C], F.layer_norm(x2[..., :C].float(), (C,), g, b, 1e-5).reshape(-1, C))[0] < 2e-3
+        assert (x2[..., C:] == 0).all() and (hn[:, C:] == 0).all()
+        if H > 7:
+            from torchvision.models.swin_transformer import _patch_merging_pad
+            g4 = 1 + 0.1 * torch.randn(4 * C, device=dev); b4 = 0.1 * torch.randn(4 * C, device=dev)
+            mg = torch.empty(N * (H // 2) ** 2, 4 * C, device=dev, dtype=torch.float16)
+            ops.swin_merge_ln(x, g4, b4, N, H, C, Cp, mg)
+            refm = F.layer_norm(_patch_merging_pad(x[..., :C].float()), (4 * C,), g4, b4, 1e-5).reshape(-1, 4 * C)
+            assert _err(mg, refm)[0] < 2e-3
+
+
+def test_window_attention_matches_torchvision():
+    from medical_tri_modal_pilot_b200 import ops
+    torch.manual_seed(2)
+    dev = "cuda"
+    for (C, heads, H, shift) in [(96, 3, 56, 3), (96, 3, 56, 0), (192, 6, 28, 3), (768, 24, 7, 3)]:
+        N = 2
+        nq = (3 * C + 127) // 128 * 128
+        Cp = (C + 127) // 128 * 128
+        rel = torch.randn(heads, 49, 49, device=dev) * 0.5
+        qkv_nat = torch.randn(N, H, H, 3 * C, device=dev).half().float()
+        # direct restatement (roll, partition, attention with bias + mask, reverse) on the q|k|v tensor
+        s_eff = shift if H > 7 else 0
+        t = torch.roll(qkv_nat, shifts=(-s_eff, -s_eff), dims=(1, 2)) if s_eff else qkv_nat
+        nW = H // 7
+        tw = t.view(N, nW, 7, nW, 7, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(N * nW * nW, 49, 3, heads, 32)
+        q, k, v = tw.permute(2, 0, 3, 1, 4)
+        attn = (q * 32 ** -0.5) @ k.transpose(-2, -1) + rel.unsqueeze(0)
+        if s_eff:
+            m = torch.zeros(H, H, device=dev)
+            cnt = 0
+            for hs in ((0, -7), (-7, -s_eff), (-s_eff, None)):
+                for wsl in ((0, -7), (-7, -s_eff), (-s_eff, None)):
+                    m[hs[0]:hs[1], wsl[0]:wsl[1]] = cnt
+                    cnt += 1
+            m = m.view(nW, 7, nW, 7).permute(0, 2, 1, 3).reshape(nW * nW, 49)
+            am = m.unsqueeze(1) - m.unsqueeze(2)
+            am = am.masked_fill(am != 0, -100.0)
+            attn = (attn.view(N, nW * nW, heads, 49, 49) + am.unsqueeze(1).unsqueeze(0)).view(-1, heads, 49, 49)
+        refw = (attn.softmax(-1) @ v).transpose(1, 2).reshape(N * H * H, C)
+        qkv_w = torch.zeros(N * H * H, nq, device=dev, dtype=torch.float16)
+        qkv_w[:, : 3 * C] = tw.reshape(N * H * H, 3 * C).half()
+        out = torch.zeros(N * H * H, Cp, device=dev, dtype=torch.float16)
+        ops.swin_window_attn(qkv_w, rel.contiguous(), N, H, C, heads, shift, out)
+        e = _err(out[:, :C], refw)
+        assert e[0] < 5e-3, (C, heads, H, shift, e)
+
+
+def test_gemm_gelu_epilogue():
+    from medical_tri_modal_pilot_b200 import ops
+    torch.manual_seed(3)
+    A = torch.randn(1000, 128, device="cuda").half(); W = (torch.randn(384, 128, device="cuda") / 11).half()
+    bias = torch.randn(384, device="cuda")
+    out = torch.empty(1000, 384, device="cuda", dtype=torch.float16)
+    ops.gemm(A, W, out=out, bias=bias, relu=2)
+    assert _err(out, F.gelu(A.float() @ W.float().t() + bias))[0] < 3e-3
+
+
+@pytest.mark.parametrize("n_img", [2, 5])
+def test_swin_feed_matches_stock_module(n_img):
+    from medical_tri_modal_pilot_b200.swin_feed import SwinFeed
+    m = _randomised_swin()
+    img = torch.rand(n_img, 1, 224, 224, device="cuda")
+    with torch.no_grad():
+        ref = m(img).reshape(n_img, 49, 768)
+    got = SwinFeed(m)(img)
+    mx, rm = _err(got, ref)
+    assert torch.isfinite(got.float()).all()
+    assert mx < 2e-2 and rm < 1e-2, (mx, rm)
+
+
+def test_model_uses_native_feed_and_matches_stock_path():
+    """TRI_MBT_VSLTCLS.encode_images: native feed vs the stock bf16 torchvision forward on the same frozen weights."""
+    from medical_tri_modal_pilot_b200.config import make_args
+    from builder.models import get_model
+    args = make_args(transformer_num_layers=2, multiimages=1, mbt_only_vslt=1, input_types="vslt_img_txt", imgtxt_time=1,
+                     dropout=0.0, batch_size=2, img_pretrain="No")
+    args.device = torch.device("cuda")
+    torch.manual_seed(0)
+    model = get_model(args)(args).cuda()
+    img = torch.rand(2, 3, 1, 224, 224, device="cuda")
+    assert model.native_swin
+    a = model.encode_images(img, None).float()
+    model.native_swin = False
+    model.img_autocast = False
+    r = model.encode_images(img, None).float()
+    mx, rm = _err(a, r)
+    assert a.shape == (6, 49, 768) and mx < 2e-2 and rm < 1e-2, (mx, rm)
