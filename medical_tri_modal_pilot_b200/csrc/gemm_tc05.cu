@@ -7,6 +7,8 @@
 // Warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
 // (TMEM -> registers -> fused bias/ReLU/dropout/residual -> global). Accumulators are double-buffered in TMEM
 // so the epilogue of tile i overlaps the MMAs of tile i+1; the kernel is persistent over output tiles.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -40,18 +42,47 @@ struct EpiParams {
   int ld_out;
 };
 
-template <int BN>
+// WS ("weight-stationary") variant: for K <= kWsMaxK the whole B operand of an n-block ([BN x K], <= 128 KB) is loaded ONCE per
+// CTA and stays in shared memory while the CTA walks over m-tiles of that n-block; the TMA ring then carries A tiles only.
+// At K = 256 a [128 x 256] output tile needs 64 KB (A) instead of 192 KB (A + B) from L2 -- the non-stationary kernel is
+// bound by that L2 -> SM operand traffic (profiles/r1b: 24 % tensor-pipe active at 4.8 TB/s of operand reads).
+template <int BN, bool WS>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 3 : 4;
+  static constexpr int kWsMaxK = (BN == 256) ? 256 : 512;
+  static constexpr int kStages = WS ? 4 : ((BN == 256) ? 3 : 4);
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutOffset = kStages * kStageBytes;            // per epilogue warp: 2 x [32 rows x 128 B]
-  static constexpr int kOutBytes = kEpiWarps * 2 * 4096;
+  static constexpr int kBBytes = BN * BK * 2;                          // one 64-wide K slice of B
+  static constexpr int kBResBytes = WS ? BN * kWsMaxK * 2 : 0;         // resident B (WS): K/64 slices
+  static constexpr int kRingOffset = kBResBytes;
+  static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
+  static constexpr int kOutOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kOutBufs = WS ? 1 : 2;                          // per epilogue warp: [32 rows x 128 B] boxes
+  static constexpr int kOutBytes = kEpiWarps * kOutBufs * 4096;
   static constexpr int kBiasOffset = kOutOffset + kOutBytes;
-  static constexpr int kBarOffset = kBiasOffset + kBiasSmemFloats * 4;
+  static constexpr int kBiasFloats = WS ? BN : kBiasSmemFloats;
+  static constexpr int kBarOffset = kBiasOffset + kBiasFloats * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
+static_assert(SmemLayout<256, true>::kTotal <= 232448 && SmemLayout<128, true>::kTotal <= 232448, "WS smem budget");
+
+// erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 output rounding):
+// erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z >= 0. ~15 instructions (2 MUFU) instead of the ~45 of
+// erff(): the FC1 epilogue of the image encoder touches 1.1 G elements per step and was instruction-bound on erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float q = poly * t * e;                    // 1 - erf(|z|)  in (0, 1]
+  const float h = 0.5f * x;
+  // x >= 0: 0.5 x (2 - q);  x < 0: 0.5 x q
+  return x >= 0.f ? fmaf(-h, q, x) : h * q;
+}
 
 // Epilogue of one 32-column chunk held by one thread (= one output row): v <- fused epilogue of the accumulators.
 __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p, const float* sbias, int row, bool row_ok,
@@ -78,9 +109,9 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
   if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (p.relu == 2) {   // exact (erf) GELU: nn.GELU() of the Swin MLP
+  } else if (p.relu == 2) {   // erf GELU (nn.GELU() of the Swin MLP): 0.5 x (1 + erf(x / sqrt 2))
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
   if (p.gate && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);
@@ -118,11 +149,11 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
   }
 }
 
-template <int BN>
+template <int BN, bool WS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, EpiParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, WS>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,16 +161,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;         // WS: resident B landed
+  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
   float* sbias = (float*)(smem + L::kBiasOffset);
+  uint8_t* ring = smem + L::kRingOffset;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_blks = (p.M + BM - 1) / BM;
   const int n_blks = p.N / BN;
   const int k_blks = p.K / BK;
-  const int num_tiles = m_blks * n_blks;
-  const bool bias_in_smem = p.bias && p.N <= kBiasSmemFloats;
+  // tile walk. non-WS: tile = blockIdx.x, += gridDim.x over all (m, n) tiles. WS: this CTA owns n-block
+  // blockIdx.x % n_blks and walks m-blocks blockIdx.x / n_blks, += gridDim.x / n_blks (gridDim.x % n_blks == 0).
+  const int it_first = WS ? (int)blockIdx.x / n_blks : (int)blockIdx.x;
+  const int it_step = WS ? (int)gridDim.x / n_blks : (int)gridDim.x;
+  const int it_end = WS ? m_blks : m_blks * n_blks;
+  const int n_fixed = WS ? ((int)blockIdx.x % n_blks) * BN : 0;
+  const bool bias_in_smem = p.bias && (WS || p.N <= kBiasSmemFloats);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -153,10 +191,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (bias_in_smem)
-    for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i];
+  if (bias_in_smem) {
+    if (WS) {
+      for (int i = threadIdx.x; i < BN; i += kThreads) sbias[i] = p.bias[n_fixed + i];
+    } else {
+      for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i];
+    }
+  }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
@@ -166,17 +210,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (WS) {
+        mbar_expect_tx(bres_bar, (uint32_t)(k_blks * L::kBBytes));
+        for (int kb = 0; kb < k_blks; ++kb) tma_load_2d(smem + kb * L::kBBytes, &tmB, bres_bar, kb * BK, n_fixed);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blks) * BM, n0 = (tile % n_blks) * BN;
+      for (int it = it_first; it < it_end; it += it_step) {
+        const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
+          uint8_t* sa = ring + stage * L::kStageBytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (!WS) tma_load_2d(sa + L::kABytes, &tmB, &full_bar[stage], kb * BK, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -189,15 +236,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (WS) {
+        mbar_wait(bres_bar, 0);
+        tc_fence_after();
+      }
+      for (int it = it_first; it < it_end; it += it_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint32_t sa = smem_u32(ring + stage * L::kStageBytes);
+          const uint32_t sb = WS ? smem_u32(smem + kb * L::kBBytes) : sa + L::kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_sdesc_sw128(sa + k * 32, 16, 1024);
@@ -216,18 +267,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // warp -> (TMEM lane quarter it may access, column half of the tile). Each thread owns one output row and walks
     // BN/2 columns in 32-column chunks; TMEM loads are software-pipelined one chunk ahead; 16-bit results are staged in
     // 128B-swizzled smem boxes of [32 rows x 64 cols] and written with TMA stores (coalesced, asynchronous, M-tail
-    // clipped by the tensor map), double-buffered per warp.
+    // clipped by the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B).
     const int e = warp - 2;
     const int quarter = warp & 3;
     const int half = e >> 2;
     constexpr int kChunks = BN / 64;   // 32-column chunks per warp
-    uint8_t* stage_buf = smem + L::kOutOffset + e * 8192;
-    const float* sb_ptr = bias_in_smem ? sbias : nullptr;
+    uint8_t* stage_buf = smem + L::kOutOffset + e * (L::kOutBufs * 4096);
+    const float* sb_ptr = bias_in_smem ? sbias - n_fixed : nullptr;
     int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blks) * BM, n0 = (tile % n_blks) * BN;
+    for (int it = it_first; it < it_end; it += it_step) {
+      const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
@@ -259,8 +310,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.out) {
           uint8_t* sbox = stage_buf + sbuf * 4096;
           if ((c & 1) == 0) {
-            // the TMA store issued two boxes ago must have finished reading this buffer
-            if (lane == 0) tma_store_wait_read1();
+            // the TMA store that last used this buffer must have finished reading it
+            if (lane == 0) {
+              if (L::kOutBufs == 2) tma_store_wait_read1();
+              else tma_store_wait_read0();
+            }
             __syncwarp();
           }
 #pragma unroll
@@ -279,7 +333,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_2d(&tmOut, sbox, colw + (c - 1) * 32, m0 + quarter * 32);
               tma_store_commit();
             }
-            sbuf ^= 1;
+            if (L::kOutBufs == 2) sbuf ^= 1;
           }
         }
       }
@@ -418,20 +472,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, bool WS>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const EpiParams& p, int grid,
               cudaStream_t st) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, WS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) {
       tmp::set_error("cudaFuncSetAttribute(gemm_tn): %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  gemm_tn_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmOut, p);
+  gemm_tn_kernel<BN, WS><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmOut, p);
   return tmp::check_launch("gemm_tn_kernel");
 }
 
@@ -509,9 +563,18 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
     tmOut = tmA;
   }
   const int tiles = m_blks * (N / BN);
+  const int n_blks = N / BN;
+  // weight-stationary variant: worth it once every CTA amortises its resident B over >= 2 m-tiles
+  static const bool ws_off = getenv("TMP_B200_GEMM_NO_WS") != nullptr;
+  const int ws_max_k = BN == 256 ? SmemLayout<256, true>::kWsMaxK : SmemLayout<128, true>::kWsMaxK;
+  if (!ws_off && K <= ws_max_k && n_blks <= sms && tiles >= 2 * sms) {
+    const int grid = (sms / n_blks) * n_blks;
+    if (BN == 256) return launch_tn<256, true>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+    return launch_tn<128, true>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+  }
   const int grid = tiles < sms ? tiles : sms;
-  if (BN == 256) return launch_tn<256>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
-  return launch_tn<128>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+  if (BN == 256) return launch_tn<256, false>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+  return launch_tn<128, false>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
 }
 
 extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
