@@ -21,11 +21,13 @@ using namespace tc05;
 
 namespace {
 
-constexpr int kComputeWarps = 8;
+constexpr int kComputeWarps = 16;  // 4 per TMEM lane quarter: each owns 16 of the 64 query columns of a half-step
+constexpr int kFlushWarps = 8;     // compute warps 0..7 also move dQ / dK / dV out of TMEM (32 columns each)
 constexpr int kThreads = 64 + 32 * kComputeWarps;
 constexpr int BT = 128;  // tile rows (keys per CTA, queries per iteration)
 constexpr int HD = 64;
-constexpr int kStages = 2;
+constexpr int kStages = 3;   // Q_i / dO_i ring: a stage is released when dV/dK of tile i retire; 2 stages left every tile
+                             // waiting a full TMA round trip
 constexpr int kTile = BT * HD * 2;   // 16 KB : [128 rows x 64 fp16]
 constexpr int kSq = BT * BT * 2;     // 32 KB : [128 x 128] fp16 as two 64-column sub-tiles
 constexpr int kStatBytes = 2 * BT * 4;  // lse[128] | delta[128] fp32 per ring stage
@@ -34,10 +36,9 @@ constexpr int kSmemK = 0;
 constexpr int kSmemV = kSmemK + kTile;
 constexpr int kSmemQ = kSmemV + kTile;
 constexpr int kSmemDO = kSmemQ + kStages * kTile;
-constexpr int kSmemPT = kSmemDO + kStages * kTile;
-constexpr int kSmemDST = kSmemPT + kSq;
+constexpr int kSmemDST = kSmemDO + kStages * kTile;   // dS^T only: P^T lives in TMEM (A operand of dV)
 constexpr int kSmemDQ = kSmemDST + kSq;                   // per compute warp: [32 rows x 32 fp32], 128B swizzle
-constexpr int kSmemStat = kSmemDQ + kComputeWarps * 4096;
+constexpr int kSmemStat = kSmemDQ + kFlushWarps * 4096;
 constexpr int kSmemBar = kSmemStat + kStages * kStatBytes;
 constexpr int kSmemTotal = kSmemBar + 256 + 1024;
 
@@ -65,7 +66,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
                 uint16_t* __restrict__ dQKV, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   Bars* bars = (Bars*)(smem + kSmemBar);
 
   const int warp = threadIdx.x >> 5;
@@ -108,7 +109,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&bars->pds_full[s], kComputeWarps);
     }
     mbar_init(&bars->dq_full, 1);
-    mbar_init(&bars->dq_empty, kComputeWarps);
+    mbar_init(&bars->dq_empty, kFlushWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_slot, 512);
@@ -121,6 +122,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_DV = tmem_base + 256;
   const uint32_t tm_DK = tmem_base + 320;
   const uint32_t tm_DQ = tmem_base + 384;
+  const uint32_t tm_PT = tmem_base + 448;   // [2] x 32 columns: P^T halves as packed fp16 (64 queries = 32 columns)
   const size_t stat_base = ((size_t)b * H + h) * T_lse;
 
   if (warp == 0) {
@@ -148,9 +150,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t idesc_kv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV += P^T dO, dK += dS^T Q (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(BT, HD, 1, 1, FMT_F16, FMT_F16);  // dQ   = dS K     (A, B MN-major)
       const uint32_t sK = smem_u32(smem + kSmemK), sV = smem_u32(smem + kSmemV);
-      const uint32_t sPT = smem_u32(smem + kSmemPT), sDST = smem_u32(smem + kSmemDST);
+      const uint32_t sDST = smem_u32(smem + kSmemDST);
       auto issue_sdp = [&](int i, int hh) {   // S^T_hh(i), dP^T_hh(i)
-        const int st = i & 1;
+        const int st = i % kStages;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile) + hh * 8192;    // 64 query rows = 8192 B
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile) + hh * 8192;
 #pragma unroll
@@ -164,13 +166,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         umma_commit(&bars->sdp_full[hh]);
       };
       auto issue_dvdk = [&](int i, int hh) {  // dV += P^T_hh dO_i[hh], dK += dS^T_hh Q_i[hh]  (reduction over 64 queries)
-        const int st = i & 1;
+        const int st = i % kStages;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile);
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tm_DV, make_sdesc_sw128(sPT + hh * (BT * 128) + k * 32, 16, 1024),
-                  make_sdesc_sw128(sDO + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv, (i | hh | k) != 0);
+          umma_ts(tm_DV, tm_PT + hh * 32 + k * 8, make_sdesc_sw128(sDO + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv,
+                  (i | hh | k) != 0);   // A = P^T_hh from TMEM: 16 queries = 8 packed columns per K step
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tm_DK, make_sdesc_sw128(sDST + hh * (BT * 128) + k * 32, 16, 1024),
@@ -189,7 +191,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_after();
         issue_dvdk(i, 0);
         if (more) {
-          mbar_wait(&bars->qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+          mbar_wait(&bars->qdo_full[(i + 1) % kStages], ((i + 1) / kStages) & 1);
           tc_fence_after();
           issue_sdp(i + 1, 0);
         }
@@ -206,7 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_ss(tm_DQ, make_sdesc_sw128(sDST + k * 2048, BT * 128, 1024),
                   make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
         umma_commit(&bars->dq_full);
-        umma_commit(&bars->qdo_empty[i & 1]);
+        umma_commit(&bars->qdo_empty[i % kStages]);
         if (more) issue_sdp(i + 1, 1);
       }
     }
@@ -214,13 +216,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ===================== compute warps =====================
     const int cw = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int colhalf = cw >> 2;        // which 32 of the 64 columns of a half-step / of the 64 dQ,dK,dV columns
+    const int colq = cw >> 2;           // which 16 of the 64 query columns of a half-step (S^T / dP^T)
+    const int colhalf = (cw >> 2) & 1;  // flush warps (cw < 8): which 32 of the 64 dQ / dK / dV columns
+    const bool flusher = cw < kFlushWarps;
     const int r = quarter * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dK/dV, query row for dQ
     const bool key_ok = (k0 + r) < len;
     const bool key_tile_partial = (k0 + BT) > len;
-    uint8_t* sPT = smem + kSmemPT;
     uint8_t* sDST = smem + kSmemDST;
-    uint8_t* sDQ = smem + kSmemDQ + cw * 4096;
+    uint8_t* sDQ = smem + kSmemDQ + (cw & (kFlushWarps - 1)) * 4096;
 
     auto dq_flush = [&](int i) {   // dQ(i): TMEM -> swizzled smem box -> TMA reduce-add into the fp32 accumulator
       mbar_wait(&bars->dq_full, i & 1);
@@ -247,28 +250,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     };
 
     for (int i = 0; i < n_q; ++i) {
-      const int st = i & 1;
+      const int st = i % kStages;
       const float* st_lse = (const float*)(smem + kSmemStat + st * kStatBytes);
       const float* st_dl = st_lse + BT;
       const bool need_mask = key_tile_partial || (i * BT + BT > len);
-      if (i == 0 || true) {
+      {
         // the ring stage (Q_i, dO_i, lse_i, delta_i) is complete before the MMA warp could issue S^T(i); observing
         // it here orders our generic-proxy reads of lse/delta after the bulk copies.
-        mbar_wait(&bars->qdo_full[st], (i >> 1) & 1);
+        mbar_wait(&bars->qdo_full[st], (i / kStages) & 1);
       }
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         mbar_wait(&bars->sdp_full[hh], i & 1);
         tc_fence_after();
-        uint32_t s[32], dp[32];
-        tmem_ld32(tmem_addr(tm_ST + hh * 64, quarter * 32, colhalf * 32), s);
-        tmem_ld32(tmem_addr(tm_DPT + hh * 64, quarter * 32, colhalf * 32), dp);
+        uint32_t s[16], dp[16];
+        tmem_ld16(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), s);
+        tmem_ld16(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dp);
         tmem_ld_wait();
-        const int qc0 = hh * 64 + colhalf * 32;   // first query column (within the 128-query tile) of this thread's run
-        uint32_t pp[16], dd[16];
+        const int qc0 = hh * 64 + colq * 16;   // first query column (within the 128-query tile) of this thread's run
+        uint32_t pp[8], dd[8];
         if (!need_mask) {
 #pragma unroll
-          for (int t = 0; t < 32; t += 4) {
+          for (int t = 0; t < 16; t += 4) {
             const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
             const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
             const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -285,7 +288,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         } else {
 #pragma unroll
-          for (int t = 0; t < 32; t += 2) {
+          for (int t = 0; t < 16; t += 2) {
             float p[2], d[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -300,28 +303,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         }
         if (hh == 0 && i > 0) {
-          // P^T / dS^T smem (both halves) may be overwritten only after the MMAs of iteration i-1 have retired
+          // P^T (TMEM) / dS^T (smem), both halves, may be overwritten only after the MMAs of iteration i-1 have retired
           mbar_wait(&bars->dq_full, (i - 1) & 1);
         }
         const uint32_t sub = hh * (BT * 128);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t off = sub + sw128_offset(r, colhalf * 4 + q4);
-          *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const uint32_t off = sub + sw128_offset(r, colq * 2 + q4);
           *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
         }
+        tmem_st8(tmem_addr(tm_PT + hh * 32, quarter * 32, colq * 8), pp);
         fence_proxy_async_smem();
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->pds_full[hh]);
-        if (hh == 0 && i > 0) dq_flush(i - 1);
+        if (hh == 0 && i > 0 && flusher) dq_flush(i - 1);
       }
     }
-    dq_flush(n_q - 1);
-    // dK_j, dV_j (all MMAs retired: last dq_full). Each warp: 32 key rows x 32 of the 64 columns of each.
+    if (flusher) dq_flush(n_q - 1);
+    // dK_j, dV_j (all MMAs retired: last dq_full). Each flush warp: 32 key rows x 32 of the 64 columns of each.
     const int kr = k0 + r;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < (flusher ? 2 : 0); ++which) {
       const uint32_t src = which == 0 ? tm_DK : tm_DV;
       uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD + colhalf * 32;
       uint32_t v[32];
@@ -337,7 +341,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                               pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
       }
     }
-    if (lane == 0) tma_store_wait_read0();
+    if (lane == 0 && flusher) tma_store_wait_read0();
   }
 
   tc_fence_before();

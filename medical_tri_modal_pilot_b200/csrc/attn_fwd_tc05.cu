@@ -9,8 +9,12 @@
 // query tiles past it (pad rows, provably dead) are written as zeros.
 //
 // One CTA = 128 query rows of one (sample, head). warp0 = TMA, warp1 = MMA issuer, warps2-5 = softmax.
-// S (128x128 fp32) and O (128x64 fp32) live in TMEM; P goes registers -> swizzled smem -> A operand of P.V;
-// V is consumed as an MN-major B operand directly from its natural [kv, d] layout.
+// S (128x128 fp32), O (128x64 fp32) and P (128x128 fp16, 64 columns) live in TMEM: P goes registers -> tcgen05.st ->
+// A operand of P.V read from TMEM (no shared-memory round trip: the SS form of the N=64 MMA needs 192 B/clk of smem
+// reads, above the 128 B/clk the SM has); the 32 KB this frees hold a third K/V ring stage (a stage is only released
+// when its MMA retires, so with two stages every tile waited a full TMA round trip). V is consumed as an MN-major B
+// operand directly from its natural [kv, d] layout. S(j+1) = Q K^T is issued as soon as S(j) has been copied to
+// registers, i.e. it runs under the exponentials of tile j.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -22,16 +26,14 @@ constexpr int kThreads = 192;
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int BKV = 128;  // keys per iteration
 constexpr int HD = 64;    // head dim
-constexpr int kKVStages = 2;
+constexpr int kKVStages = 3;
 
 constexpr int kQBytes = BQ * HD * 2;       // 16 KB
 constexpr int kKBytes = BKV * HD * 2;      // 16 KB
-constexpr int kPBytes = BQ * BKV * 2;      // 32 KB (two K-major sub-tiles of 64 keys)
 constexpr int kSmemQ = 0;
 constexpr int kSmemK = kSmemQ + kQBytes;
 constexpr int kSmemV = kSmemK + kKVStages * kKBytes;
-constexpr int kSmemP = kSmemV + kKVStages * kKBytes;
-constexpr int kSmemBar = kSmemP + kPBytes;
+constexpr int kSmemBar = kSmemV + kKVStages * kKBytes;
 constexpr int kSmemTotal = kSmemBar + 128 + 896;  // barriers + alignment slack
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -47,8 +49,9 @@ struct Bars {
   uint64_t k_full[kKVStages], k_empty[kKVStages];
   uint64_t v_full[kKVStages], v_empty[kKVStages];
   uint64_t s_full;   // MMA -> softmax : S tile ready in TMEM
-  uint64_t p_full;   // softmax -> MMA : P in smem (and O rescaled)
-  uint64_t o_done;   // MMA -> softmax : P.V retired (P smem / O TMEM reusable)
+  uint64_t s_free;   // softmax -> MMA : S tile copied to registers (TMEM S reusable: S(j+1) may be issued)
+  uint64_t p_full;   // softmax -> MMA : P in TMEM (and O rescaled)
+  uint64_t o_done;   // MMA -> softmax : P.V retired (P / O TMEM reusable)
   uint32_t tmem_slot;
 };
 
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __restrict__ kv_len, int T, int ld_o,
                 uint16_t* __restrict__ O, float* __restrict__ lse2, int T_lse, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   Bars* bars = (Bars*)(smem + kSmemBar);
 
   const int warp = threadIdx.x >> 5;
@@ -91,6 +94,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       mbar_init(&bars->v_empty[s], 1);
     }
     mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_free, 4);
     mbar_init(&bars->p_full, 4);
     mbar_init(&bars->o_done, 1);
     fence_barrier_init();
@@ -102,6 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tmem_S = tmem_base;        // columns [0,128)
   const uint32_t tmem_O = tmem_base + 128;  // columns [128,192)
+  const uint32_t tmem_P = tmem_base + 192;  // columns [192,256): 128 fp16 per lane, two per column
 
   if (warp == 0) {
     if (lane == 0) {
@@ -124,10 +129,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       constexpr uint32_t idesc_s = make_idesc(BQ, BKV, 0, 0, FMT_F16, FMT_F16);  // S = Q K^T, both K-major
       constexpr uint32_t idesc_o = make_idesc(BQ, HD, 0, 1, FMT_F16, FMT_F16);   // O += P V, V MN-major
       const uint32_t sQ = smem_u32(smem + kSmemQ);
-      const uint32_t sP = smem_u32(smem + kSmemP);
       mbar_wait(&bars->q_full, 0);
-      int st = 0;
-      uint32_t ph = 0;
       // prologue: S(0)
       mbar_wait(&bars->k_full[0], 0);
       tc_fence_after();
@@ -140,33 +142,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         umma_commit(&bars->s_full);
         umma_commit(&bars->k_empty[0]);
       }
+      int stK = 1 % kKVStages, stV = 0;       // ring stage of K(j+1) / of V(j)
+      uint32_t phK = 0, phV = 0;
       for (int j = 0; j < n_kv; ++j) {
-        // O += P(j) V(j)
-        mbar_wait(&bars->p_full, j & 1);
-        mbar_wait(&bars->v_full[st], ph);
-        tc_fence_after();
-        const uint32_t sV = smem_u32(smem + kSmemV + st * kKBytes);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t adesc = make_sdesc_sw128(sP + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_sdesc_sw128(sV + k * 2048, BKV * 128, 1024);
-          umma_ss(tmem_O, adesc, bdesc, idesc_o, (j | k) != 0);
-        }
-        umma_commit(&bars->o_done);
-        umma_commit(&bars->v_empty[st]);
-        if (++st == kKVStages) { st = 0; ph ^= 1; }
-        // S(j+1) = Q K(j+1)^T   (S TMEM was drained by the softmax warps before p_full(j))
+        // S(j+1) = Q K(j+1)^T as soon as the softmax warps have copied S(j) out of TMEM: the QK^T MMA runs under
+        // the exponentials of tile j instead of after them
         if (j + 1 < n_kv) {
-          mbar_wait(&bars->k_full[st], ph);
+          mbar_wait(&bars->s_free, j & 1);
+          mbar_wait(&bars->k_full[stK], phK);
           tc_fence_after();
-          const uint32_t sK = smem_u32(smem + kSmemK + st * kKBytes);
+          const uint32_t sK = smem_u32(smem + kSmemK + stK * kKBytes);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
             umma_ss(tmem_S, make_sdesc_sw128(sQ + k * 32, 16, 1024), make_sdesc_sw128(sK + k * 32, 16, 1024),
                     idesc_s, k != 0);
           umma_commit(&bars->s_full);
-          umma_commit(&bars->k_empty[st]);
+          umma_commit(&bars->k_empty[stK]);
+          if (++stK == kKVStages) { stK = 0; phK ^= 1; }
         }
+        // O += P(j) V(j): A = P from TMEM (16 keys = 8 columns per K step), B = V MN-major from smem
+        mbar_wait(&bars->p_full, j & 1);
+        mbar_wait(&bars->v_full[stV], phV);
+        tc_fence_after();
+        const uint32_t sV = smem_u32(smem + kSmemV + stV * kKBytes);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_ts(tmem_O, tmem_P + k * 8, make_sdesc_sw128(sV + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0);
+        umma_commit(&bars->o_done);
+        umma_commit(&bars->v_empty[stV]);
+        if (++stV == kKVStages) { stV = 0; phV ^= 1; }
       }
     }
   } else {
@@ -175,7 +179,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t t_S = tmem_addr(tmem_S, quarter * 32, 0);
     const uint32_t t_O = tmem_addr(tmem_O, quarter * 32, 0);
-    uint8_t* sP = smem + kSmemP;
+    const uint32_t t_P = tmem_addr(tmem_P, quarter * 32, 0);
     float m_ref = -INFINITY;  // running reference max (raw score units)
     float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
@@ -193,15 +197,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         tmem_ld32(t_S + 96, s3);
         tmem_ld_wait();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free);
       const int kbase = j * BKV;
       if (kbase + BKV > len) {
 #pragma unroll
         for (int c = 0; c < 128; ++c)
           if (kbase + c >= len) s[c] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
-      for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+      for (int c = 0; c < 128; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(s[c + u]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescale: keep the old reference max unless the new max exceeds it by > 8 (log2 units)
       float m_new = m_ref;
       const bool bump = (mx - m_ref) * scale_log2 > 8.f;  // also true on the first tile (m_ref = -inf)
@@ -210,38 +221,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       const float moff = m_new * scale_log2;
       l *= alpha;
       m_ref = m_new;
-      // P smem and O TMEM are free once P.V(j-1) has retired (in-order MMA pipe: already true when S(j) landed)
-      if (j > 0) {
-        mbar_wait(&bars->o_done, (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, bump)) {
-          uint32_t o[32];
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int hblk = 0; hblk < 2; ++hblk) {  // two runs of 64 keys = 32 packed columns each
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[hblk * 64 + c]), scale_log2, -moff));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[hblk * 64 + c + 1]), scale_log2, -moff));
+          rs4[c & 3] += p0;
+          rs4[(c & 3) + 1] += p1;
+          pk[c >> 1] = pack_f16x2(p0, p1);
+        }
+        // P and O TMEM are free once P.V(j-1) has retired; the first 64 exponentials above do not need them, so the
+        // wait sits here, after them
+        if (hblk == 0 && j > 0) {
+          mbar_wait(&bars->o_done, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, bump)) {
+            uint32_t o[32];
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(t_O + c * 32, o);
-            tmem_ld_wait();
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(t_O + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(t_O + c * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(t_O + c * 32, o);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
+        tmem_st32(t_P + hblk * 32, pk);
       }
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys (16 B of bf16)
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = ex2_approx(fmaf(__uint_as_float(s[c * 8 + i]), scale_log2, -moff));
-          rs += p[i];
-        }
-        const uint4 u = make_uint4(pack_f16x2(p[0], p[1]), pack_f16x2(p[2], p[3]), pack_f16x2(p[4], p[5]),
-                                   pack_f16x2(p[6], p[7]));
-        *reinterpret_cast<uint4*>(sP + (c >> 3) * (BQ * 128) + sw128_offset(r, c & 7)) = u;
-      }
-      l += rs;
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);

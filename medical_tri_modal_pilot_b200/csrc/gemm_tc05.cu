@@ -156,7 +156,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using L = SmemLayout<BN, WS>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
@@ -285,21 +285,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const int colw = n0 + half * (BN / 2);
       const uint32_t taddr = tmem_addr(tmem_base, quarter * 32, acc * BN + half * (BN / 2));
-      uint32_t r[2][32];
-      tmem_ld32(taddr, r[0]);
-#pragma unroll
+      // The chunk loop is deliberately NOT unrolled: one copy of the fused epilogue keeps the kernel ~25 KB of SASS
+      // (fully unrolled it was 100 KB and the 8 epilogue warps stalled on instruction fetch: ncu no_instruction 1.2/issue).
+      uint32_t r[32];
+      tmem_ld32(taddr, r);
+#pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         tmem_ld_wait();
-        if (c + 1 < kChunks) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (c + 1 < kChunks) tmem_ld32(taddr + (c + 1) * 32, r);   // next chunk in flight under this chunk's math
         if (c == kChunks - 1) {
           // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
         const int col0 = colw + c * 32;
         epilogue_math(v, p, sb_ptr, row, row_ok, col0);
         if (p.out_f32 && row_ok) {
@@ -373,7 +375,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   using L = WgradSmem<BNW>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;

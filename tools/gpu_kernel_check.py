@@ -253,8 +253,10 @@ def case_gemm():
     res = {}
     # (A dtype, B dtype, out dtype): the product uses fp16 everywhere; bf16 x bf16 stays supported by the kernel
     for tag, (da, db_, do) in {"fwd": (ACT, ACT, ACT), "bf16": (_t.bfloat16,) * 3}.items():
+        # the last four shapes take the weight-stationary variant (K <= 256 / 512, >= 2 tiles per SM), incl. an M tail
         for (M, N, K) in [(128, 128, 64), (300, 256, 256), (4096, 768, 256), (1000, 1024, 256), (1001, 256, 1024),
-                          (20000, 256, 768)]:
+                          (20000, 256, 768), (40001, 768, 256), (38000, 1024, 256), (40001, 384, 128),
+                          (50000, 128, 384)]:
             A = torch.randn(M, K, device=dev).to(da)
             Bw = (torch.randn(N, K, device=dev) / K ** 0.5).to(db_)
             bias = torch.randn(N, device=dev)
