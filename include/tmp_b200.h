@@ -13,6 +13,9 @@
  * keeps no global state and never synchronises. Return 0 on success, >0 = cudaError_t, <0 = argument/driver
  * error; tmp_last_error() returns the message (thread-local). D = 256 channels, H = 4 heads of 64 everywhere
  * (control/config.py:97,99 defaults; the kernels are specialised for them).
+ * CUDA GRAPHS: every launch is capturable. The only per-step scalars of a training step are read from DEVICE words
+ * when the caller supplies them, so that one captured graph serves every step: `seed_dev` (uint32, added to the
+ * scalar dropout `seed`; NULL = scalar only) and tmp_adamw_step_dev's `lr_dev` / `step_dev`.
  */
 #ifndef TMP_B200_H
 #define TMP_B200_H
@@ -53,15 +56,16 @@ int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* const* val4
 int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
-                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, void* X0, void* stream);
+                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                            void* X0, void* stream);
 /* gradient accumulators are fp32 and ADDED to: g_val/g_tim [4,256] (dW, db, dLN.w, dLN.b), g_feat[20,256],
  * g_cls[256], g_bott[4,256], g_ln[2,256]; dX0[B,5+n,256] and dproj[B*n,256] (written, kind 1) are fp16. */
 int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
-                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, const void* dX0, float* g_val,
-                            float* g_tim, float* g_feat, float* g_cls, float* g_bott, float* g_ln, void* dproj,
-                            void* stream);
+                            const float* pe, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                            const void* dX0, float* g_val, float* g_tim, float* g_feat, float* g_cls, float* g_bott,
+                            float* g_ln, void* dproj, void* stream);
 
 /* ---- a9: LayerNorm (module.py:130-144: unbiased std, eps on std) ------------------------------------------
  * fwd: if add != NULL: sum_out = x + add, y = LN(sum_out) (encoder.py:27-30 residual fused); else y = LN(x).
@@ -70,8 +74,8 @@ int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float*
 int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
                       void* sum_out, void* y, void* stream);
 int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows, void* dx,
-                      void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, float* dgamma, float* dbeta,
-                      void* stream);
+                      void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev, float* dgamma,
+                      float* dbeta, void* stream);
 
 /* ---- a10/a11: tcgen05 GEMMs -------------------------------------------------------------------------------
  * out[M,N] = residual + dropout( gate>0 ? act(alpha * A[M,K].B[N,K]^T + bias) : 0 ),  act = relu: 0 none, 1 ReLU, 2 GELU(erf)
@@ -81,7 +85,7 @@ int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const flo
 int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N, int K,
                           float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
                           const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
-                          void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
+                          const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
 /* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X) */
 int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
                    float* dW, void* stream);
@@ -106,7 +110,8 @@ int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int 
                            const long long* missing, int B, void* stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------------------- */
-int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt, void* stream);
+int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                      const uint32_t* seed_dev, void* stream);
 /* fp16 gradient tensors, n % 8 == 0.
  * tmp_cast_weights: descs = device array of n_desc records {const float* src; fp16* dst; fp16* dst_t; int R; int C}
  * (32 bytes): dst[R,C] = fp16(src), dst_t[C,R] = fp16(src)^T (either may be NULL). */
@@ -117,6 +122,10 @@ int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* 
  * flat fp32 parameter / gradient buffers of the fused path: w,g,m,v fp32 [n], n % 4 == 0; step >= 1. ---------- */
 int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, void* stream);
+/* same update with the learning rate and the step count read from DEVICE words (lr_dev: fp32, step_dev: int32 >= 1;
+ * bias corrections are evaluated in the kernel) -- the form a captured CUDA graph replays. */
+int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1,
+                       float beta2, float eps, float weight_decay, const int32_t* step_dev, void* stream);
 
 /* ---- image-encoder feed: the glue of the frozen Swin-T forward around the tcgen05 GEMMs
  * (reference builder/models/src/swin_transformer.py: patch embedding :541-551, SwinTransformerBlock.forward :447-450,

@@ -23,22 +23,23 @@ SIGNATURES = {
     "tmp_debug_materialize_mask": [_vp, _i, _i, _vp, _vp],
     "tmp_umse_embed_fwd": [_vp, _ll, _pp, _pp, _vp, _vp, _i, _vp],
     "tmp_stream_prologue_fwd": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
-                                _u32, _vp, _vp],
+                                _u32, _vp, _vp, _vp],
     "tmp_stream_prologue_bwd": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
-                                _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                                _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tmp_layernorm_fwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
-    "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp],
+    "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
     "tmp_gemm_bias_act_fwd": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _i, _vp, _i, _i, _f, _u32,
-                              _u32, _vp, _i, _vp, _i, _vp],
+                              _u32, _vp, _vp, _i, _vp, _i, _vp],
     "tmp_gemm_wgrad": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
     "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
     "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "tmp_bottleneck_mix_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
-    "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp],
+    "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
+    "tmp_adamw_step_dev": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _vp],
     "tmp_swin_patch_embed_ln": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tmp_swin_ln_window": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "tmp_swin_window_attn": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],

@@ -78,4 +78,4 @@ int num_sms() {
 }  // namespace tmp
 
 extern "C" const char* tmp_last_error(void) { return tmp::g_err; }
-extern "C" int tmp_abi_version(void) { return 1; }
+extern "C" int tmp_abi_version(void) { return 2; }   // 2: seed_dev words, tmp_adamw_step_dev

@@ -142,6 +142,7 @@ struct PrologueParams {
   const float* ln_b;
   const float* pe;             // [>=T-4, 256] or null
   uint32_t drop_thr16; float drop_scale; uint32_t seed, salt;
+  const uint32_t* seed_dev;    // optional device word added to `seed` (per-step counter of a captured CUDA graph)
   h16* X0;                     // [B, T, 256] fp16
 };
 
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
     }
     if (p.drop_thr16) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-      dropout_apply_run<8>(y, dropout_key(p.seed, p.salt), base, p.drop_thr16, p.drop_scale);
+      dropout_apply_run<8>(y, dropout_key(effective_seed(p.seed, p.seed_dev), p.salt), base, p.drop_thr16, p.drop_scale);
     }
     store8<ACT>(dst, y);
   }
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
     }
     if (p.drop_thr16) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-      dropout_apply_run<8>(g, dropout_key(p.seed, p.salt), base, p.drop_thr16, p.drop_scale);
+      dropout_apply_run<8>(g, dropout_key(effective_seed(p.seed, p.seed_dev), p.salt), base, p.drop_thr16, p.drop_scale);
     }
     float s1 = 0.f;
 #pragma unroll
@@ -408,7 +409,8 @@ extern "C" int tmp_umse_embed_fwd(const float* x, long long n_tok, const float* 
 static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float* x, const float* const* val4,
                          const void* proj, const float* times, int n_slots, int feat_id, const float* const* tim4,
                          const float* Wfeat, const float* cls, const float* bottlenecks, const float* ln_g,
-                         const float* ln_b, const float* pe, float drop_p, uint32_t seed, uint32_t salt, void* X0) {
+                         const float* ln_b, const float* pe, float drop_p, uint32_t seed, uint32_t salt,
+                         const uint32_t* seed_dev, void* X0) {
   TMP_REQUIRE(kind == 0 || kind == 1, "prologue: kind must be 0 (vslt) or 1 (img/txt)");
   TMP_REQUIRE(B > 0 && n >= 0 && tim4 && Wfeat && cls && bottlenecks && ln_g && ln_b && X0, "prologue: bad argument");
   TMP_REQUIRE(kind == 1 || (x && val4), "prologue: vslt stream needs x and the value branch");
@@ -425,7 +427,7 @@ static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float*
   p.Wfeat = Wfeat; p.cls = cls; p.bottlenecks = bottlenecks; p.ln_g = ln_g; p.ln_b = ln_b; p.pe = pe;
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.seed = seed; p.salt = salt;
+  p.seed = seed; p.salt = salt; p.seed_dev = seed_dev;
   p.X0 = (h16*)X0;
   return TMP_OK;
 }
@@ -434,10 +436,11 @@ extern "C" int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, c
                                        const void* proj, const float* times, int n_slots, int feat_id,
                                        const float* const* tim4, const float* Wfeat, const float* cls,
                                        const float* bottlenecks, const float* ln_g, const float* ln_b, const float* pe,
-                                       float drop_p, uint32_t seed, uint32_t salt, void* X0, void* stream) {
+                                       float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* X0,
+                                       void* stream) {
   PrologueParams p;
   int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
-                         ln_b, pe, drop_p, seed, salt, X0);
+                         ln_b, pe, drop_p, seed, salt, seed_dev, X0);
   if (rc) return rc;
   const int grid = grid_for_rows((long long)B * p.T);
   if (kind == 0) stream_prologue_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
@@ -449,13 +452,14 @@ extern "C" int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, c
                                        const void* proj, const float* times, int n_slots, int feat_id,
                                        const float* const* tim4, const float* Wfeat, const float* cls,
                                        const float* bottlenecks, const float* ln_g, const float* ln_b, const float* pe,
-                                       float drop_p, uint32_t seed, uint32_t salt, const void* dX0, float* g_val,
+                                       float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                                       const void* dX0, float* g_val,
                                        float* g_tim, float* g_feat, float* g_cls, float* g_bott, float* g_ln,
                                        void* dproj, void* stream) {
   PrologueBwdParams q;
   // X0 is not written by the backward; pass dX0 to satisfy the non-null check
   int rc = fill_prologue(q.f, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
-                         ln_b, pe, drop_p, seed, salt, const_cast<void*>(dX0));
+                         ln_b, pe, drop_p, seed, salt, seed_dev, const_cast<void*>(dX0));
   if (rc) return rc;
   TMP_REQUIRE(dX0 && g_tim && g_feat && g_cls && g_bott && g_ln, "prologue_bwd: null gradient buffer");
   TMP_REQUIRE(kind == 1 || g_val, "prologue_bwd: vslt needs g_val");

@@ -36,7 +36,8 @@ struct EpiParams {
   int out_fmt, gate_fmt, res_fmt;
   uint32_t drop_thr16;    // 0 = no dropout; else round(p*65536)
   float drop_scale;       // 1/(1-p)
-  uint32_t drop_key;      // dropout_key(seed, salt)
+  uint32_t drop_seed, drop_salt;   // mask = f(dropout_key(drop_seed + *drop_seed_dev, drop_salt), element index)
+  const uint32_t* drop_seed_dev;   // optional device word added to the seed (CUDA-graph replays), or null
   uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
   float* out_f32;         // [M, ld_out] fp32 (or null) -- direct stores
   int ld_out;
@@ -86,7 +87,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // Epilogue of one 32-column chunk held by one thread (= one output row): v <- fused epilogue of the accumulators.
 __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p, const float* sbias, int row, bool row_ok,
-                                              int col0) {
+                                              int col0, uint32_t drop_key) {
   if (p.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
@@ -130,7 +131,7 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
     }
   }
   if (p.drop_thr16)
-    dropout_apply_run<32>(v, p.drop_key, (uint32_t)row * (uint32_t)p.N + (uint32_t)col0, p.drop_thr16, p.drop_scale);
+    dropout_apply_run<32>(v, drop_key, (uint32_t)row * (uint32_t)p.N + (uint32_t)col0, p.drop_thr16, p.drop_scale);
   if (p.residual && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
     uint4 u[4];
@@ -277,6 +278,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t drop_key = p.drop_thr16 ? dropout_key(effective_seed(p.drop_seed, p.drop_seed_dev), p.drop_salt) : 0u;
     for (int it = it_first; it < it_end; it += it_step) {
       const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -303,7 +305,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         const int col0 = colw + c * 32;
-        epilogue_math(v, p, sb_ptr, row, row_ok, col0);
+        epilogue_math(v, p, sb_ptr, row, row_ok, col0, drop_key);
         if (p.out_f32 && row_ok) {
           float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
 #pragma unroll
@@ -526,8 +528,8 @@ static bool fmt_ok(int f) { return f == FMT_F16 || f == FMT_BF16; }
 extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N,
                                      int K, float alpha, const float* bias, int relu, const void* gate, int gate_fmt,
                                      int ld_gate, const void* residual, int res_fmt, int ld_res, float drop_p,
-                                     uint32_t seed, uint32_t salt, void* out16, int out_fmt, float* out_f32, int ld_out,
-                                     void* stream) {
+                                     uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* out16, int out_fmt,
+                                     float* out_f32, int ld_out, void* stream) {
   void* out_bf16 = out16;
   TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
   TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok(gate_fmt)) &&
@@ -554,7 +556,7 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.out_fmt = out_fmt; p.gate_fmt = gate_fmt; p.res_fmt = res_fmt;
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.drop_key = dropout_key(seed, salt);
+  p.drop_seed = seed; p.drop_salt = salt; p.drop_seed_dev = seed_dev;
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   CUtensorMap tmOut;
   if (out_bf16) {

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restric
                                                             const float* __restrict__ gamma, long long rows,
                                                             h16* __restrict__ dx, h16* __restrict__ dx_drop,
                                                             uint32_t drop_thr16, float drop_scale, uint32_t seed,
-                                                            uint32_t salt, float* __restrict__ dgamma,
+                                                            uint32_t salt, const uint32_t* __restrict__ seed_dev,
+                                                            float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta) {
   __shared__ float sAcc[2 * D];
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sAcc[i] = 0.f;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restric
     store8<GRD>(dx + row * D + lane * 8, out);
     if (dx_drop) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
-      dropout_apply_run<8>(out, dropout_key(seed, salt), base, drop_thr16, drop_scale);
+      dropout_apply_run<8>(out, dropout_key(effective_seed(seed, seed_dev), salt), base, drop_thr16, drop_scale);
       store8<GRD>(dx_drop + row * D + lane * 8, out);
     }
   }
@@ -273,13 +274,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const h16* __restrict__ dY,
 }
 
 __global__ void dropout_apply_kernel(const h16* __restrict__ in, h16* __restrict__ out, long long n8,
-                                     uint32_t thr16, float scale, uint32_t seed, uint32_t salt) {
+                                     uint32_t thr16, float scale, uint32_t seed, uint32_t salt,
+                                     const uint32_t* __restrict__ seed_dev) {
   const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i8 >= n8) return;
   float v[8];
   load8<GRD>(in + i8 * 8, v);
   const uint32_t base = (uint32_t)(i8 * 8);
-  dropout_apply_run<8>(v, dropout_key(seed, salt), base, thr16, scale);
+  dropout_apply_run<8>(v, dropout_key(effective_seed(seed, seed_dev), salt), base, thr16, scale);
   store8<GRD>(out + i8 * 8, v);
 }
 
@@ -317,10 +319,22 @@ __global__ void cast_weights_kernel(const CastDesc* __restrict__ descs) {
 // decoupled weight decay, bias-corrected moments, eps added after the sqrt(v)/sqrt(bc2) division).
 // 28 B/parameter of HBM traffic (read w,g,m,v; write w,m,v), one launch for all fused-path parameters.
 // ------------------------------------------------------------------------------------------------
+template <bool DEV>
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ w, const float4* __restrict__ g,
                                                     float4* __restrict__ m, float4* __restrict__ v, long long n4,
-                                                    float lr, float b1, float b2, float eps, float decay,
-                                                    float inv_bc1, float inv_sqrt_bc2) {
+                                                    float lr, float b1, float b2, float eps, float wd,
+                                                    float inv_bc1, float inv_sqrt_bc2,
+                                                    const float* __restrict__ lr_dev,
+                                                    const int32_t* __restrict__ step_dev) {
+  if (DEV) {
+    // learning rate / step count live in device memory (CUDA-graph replays): bias corrections per thread, in double
+    // like the host path (pow of a handful of values, once per thread)
+    lr = __ldg(lr_dev);
+    const double t = (double)__ldg(step_dev);
+    inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, t)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+  }
+  const float decay = 1.f - lr * wd;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 W = w[i], M = m[i], V = v[i];
@@ -381,8 +395,8 @@ extern "C" int tmp_layernorm_fwd(const void* x, const void* add, const float* ga
 }
 
 extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
-                                 void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, float* dgamma,
-                                 float* dbeta, void* stream) {
+                                 void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt,
+                                 const uint32_t* seed_dev, float* dgamma, float* dbeta, void* stream) {
   TMP_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && rows >= 0, "layernorm_bwd: bad argument");
   TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: dropout p out of range");
   if (rows == 0) return TMP_OK;
@@ -392,7 +406,7 @@ extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   layernorm_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const h16*)dy, (const h16*)x, (const h16*)dres, gamma, rows, (h16*)dx, thr ? (h16*)dx_drop : nullptr, thr,
-      scale, seed, salt, dgamma, dbeta);
+      scale, seed, salt, seed_dev, dgamma, dbeta);
   return tmp::check_launch("layernorm_bwd_kernel");
 }
 
@@ -426,13 +440,13 @@ extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out
 }
 
 extern "C" int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
-                                 void* stream) {
+                                 const uint32_t* seed_dev, void* stream) {
   TMP_REQUIRE(in && out && n >= 0 && n % 8 == 0 && drop_p >= 0.f && drop_p < 1.f, "dropout_apply: bad argument");
   if (n == 0) return TMP_OK;
   const uint32_t thr = (uint32_t)(drop_p * 65536.f + 0.5f);
   const long long n8 = n / 8;
   dropout_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const h16*)in, (h16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt);
+      (const h16*)in, (h16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt, seed_dev);
   return tmp::check_launch("dropout_apply_kernel");
 }
 
@@ -445,17 +459,33 @@ extern "C" int tmp_cast_weights(const void* descs, int n_desc, int max_R, int ma
 }
 
 // w, g, m, v: fp32 [n], n % 4 == 0, 16-byte aligned. step >= 1 (bias correction).
+static int adamw_grid(long long n4) {
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)tmp::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)blocks;
+}
+
 extern "C" int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int step, void* stream) {
   TMP_REQUIRE(w && g && m && v && n >= 0 && n % 4 == 0 && step >= 1, "adamw_step: bad argument");
   if (n == 0) return TMP_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const long long n4 = n / 4;
-  long long blocks = (n4 + 255) / 256;
-  const long long cap = (long long)tmp::num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4,
-                                                             lr, beta1, beta2, eps, 1.f - lr * weight_decay,
-                                                             (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)));
+  adamw_kernel<false><<<adamw_grid(n4), 256, 0, (cudaStream_t)stream>>>(
+      (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
+      (float)(1.0 / sqrt(bc2)), nullptr, nullptr);
+  return tmp::check_launch("adamw_kernel");
+}
+
+extern "C" int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev,
+                                  float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
+                                  void* stream) {
+  TMP_REQUIRE(w && g && m && v && lr_dev && step_dev && n >= 0 && n % 4 == 0, "adamw_step_dev: bad argument");
+  if (n == 0) return TMP_OK;
+  const long long n4 = n / 4;
+  adamw_kernel<true><<<adamw_grid(n4), 256, 0, (cudaStream_t)stream>>>(
+      (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, lr_dev,
+      step_dev);
   return tmp::check_launch("adamw_kernel");
 }

@@ -292,6 +292,11 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __host__ __device__ __forceinline__ uint32_t dropout_key(uint32_t seed, uint32_t salt) {
   return mix32(seed) ^ (salt * 0x85ebca6bU);
 }
+// seed actually used by a launch: the scalar `seed` plus an optional DEVICE word (the per-step counter that lets one
+// captured CUDA graph draw a fresh mask on every replay).
+__device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t* seed_dev) {
+  return seed_dev ? seed + __ldg(seed_dev) : seed;
+}
 __host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t pair_idx) {
   uint32_t h = pair_idx * 0x9E3779B1U + key;
   h ^= h >> 16;

@@ -73,19 +73,19 @@ def umse_embed(x, val4, tim4, Wfeat, out_dtype=torch.float32):
 
 
 def stream_prologue_fwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
-                        pe, drop_p, seed, salt, X0):
+                        pe, drop_p, seed, salt, X0, seed_dev=None):
     check(_lib.load().tmp_stream_prologue_fwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
                                               ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
                                               ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
-                                              salt, ptr(X0), stream_ptr()), "tmp_stream_prologue_fwd")
+                                              salt, ptr(seed_dev), ptr(X0), stream_ptr()), "tmp_stream_prologue_fwd")
 
 
 def stream_prologue_bwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
-                        pe, drop_p, seed, salt, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln, dproj):
+                        pe, drop_p, seed, salt, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln, dproj, seed_dev=None):
     check(_lib.load().tmp_stream_prologue_bwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
                                               ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
                                               ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
-                                              salt, ptr(dX0), ptr(g_val), ptr(g_tim), ptr(g_feat), ptr(g_cls),
+                                              salt, ptr(seed_dev), ptr(dX0), ptr(g_val), ptr(g_tim), ptr(g_feat), ptr(g_cls),
                                               ptr(g_bott), ptr(g_ln), ptr(dproj), stream_ptr()),
           "tmp_stream_prologue_bwd")
 
@@ -96,15 +96,16 @@ def layernorm_fwd(x, gamma, beta, y, add=None, sum_out=None):
                                         stream_ptr()), "tmp_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, dres, gamma, dx, dgamma, dbeta, dx_drop=None, drop_p=0.0, seed=0, salt=0):
+def layernorm_bwd(dy, x, dres, gamma, dx, dgamma, dbeta, dx_drop=None, drop_p=0.0, seed=0, salt=0, seed_dev=None):
     rows = x.numel() // D
     check(_lib.load().tmp_layernorm_bwd(ptr(dy), ptr(x), ptr(dres), ptr(gamma), rows, ptr(dx), ptr(dx_drop),
-                                        float(drop_p), seed, salt, ptr(dgamma), ptr(dbeta), stream_ptr()),
+                                        float(drop_p), seed, salt, ptr(seed_dev), ptr(dgamma), ptr(dbeta),
+                                        stream_ptr()),
           "tmp_layernorm_bwd")
 
 
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
-         salt=0, M=None):
+         salt=0, M=None, seed_dev=None):
     """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16."""
     K = A.shape[-1]
     M = A.numel() // K if M is None else M
@@ -114,7 +115,8 @@ def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residu
                                             Bw.stride(0), M, N, K, float(alpha), ptr(bias), int(relu), ptr(gate),
                                             _fmt(gate), gate.shape[-1] if gate is not None else 0, ptr(residual),
                                             _fmt(residual), residual.shape[-1] if residual is not None else 0,
-                                            float(drop_p), seed, salt, ptr(out), _fmt(out), ptr(out_f32), ld_out,
+                                            float(drop_p), seed, salt, ptr(seed_dev), ptr(out), _fmt(out), ptr(out_f32),
+                                            ld_out,
                                             stream_ptr()),
           "tmp_gemm_bias_act_fwd")
 
@@ -157,8 +159,9 @@ def bottleneck_mix_bwd(dYv, dYi, dYt, upper_has_img_txt, missing):
           "tmp_bottleneck_mix_bwd")
 
 
-def dropout_apply(inp, out, drop_p, seed, salt):
-    check(_lib.load().tmp_dropout_apply(ptr(inp), ptr(out), inp.numel(), float(drop_p), seed, salt, stream_ptr()),
+def dropout_apply(inp, out, drop_p, seed, salt, seed_dev=None):
+    check(_lib.load().tmp_dropout_apply(ptr(inp), ptr(out), inp.numel(), float(drop_p), seed, salt, ptr(seed_dev),
+                                        stream_ptr()),
           "tmp_dropout_apply")
 
 
@@ -172,6 +175,16 @@ def adamw_step(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
         _cuda_contig(t, torch.float32, nm)
     check(_lib.load().tmp_adamw_step(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), float(lr), float(beta1), float(beta2),
                                      float(eps), float(weight_decay), int(step), stream_ptr()), "tmp_adamw_step")
+
+
+def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev):
+    """Same update with lr (fp32 [1]) and the step count (int32 [1]) read from device memory: CUDA-graph replayable."""
+    for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v"), (lr_dev, "lr_dev")):
+        _cuda_contig(t, torch.float32, nm)
+    _cuda_contig(step_dev, torch.int32, "step_dev")
+    check(_lib.load().tmp_adamw_step_dev(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(lr_dev), float(beta1),
+                                         float(beta2), float(eps), float(weight_decay), ptr(step_dev), stream_ptr()),
+          "tmp_adamw_step_dev")
 
 
 # ---- image-encoder feed (csrc/swin.cu) -------------------------------------------------------------------------

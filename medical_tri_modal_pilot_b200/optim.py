@@ -23,20 +23,38 @@ class FlatAdamW(torch.optim.Optimizer):
         self.v = torch.zeros(self.n_live, dtype=torch.float32, device=dev)
         flat_ids = {id(p) for _, p in self.fp.layout}
         self.rest = [p for p in params if id(p) not in flat_ids]
-        self._rest_opt = torch.optim.AdamW(self.rest, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # The step count and the learning rate live in device memory (`t_dev`, `lr_dev`): the whole optimizer step is
+        # a fixed sequence of launches with no per-step host scalars, i.e. replayable inside a captured CUDA graph
+        # (trainer.GraphedStep). The few head parameters use torch.optim.AdamW in its capturable form.
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+        self._rest_opt = torch.optim.AdamW(self.rest, lr=torch.tensor(float(lr), device=dev), betas=betas, eps=eps,
+                                           weight_decay=weight_decay, capturable=True)
         self.t = 0
+
+    def sync_lr(self):
+        """param_groups[0]['lr'] (driven by LR schedulers) -> the device words. A no-op while the value is unchanged;
+        must run OUTSIDE a graph capture (GraphedStep calls it before every replay)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            for rg in self._rest_opt.param_groups:
+                rg["lr"].fill_(lr)
+            self._lr_host = lr
 
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         self.t += 1
+        self.t_dev.add_(1)
         fp = self.fp
         if fp.grads_fresh:
-            ops.adamw_step(fp.flat_w[: self.n_live], fp.flat_g[: self.n_live], self.m, self.v, g["lr"], g["betas"][0],
-                           g["betas"][1], g["eps"], g["weight_decay"], self.t)
+            ops.adamw_step_dev(fp.flat_w[: self.n_live], fp.flat_g[: self.n_live], self.m, self.v, self.lr_dev,
+                               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.t_dev)
             fp.grads_fresh = False
-        for rg in self._rest_opt.param_groups:
-            rg["lr"] = g["lr"]
         self._rest_opt.step()
         return None
 

@@ -60,6 +60,8 @@ class FusedPath:
         # img / txt modality streams on side CUDA streams (TMP_B200_SINGLE_STREAM=1 serialises them: debugging aid)
         self.multi_stream = os.environ.get("TMP_B200_SINGLE_STREAM", "0") != "1"
         self.grad_scale = GRAD_SCALE
+        self.seed_base = None     # dropout seed = seed_base + step_dev (device int32 counter, see forward)
+        self.step_dev = None
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter flattening
@@ -226,7 +228,7 @@ class FusedPath:
         common = dict(tim4=self._branch("ie_time"), Wfeat=self.W("ie_feat.weight", 20, D),
                       cls=self.W(f"{F}.cls_token_per_modality.{s}", D), bottlenecks=self.W(f"{F}.bottlenecks", 4, D),
                       ln_g=self.W(f"{F}.layer_norms_in.{s}.weight", D), ln_b=self.W(f"{F}.layer_norms_in.{s}.bias", D),
-                      pe=pe, drop_p=ctx["p"], seed=ctx["seed"], salt=1000 + s)
+                      pe=pe, drop_p=ctx["p"], seed=ctx["seed"], salt=1000 + s, seed_dev=ctx["seed_dev"])
         if s == 0:
             return dict(kind=0, B=B, n=n, x=ctx["x"], val4=self._branch("ie_vslt"), proj=None, times=None, n_slots=0,
                         feat_id=0, **common)
@@ -241,9 +243,15 @@ class FusedPath:
         self._ensure_workspace(B, L, n_img)
         NL = m.num_layers
         p = m.dropout if training else 0.0
+        # dropout masks are a function of (seed_base + device step counter, salt, element): the counter lives in HBM and
+        # is bumped by a device op, so a captured CUDA graph of the step draws fresh masks on every replay
         self.step += 1
-        seed = (int(torch.initial_seed()) * 1000003 + self.step) & 0x7FFFFFFF
-        ctx = dict(B=B, L=L, n_img=n_img, p=p, seed=seed)
+        if self.seed_base is None:
+            self.seed_base = (int(torch.initial_seed()) * 1000003) & 0x7FFFFFFF
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=x.device)
+        if training:
+            self.step_dev.add_(1)
+        ctx = dict(B=B, L=L, n_img=n_img, p=p, seed=self.seed_base, seed_dev=self.step_dev)
         ctx["x"] = x.float().contiguous()
         ctx["img_time"] = img_time.float().reshape(B, n_img).contiguous()
         ctx["txt_time"] = txt_time.float().contiguous()
@@ -321,15 +329,16 @@ class FusedPath:
         st = self.ws[s]
         w, _, h16 = self.blocks[(l, s)]
         B, T, M = ctx["B"], st["T"], st["M"]
-        p, seed = ctx["p"], ctx["seed"]
+        p, seed, sd = ctx["p"], ctx["seed"], ctx["seed_dev"]
         x = st["X"][l]
         ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, st["xn"][l])
         ops.gemm(st["xn"][l], h16.wqkv, out=st["qkv"][l], bias=w.bqkv)
         ops.attn_fwd(st["qkv"][l], ctx["kv_len"][s], B, T, st["O"][l], st["lse"][l])
         ops.layernorm_fwd(x, w.ln2_g, w.ln2_b, st["hn"][l], add=st["O"][l], sum_out=st["h"][l])
-        ops.gemm(st["hn"][l], h16.w1, out=st["a"][l], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3 + s) * 4 + 1)
+        ops.gemm(st["hn"][l], h16.w1, out=st["a"][l], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3 + s) * 4 + 1,
+                 seed_dev=sd)
         ops.gemm(st["a"][l], h16.w2, out=st["X"][l + 1].view(M, D), bias=w.b2, residual=st["h"][l], drop_p=p,
-                 seed=seed, salt=(l * 3 + s) * 4 + 2)
+                 seed=seed, salt=(l * 3 + s) * 4 + 2, seed_dev=sd)
 
     # ------------------------------------------------------------------------------------------------------------
     def backward(self, d_cls):
@@ -397,7 +406,7 @@ class FusedPath:
         p, seed = ctx["p"], ctx["seed"]
         gy = st["g_y"].view(M, D)
         if p > 0:
-            ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2)
+            ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2, seed_dev=ctx["seed_dev"])
             gyd = st["g_yd"].view(M, D)
         else:
             gyd = gy

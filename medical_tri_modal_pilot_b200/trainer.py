@@ -143,6 +143,106 @@ def train_step(args, model, optimizer, criterion, b, scheduler=None, iteration=0
     return loss.detach()
 
 
+_RAW_KEYS = ("train_x", "static_x", "input_lengths", "train_y", "x_img", "x_txt", "txt_lengths", "img_time", "txt_time",
+             "missing")
+
+
+class GraphedStep:
+    """The whole optimisation step (casts of `prepare_batch`, frozen image encoder, fused encoder forward + backward on
+    three CUDA streams, classifier head + its autograd, gradient all-reduce, AdamW) captured ONCE as a CUDA graph and
+    replayed per iteration. The eager step issues ~450 launches and costs ~14 ms of host time against ~15 ms of device
+    time at the bench workload (tools/step_breakdown.py): it is launch-bound as soon as the kernels get faster.
+
+    Everything that varies between steps is data in HBM: the batch (static input buffers, refilled by `load`), the
+    dropout step counter (`FusedPath.step_dev`), AdamW's step count and learning rate (`FlatAdamW.t_dev / lr_dev`).
+    Calls 1..WARMUP with a given input signature run eagerly on the capture stream (lazy initialisation: workspaces,
+    cuBLAS handles, autograd buffers), the next call captures, later calls replay."""
+
+    WARMUP = 2
+
+    def __init__(self, args, model, optimizer, criterion, raw):
+        self.args, self.model, self.optimizer, self.criterion = args, model, optimizer, criterion
+        self.key = self.signature(raw, model, optimizer)
+        dev = next(model.ie_vslt.parameters()).device
+        self.device = dev
+        self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in raw.items()}
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self.loss = None
+        self.calls = 0
+        self.launches_per_replay = 0
+
+    @staticmethod
+    def signature(raw, model, optimizer):
+        return (tuple((k, tuple(v.shape), v.dtype) for k, v in raw.items()), id(optimizer), bool(model.training))
+
+    def load(self, raw):
+        """Host (pinned) or device tensors of one batch -> the static input buffers (asynchronous copies)."""
+        for k, v in raw.items():
+            if v.data_ptr() != self.static[k].data_ptr():
+                self.static[k].copy_(v, non_blocking=True)
+
+    def _eager(self):
+        s = self.static
+        b = prepare_batch(self.args, self.device, s["train_x"], s["static_x"], s["input_lengths"], s["train_y"], s["x_img"],
+                          s["x_txt"], s["txt_lengths"], (s["img_time"], s["txt_time"]), s["missing"])
+        return train_step(self.args, self.model, self.optimizer, self.criterion, b)
+
+    def step(self, scheduler=None, iteration=0, logger=None):
+        """One optimisation step on the batch currently in the static buffers; returns the loss (device tensor)."""
+        from . import _lib
+        self.calls += 1
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        if self.graph is None:
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            if self.calls <= self.WARMUP:
+                with torch.cuda.stream(self.stream):
+                    self.loss = self._eager()
+                cur.wait_stream(self.stream)
+            else:
+                self.optimizer.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
+                n0 = _lib.launch_count
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self.loss = self._eager()
+                self.launches_per_replay = _lib.launch_count - n0
+                _lib.launch_count = n0
+                self.graph = g
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.launch_count += self.launches_per_replay
+        if scheduler is not None:
+            scheduler.step(iteration)
+            if logger is not None:
+                logger.log_lr(scheduler.get_lr()[0], iteration)
+        return self.loss
+
+
+def graphs_enabled(args, optimizer, scaler=None) -> bool:
+    """CUDA-graph replay of the train step: on by default (`args.cuda_graph` / env TMP_B200_GRAPH=0 turn it off) when
+    the optimizer keeps its per-step scalars on the device (optim.FlatAdamW)."""
+    import os
+    flag = getattr(args, "cuda_graph", None)
+    if flag is None:
+        flag = os.environ.get("TMP_B200_GRAPH", "1") != "0"
+    return bool(flag) and scaler is None and hasattr(optimizer, "sync_lr")
+
+
+def graphed_step(args, model, optimizer, criterion, raw) -> GraphedStep:
+    """The model's cached GraphedStep for this input signature (one per signature; a new signature = new capture)."""
+    cache = model.__dict__.setdefault("_graphed_steps", {})
+    key = GraphedStep.signature(raw, model, optimizer)
+    gs = cache.get(key)
+    if gs is None:
+        if len(cache) >= 4:                       # e.g. a ragged last batch every epoch: keep the cache bounded
+            cache.pop(next(iter(cache)))
+        gs = cache[key] = GraphedStep(args, model, optimizer, criterion, raw)
+    return gs
+
+
 def missing_trainer(args, iteration, train_x, static_x, input_lengths, train_y, model, logger, device, scheduler=None,
                     optimizer=None, criterion=None, scaler=None, flow_type=None, output_lengths=None, seq_lengths=None,
                     x_img=None, x_txt=None, txt_lengths=None, imgtxt_time=None, missing=None, reports_tokens=None,
@@ -150,6 +250,12 @@ def missing_trainer(args, iteration, train_x, static_x, input_lengths, train_y, 
     """Same signature and return value as reference builder/trainer/trainer.py:20-241 (TIE branch)."""
     if getattr(args, "vslt_type", "TIE") != "TIE":
         raise NotImplementedError("B200 trainer implements --vslt-type TIE")
+    if flow_type == "train" and graphs_enabled(args, optimizer, scaler) and torch.device(device).type == "cuda":
+        raw = dict(zip(_RAW_KEYS, (train_x, static_x, input_lengths, train_y, x_img, x_txt, txt_lengths, imgtxt_time[0],
+                                   imgtxt_time[1], missing)))
+        gs = graphed_step(args, model, optimizer, criterion, raw)
+        gs.load(raw)
+        return model, gs.step(scheduler, iteration, logger).item()
     b = prepare_batch(args, device, train_x, static_x, input_lengths, train_y, x_img, x_txt, txt_lengths, imgtxt_time,
                       missing)
     if flow_type == "train":

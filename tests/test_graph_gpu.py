@@ -1,0 +1,111 @@
+"""CUDA-graph replay of the training step (trainer.GraphedStep) == the eager step, and the device-resident per-step
+scalars (dropout step counter, AdamW step / learning rate) behave like their host-scalar forms."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer_inputs(batch):
+    miss = batch["missing"]
+    miss3 = torch.stack([torch.zeros_like(miss), (miss >= 2).long(), (miss % 2).long()], 1).float()
+    static = torch.stack([batch["gen"], batch["age"]], 1)
+    return static, miss3
+
+
+def _run_steps(cuda_graph, n_steps, dropout=0.0, lrs=None):
+    from golden_util import fixture_inputs, fixture_names, load_fixture
+    from builder.trainer import get_trainer
+    from medical_tri_modal_pilot_b200.optim import FlatAdamW
+    from test_model_parity_gpu import build_model
+    fx = load_fixture(fixture_names()[0])
+    sd, batch, cfg = fixture_inputs(fx)
+    B = batch["x"].shape[0]
+    torch.manual_seed(0)
+    model = build_model(cfg, sd, B, dropout=dropout).train()
+    model.args.cuda_graph = cuda_graph
+    # eps = 1e-3: with the default 1e-8 AdamW turns the ~1e-7 run-to-run jitter of the fp32-atomic weight gradients
+    # into full-size +-lr updates of the near-zero-gradient parameters, and two EAGER runs already drift apart
+    opt = FlatAdamW(model, lr=1e-3, weight_decay=1e-2, eps=1e-3)
+    crit = torch.nn.BCEWithLogitsLoss()
+    static, miss3 = _trainer_inputs(batch)
+    losses = []
+    for it in range(n_steps):
+        if lrs is not None:
+            opt.param_groups[0]["lr"] = lrs[it]
+        _, loss = get_trainer(model.args, it, batch["x"], static, batch["input_lengths"], batch["y"], None, model, None,
+                              torch.device("cuda"), None, opt, crit, x_txt=batch["txts"], x_img=batch["img_feats"],
+                              txt_lengths=batch["txt_lengths"], imgtxt_time=(batch["img_time"], batch["txt_time"]),
+                              missing=miss3, flow_type="train")
+        losses.append(loss)
+    params = {k: p.detach().clone() for k, p in model.named_parameters() if not k.startswith("img_encoder.")}
+    return losses, params, model
+
+
+def test_graph_replay_matches_eager_steps():
+    """6 optimisation steps (2 eager warm-up calls, capture, 4 replays) with a changing learning rate give the same
+    loss curve and parameters as 6 eager steps (fp32 atomics in the weight-gradient kernels allow ~1e-6 jitter; the
+    bar is 3x the drift between two eager runs, floor 2e-4)."""
+    lrs = [1e-3, 1e-3, 5e-4, 5e-4, 2e-3, 1e-3]
+    l_e, p_e, _ = _run_steps(False, 6, lrs=lrs)
+    l_e2, _, _ = _run_steps(False, 6, lrs=lrs)
+    l_g, p_g, model = _run_steps(True, 6, lrs=lrs)
+    tol = max(2e-4, 3 * max(abs(a - b) for a, b in zip(l_e, l_e2)))
+    gs = next(iter(model.__dict__["_graphed_steps"].values()))
+    assert gs.graph is not None and gs.launches_per_replay > 50
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) < tol, (l_e, l_e2, l_g)
+    assert l_e[-1] < l_e[0]                 # it trains
+    for k in p_e:
+        d = (p_e[k] - p_g[k]).abs().max().item()
+        assert d <= 2e-4 + 1e-3 * p_e[k].abs().max().item() + 10 * tol, (k, d)
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    """With dropout on, two replays of the same graph on the same batch must not reuse the mask: the device step counter
+    feeds the hash. Checked on the X0 activations (prologue dropout) saved by consecutive replays."""
+    from medical_tri_modal_pilot_b200 import trainer
+    losses, _, model = _run_steps(True, 4, dropout=0.3)
+    fp = model._fused
+    x_a = fp.ws[0]["X"][0].clone()
+    gs = next(iter(model.__dict__["_graphed_steps"].values()))
+    assert gs.graph is not None
+    c0 = int(fp.step_dev.item())
+    gs.step()
+    torch.cuda.synchronize()
+    assert int(fp.step_dev.item()) == c0 + 1
+    x_b = fp.ws[0]["X"][0]
+    za, zb = (x_a[:, 5:] == 0), (x_b[:, 5:] == 0)
+    assert 0.2 < za.float().mean().item() < 0.4 and 0.2 < zb.float().mean().item() < 0.4
+    assert (za != zb).float().mean().item() > 0.2       # independent masks differ on 2 p (1-p) = 42 % of the elements
+
+
+def test_seed_dev_equals_scalar_seed():
+    from medical_tri_modal_pilot_b200 import ops
+    g = torch.randn(64, 256, device="cuda").half()
+    o1, o2 = torch.empty_like(g), torch.empty_like(g)
+    ops.dropout_apply(g, o1, 0.25, 1234 + 7, 5)
+    ops.dropout_apply(g, o2, 0.25, 1234, 5, seed_dev=torch.tensor([7], dtype=torch.int32, device="cuda"))
+    assert torch.equal(o1, o2)
+    A = torch.randn(256, 256, device="cuda").half()
+    W = torch.randn(256, 256, device="cuda").half() / 16
+    y1, y2 = torch.empty(256, 256, device="cuda", dtype=torch.float16), torch.empty(256, 256, device="cuda", dtype=torch.float16)
+    ops.gemm(A, W, out=y1, drop_p=0.25, seed=99 + 3, salt=11)
+    ops.gemm(A, W, out=y2, drop_p=0.25, seed=99, salt=11, seed_dev=torch.tensor([3], dtype=torch.int32, device="cuda"))
+    assert torch.equal(y1, y2) and 0.15 < (y1 == 0).float().mean().item() < 0.35
+
+
+def test_adamw_dev_equals_host_scalars():
+    from medical_tri_modal_pilot_b200 import ops
+    torch.manual_seed(1)
+    n = 1 << 18
+    w1 = torch.randn(n, device="cuda"); w2 = w1.clone()
+    m1, v1, m2, v2 = (torch.zeros(n, device="cuda") for _ in range(4))
+    lr_dev = torch.zeros(1, device="cuda")
+    t_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for t, lr in ((1, 3e-3), (2, 1e-3), (3, 2e-3)):
+        g = torch.randn(n, device="cuda")
+        ops.adamw_step(w1, g, m1, v1, lr, 0.9, 0.999, 1e-8, 1e-2, t)
+        lr_dev.fill_(lr); t_dev.fill_(t)
+        ops.adamw_step_dev(w2, g, m2, v2, lr_dev, 0.9, 0.999, 1e-8, 1e-2, t_dev)
+    assert (w1 - w2).abs().max().item() < 1e-6
