@@ -106,6 +106,7 @@ def test_logits_and_grads(name):
     # the fused path differs.
     g_bf16, _, _ = _oracle_grads(sd, batch, cfg, autocast=torch.bfloat16)
     rows_bf16, glob_bf16 = _cosines(g_bf16, g_ref, floor=1e-4)
+    rows, glob = _cosines({k: named[k].grad for k in live}, g_ref, floor=1e-4)
     assert glob >= 0.99 and glob >= glob_bf16 - 1e-3, ("end-to-end global", glob, "bf16-autocast oracle", glob_bf16)
     med, med_bf16 = np.median(list(rows.values())), np.median(list(rows_bf16.values()))
     assert med >= 0.99 and med >= med_bf16 - 1e-3, ("end-to-end median", med, "bf16-autocast oracle", med_bf16)
