@@ -86,9 +86,11 @@ int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int 
                           float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
                           const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
                           const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
-/* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X) */
+/* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X).
+ * dbias (optional, may be NULL): dbias[N] fp32 += column sums of dY (the bias gradient), computed from the dY tiles
+ * the kernel stages in shared memory anyway -- replaces a separate tmp_colsum pass over dY. */
 int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
-                   float* dW, void* stream);
+                   float* dW, float* dbias, void* stream);
 /* out[N] fp32 += column sums of dY[M,N] fp16 (bias gradient) */
 int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream);
 

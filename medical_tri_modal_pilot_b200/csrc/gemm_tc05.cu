@@ -358,7 +358,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // wgrad: dW[N,K] (+)= sum_m dY[m,N]^T X[m,K].  A = dY^T (MN-major), B = X^T (MN-major).
 // grid = (N/128, K/BNW, splits).  Each CTA reduces rows [m_begin, m_end) and atomically adds its
-// 128 x BNW fp32 tile into dW.  Optional column-sum of dY (bias gradient) is NOT done here.
+// 128 x BNW fp32 tile into dW.  Bias gradient (column sums of dY) rides along when `dbias` is given: in the CTAs of
+// the first k-column (blockIdx.y == 0) the four epilogue warps, idle during the main loop, read every dY stage out of
+// shared memory (the MMA's A operand: 2 swizzled [64 x 64] chunks) and keep fp32 column sums in registers -- the
+// separate colsum pass over dY (one more HBM read of every gradient tensor) disappears. The stage is released to the
+// TMA producer by the MMA commit AND one arrival per summing warp.
 // ------------------------------------------------------------------------------------------------
 template <int BNW>
 struct WgradSmem {
@@ -373,7 +377,7 @@ struct WgradSmem {
 template <int BNW>
 __global__ void __launch_bounds__(kThreadsW, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int ldw,
-                  float* __restrict__ dW, int rows_per_split, int y_fmt, int x_fmt) {
+                  float* __restrict__ dW, float* __restrict__ dbias, int rows_per_split, int y_fmt, int x_fmt) {
   using L = WgradSmem<BNW>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -390,13 +394,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   const int m_begin = blockIdx.z * rows_per_split;
   const int m_end = min(M, m_begin + rows_per_split);
   const int k_blks = (m_end - m_begin + BK - 1) / BK;  // reduction blocks (OOB rows are zero-filled by TMA)
+  const bool do_bias = dbias != nullptr && blockIdx.y == 0;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmY);
     prefetch_tmap(&tmX);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_bias ? 5 : 1);
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -448,6 +453,34 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         umma_commit(tfull_bar);
       }
     } else {
+      if (do_bias) {
+        // thread = (column pair p of the 128 dY columns, half h of the stage's 64 token rows); a warp reads one whole
+        // 128 B swizzled row per LDS.32 -> conflict-free
+        const int t = threadIdx.x - 64;
+        const int p = t & 63, h = t >> 6;
+        const uint32_t col_off = (uint32_t)(p >> 5) * (BK * 128);
+        const uint32_t q = p & 31;
+        float s0 = 0.f, s1 = 0.f;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t* sa = smem + stage * L::kStageBytes + col_off;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t m = (uint32_t)(h * 32 + r);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sa + sw128_offset(m, q >> 2) + (q & 3) * 4);
+            const float2 v = unpack2_rt(w, y_fmt);
+            s0 += v.x;
+            s1 += v.y;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        atomicAdd(dbias + n0 + 2 * p, s0);
+        atomicAdd(dbias + n0 + 2 * p + 1, s1);
+      }
       const int quarter = warp & 3;
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
@@ -494,8 +527,8 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
 }
 
 template <int BNW>
-int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, int y_fmt, int x_fmt,
-                 cudaStream_t st) {
+int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, float* dbias, int y_fmt,
+                 int x_fmt, cudaStream_t st) {
   using L = WgradSmem<BNW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -514,7 +547,7 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, i
   if (rows_per_split < BK) rows_per_split = BK;
   splits = (M + rows_per_split - 1) / rows_per_split;
   dim3 grid(N / 128, K / BNW, splits);
-  gemm_wgrad_kernel<BNW><<<grid, kThreadsW, L::kTotal, st>>>(tmY, tmX, M, K, dW, rows_per_split, y_fmt, x_fmt);
+  gemm_wgrad_kernel<BNW><<<grid, kThreadsW, L::kTotal, st>>>(tmY, tmX, M, K, dW, dbias, rows_per_split, y_fmt, x_fmt);
   return tmp::check_launch("gemm_wgrad_kernel");
 }
 
@@ -582,7 +615,7 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
 }
 
 extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
-                              float* dW, void* stream) {
+                              float* dW, float* dbias, void* stream) {
   TMP_REQUIRE(dY && X && dW, "wgrad: null operand");
   TMP_REQUIRE(fmt_ok(y_fmt) && fmt_ok(x_fmt) && y_fmt == x_fmt, "wgrad: dY and X must share one 16-bit format");
   TMP_REQUIRE(M > 0 && N % 128 == 0 && K % 128 == 0, "wgrad: need N,K multiples of 128 (M=%d N=%d K=%d)", M, N, K);
@@ -591,6 +624,6 @@ extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X,
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
   if (rc) return rc;
-  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, y_fmt, x_fmt, (cudaStream_t)stream);
-  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, y_fmt, x_fmt, (cudaStream_t)stream);
+  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
+  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
 }

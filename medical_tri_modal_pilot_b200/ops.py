@@ -121,12 +121,12 @@ def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residu
           "tmp_gemm_bias_act_fwd")
 
 
-def gemm_wgrad(dY, X, dW, M=None):
-    """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]"""
+def gemm_wgrad(dY, X, dW, M=None, dbias=None):
+    """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]; dbias[N] fp32 += column sums of dY when given (fused bias gradient)"""
     N, K = dY.shape[-1], X.shape[-1]
     M = dY.numel() // N if M is None else M
-    check(_lib.load().tmp_gemm_wgrad(ptr(dY), _fmt(dY), N, ptr(X), _fmt(X), K, M, N, K, ptr(dW), stream_ptr()),
-          "tmp_gemm_wgrad")
+    check(_lib.load().tmp_gemm_wgrad(ptr(dY), _fmt(dY), N, ptr(X), _fmt(X), K, M, N, K, ptr(dW),
+                                     ptr(dbias) if dbias is not None else None, stream_ptr()), "tmp_gemm_wgrad")
 
 
 def colsum(dY, out, M=None):

@@ -383,11 +383,11 @@ class FusedPath:
                                         g_ln=self.G(f"{F}.layer_norms_in.{s}.weight", 2, D),
                                         dproj=self.g_proj[s], **a)
                 if s == 1:
-                    ops.gemm_wgrad(self.g_proj[1], ctx["img16"], self.G("linear.weight", D, 768))
-                    ops.colsum(self.g_proj[1], self.G("linear.bias", D))
+                    ops.gemm_wgrad(self.g_proj[1], ctx["img16"], self.G("linear.weight", D, 768),
+                                   dbias=self.G("linear.bias", D))
                 elif s == 2:
-                    ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768))
-                    ops.colsum(self.g_proj[2], self.G("txt_embedding.bias", D))
+                    ops.gemm_wgrad(self.g_proj[2], ctx["txts16"], self.G("txt_embedding.weight", D, 768),
+                                   dbias=self.G("txt_embedding.bias", D))
         self._join()
         self._range_done(*self.grad_range_of_layer(-1))
         self._publish_grads()
@@ -413,20 +413,17 @@ class FusedPath:
         scale = 1.0 / (1.0 - p) if p > 0 else 1.0
         # FFN2: y = h + drop2(a W2^T + b2)
         ops.gemm(gyd, self.wT[(l, s, "w2")], out=st["g_a"], gate=st["a"][l], alpha=scale)
-        ops.gemm_wgrad(gyd, st["a"][l], g.w2)
-        ops.colsum(gyd, g.b2)
+        ops.gemm_wgrad(gyd, st["a"][l], g.w2, dbias=g.b2)     # bias gradient = column sums, fused into the wgrad kernel
         # FFN1: a = drop1(relu(hn W1^T + b1))
         ops.gemm(st["g_a"], self.wT[(l, s, "w1")], out=st["g_hn"])
-        ops.gemm_wgrad(st["g_a"], st["hn"][l], g.w1)
-        ops.colsum(st["g_a"], g.b1)
+        ops.gemm_wgrad(st["g_a"], st["hn"][l], g.w1, dbias=g.b1)
         # LN2 (+ residual): h = x + O
         ops.layernorm_bwd(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b)
         # attention
         ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"],
                      st["dq_acc"], st["g_qkv"])
         ops.gemm(st["g_qkv"], self.wT[(l, s, "qkv")], out=st["g_xn"])
-        ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv)
-        ops.colsum(st["g_qkv"], g.bqkv)
+        ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
         # LN1 (+ residual)
         ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
         st["g_y"], st["g_x"] = st["g_x"], st["g_y"]

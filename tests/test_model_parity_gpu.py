@@ -109,7 +109,8 @@ def test_logits_and_grads(name):
     rows, glob = _cosines({k: named[k].grad for k in live}, g_ref, floor=1e-4)
     assert glob >= 0.99 and glob >= glob_bf16 - 1e-3, ("end-to-end global", glob, "bf16-autocast oracle", glob_bf16)
     med, med_bf16 = np.median(list(rows.values())), np.median(list(rows_bf16.values()))
-    assert med >= 0.99 and med >= med_bf16 - 1e-3, ("end-to-end median", med, "bf16-autocast oracle", med_bf16)
+    # median over tensors: measured 0.987 on the B=16 fixture where the bf16-autocast oracle itself reaches 0.984
+    assert med >= 0.98 and med >= med_bf16 - 1e-3, ("end-to-end median", med, "bf16-autocast oracle", med_bf16)
     for k in live:
         nr = g_ref[k].norm().item()
         if nr < 1e-4:               # mathematically-zero gradients (see test_oracle_golden): only bound the magnitude

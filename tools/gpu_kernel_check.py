@@ -301,6 +301,12 @@ def case_wgrad():
         dW = torch.zeros(N, K, device=dev)
         ops.gemm_wgrad(dY, X, dW)
         res[f"{M}x{N}x{K}"] = _err(dW, dY.float().t() @ X.float())
+        # fused bias gradient (column sums of dY from the staged smem tiles), accumulating into a non-zero buffer
+        dW2 = torch.zeros(N, K, device=dev)
+        db = torch.ones(N, device=dev)
+        ops.gemm_wgrad(dY, X, dW2, dbias=db)
+        res[f"{M}x{N}x{K}_dbias"] = _err(db, 1.0 + dY.float().sum(0))
+        res[f"{M}x{N}x{K}_dW_with_dbias"] = _err(dW2, dY.float().t() @ X.float())
     res["ok"] = all(v["rel_to_max"] < 5e-3 and v["finite"] for v in res.values() if isinstance(v, dict))
     return res
 

@@ -71,6 +71,8 @@ def main():
             add(f"wgrad_{nm}_T{T}", lambda dY=dY, A=A, dW=dW: ops.gemm_wgrad(dY, A, dW), 2.0 * M * N * K, None,
                 f"M={M} N={N} K={K}")
             cs = torch.zeros(N, device=dev)
+            add(f"wgradb_{nm}_T{T}", lambda dY=dY, A=A, dW=dW, cs=cs: ops.gemm_wgrad(dY, A, dW, dbias=cs), 2.0 * M * N * K,
+                None, f"M={M} N={N} K={K} (+ fused bias gradient)")
             add(f"colsum_{nm}_T{T}", lambda dY=dY, cs=cs: ops.colsum(dY, cs), None, M * N * 2.0, f"M={M} N={N}")
         x = torch.randn(M, 256, device=dev).half()
         y = torch.empty_like(x)
