@@ -126,7 +126,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const size_t stat_base = ((size_t)b * H + h) * T_lse;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bars->kv_full, 2 * kTile);
       tma_load_2d(smem + kSmemK, &tmQKV, &bars->kv_full, 256 + h * HD, row_base + k0);
       tma_load_2d(smem + kSmemV, &tmQKV, &bars->kv_full, 512 + h * HD, row_base + k0);
@@ -144,7 +144,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // all operands fp16 (kind::f16 needs A and B in the same format; gradients are fp16 with a host-side scale)
       constexpr uint32_t idesc_s = make_idesc(BT, 64, 0, 0, FMT_F16, FMT_F16);   // S^T_h / dP^T_h : [128 keys x 64 q]
       constexpr uint32_t idesc_kv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV += P^T dO, dK += dS^T Q (B MN-major)

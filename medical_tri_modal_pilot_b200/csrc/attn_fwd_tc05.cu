@@ -109,7 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
   const uint32_t tmem_P = tmem_base + 192;  // columns [192,256): 128 fp16 per lane, two per column
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bars->q_full, kQBytes);
       tma_load_2d(smem + kSmemQ, &tmQKV, &bars->q_full, h * HD, row_base + q0);
       int st = 0;
@@ -125,7 +125,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc(BQ, BKV, 0, 0, FMT_F16, FMT_F16);  // S = Q K^T, both K-major
       constexpr uint32_t idesc_o = make_idesc(BQ, HD, 0, 1, FMT_F16, FMT_F16);   // O += P V, V MN-major
       const uint32_t sQ = smem_u32(smem + kSmemQ);

@@ -210,7 +210,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       if (WS) {
         mbar_expect_tx(bres_bar, (uint32_t)(k_blks * L::kBBytes));
         for (int kb = 0; kb < k_blks; ++kb) tma_load_2d(smem + kb * L::kBBytes, &tmB, bres_bar, kb * BK, n_fixed);
@@ -231,7 +231,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BM, BN, 0, 0, p.a_fmt, p.b_fmt);
       int stage = 0;
       uint32_t phase = 0;
@@ -414,7 +414,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 
   if (k_blks > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < k_blks; ++kb) {
@@ -431,7 +431,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc = make_idesc(128, BNW, 1, 1, y_fmt, x_fmt);
         int stage = 0;
         uint32_t phase = 0;

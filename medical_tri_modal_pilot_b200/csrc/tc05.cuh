@@ -16,6 +16,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a CONVERGED warp. ptxas knows that exactly one thread runs the guarded region, so instructions that take
+// uniform-register operands (tcgen05.mma descriptors, TMA, commit) are issued directly; behind `if (lane == 0)` it
+// cannot prove that and wraps every such instruction in an ELECT / BRA.U.ANY "waterfall" loop (~19 SASS instructions
+// and ~100 cycles per tcgen05.mma, tools/microbench/ub_mma.cu) -- slower than the 32-cycle N=64 MMAs it feeds.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // 1024 B-aligned base inside the dynamic shared-memory window (128B-swizzle atoms need it). Written as an OFFSET from
 // the `extern __shared__` symbol: casting through uintptr_t made nvcc lose the address space and emit generic
 // LD.E / ST.E (slower, "lg" stalls) for every smem access of the compute warps instead of LDS / STS.

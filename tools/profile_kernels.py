@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE config 5: attention alone, seq 256..4096, full / ragged / de-selected samples")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_times.json"))
     a = ap.parse_args()
     dev = "cuda"
@@ -38,7 +40,33 @@ def main():
             return
         cases.append((name, fn, flops, bytes_, shape))
 
-    for T in (1005, 2005, 152, 133):
+    if a.sweep:
+        # kv_len patterns: "full" = every sample at T; "ragged" = U{T/4..T} (one sample at T); "half_missing" = the
+        # modality is de-selected (kv_len 0) for every second sample, the rest ragged. Flops count live
+        # (query, key) pairs only: 4*len_b^2*64 per head forward, x2.5 backward.
+        gen = torch.Generator().manual_seed(0)
+        for T in (256, 512, 1024, 2048, 4096):
+            Bs = max(8, min(B, (64 * 1024) // T))
+            M = Bs * T
+            Tl = ops.lse_len(T)
+            qkv = torch.randn(M, 768, device=dev).half()
+            O = torch.empty(M, 256, device=dev, dtype=torch.float16)
+            lse = torch.zeros(Bs, 4, Tl, device=dev)
+            dO = (torch.randn(M, 256, device=dev) * 0.1).half()
+            delta = torch.empty(Bs, 4, Tl, device=dev)
+            dq = torch.empty(M, 256, device=dev)
+            dqkv = torch.empty(M, 768, device=dev, dtype=torch.float16)
+            rag = torch.randint(T // 4, T + 1, (Bs,), generator=gen); rag[0] = T
+            half = rag.clone(); half[1::2] = 0
+            for pat, lens in (("full", torch.full((Bs,), T)), ("ragged", rag), ("half_missing", half)):
+                kv = lens.to(device=dev, dtype=torch.int32)
+                f_fwd = float((lens.double() ** 2).sum()) * 4.0 * 64 * 4
+                add(f"sweep_attn_fwd_S{T}_{pat}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, Bs=Bs:
+                    ops.attn_fwd(qkv, kv, Bs, T, O, lse), f_fwd, None, f"B={Bs} H=4 S={T} d=64 kv_len={pat}")
+                add(f"sweep_attn_bwd_S{T}_{pat}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, dO=dO, delta=delta, dq=dq,
+                    dqkv=dqkv, Bs=Bs: ops.attn_bwd(qkv, O, dO, kv, Bs, T, lse, delta, dq, dqkv), 2.5 * f_fwd, None,
+                    f"B={Bs} H=4 S={T} d=64 kv_len={pat}")
+    for T in (() if a.sweep else (1005, 2005, 152, 133)):
         M = B * T
         Tl = ops.lse_len(T)
         qkv = (torch.randn(M, 768, device=dev)).half()
@@ -85,7 +113,7 @@ def main():
         add(f"layernorm_bwd_T{T}", lambda x=x, dx=dx: ops.layernorm_bwd(x, x, x, g, dx, dg, db), None,
             M * 256 * 2 * 4.0, f"rows={M}")
     # UMSE embedding at >= 512k tokens (stable HBM figure), 12 B in + 512 B fp16 out per token
-    n_tok = 1 << 20
+    n_tok = 0 if a.sweep else 1 << 20
     xt = torch.empty(n_tok, 3, device=dev)
     xt[:, 0] = -torch.rand(n_tok, device=dev) * 24; xt[:, 1] = torch.rand(n_tok, device=dev)
     xt[:, 2] = torch.randint(0, 18, (n_tok,), device=dev).float()
@@ -93,7 +121,8 @@ def main():
                   torch.zeros(256, device=dev)]
     v4, t4 = mk(), mk()
     Wf = torch.randn(20, 256, device=dev)
-    add("umse_embed_fwd_1M", lambda: ops.umse_embed(xt, v4, t4, Wf, torch.float16), None, n_tok * 524.0,
+    if not a.sweep:
+      add("umse_embed_fwd_1M", lambda: ops.umse_embed(xt, v4, t4, Wf, torch.float16), None, n_tok * 524.0,
         f"tokens={n_tok}")
 
     results = []
