@@ -313,8 +313,7 @@ def run_b200(a):
     roof = dominant_kernel_roofline(a, model, peaks, peak_src)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, model)
         return
     line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -329,8 +328,24 @@ def run_b200(a):
         v, ms, info = cpu_reference(a, steps=3, warmup=1, budget_s=a.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", **info}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, model)
+
+
+def _finish(world, model):
+    """End of a multi-rank run. The NCCL communicator is referenced by the captured CUDA graphs of the train step, and
+    `destroy_process_group()` then blocks in ncclCommDestroy (measured on 2 x B200: the JSON line was printed and the
+    job never exited). All ranks meet at a barrier, drop the graphs, and leave without running the communicator's
+    destructor; the result line is already flushed."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+    model.__dict__.pop("_graphed_steps", None)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def dominant_kernel_roofline(a, model, peaks, peak_src, iters=10):

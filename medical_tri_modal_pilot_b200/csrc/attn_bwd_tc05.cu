@@ -36,8 +36,16 @@ constexpr int kSmemK = 0;
 constexpr int kSmemV = kSmemK + kTile;
 constexpr int kSmemQ = kSmemV + kTile;
 constexpr int kSmemDO = kSmemQ + kStages * kTile;
-constexpr int kSmemDST = kSmemDO + kStages * kTile;   // dS^T only: P^T lives in TMEM (A operand of dV)
-constexpr int kSmemDQ = kSmemDST + kSq;                   // per compute warp: [32 rows x 32 fp32], 128B swizzle
+// dS^T only (P^T lives in TMEM, A operand of dV): three [128 keys x 64 queries] fp16 sub-tiles  D0a | D1 | D0b.
+// Half 1 has one buffer, half 0 alternates between D0a (even query tiles) and D0b (odd): dQ(i) = dS(i).K reads BOTH
+// halves and is the last MMA of iteration i, so with a single half-0 buffer the compute warps could not store
+// dS^T(i+1, half 0) before dQ(i) had retired -- they sat on that barrier for 13 % of the kernel (profiles/r1g). With the
+// second buffer every overwrite is ordered by the sdp_full barrier the warps wait on anyway (tcgen05.commit covers
+// all earlier MMAs of the issuing thread). dQ of an odd tile reads the pair (D1, D0b), i.e. its M rows come out with
+// the two 64-query halves swapped; the flush undoes that with the row coordinate of the TMA reduce.
+constexpr int kSmemDST = kSmemDO + kStages * kTile;
+constexpr int kHalf = BT * 128;                           // 16 KB: one [128 x 64] fp16 sub-tile
+constexpr int kSmemDQ = kSmemDST + 3 * kHalf;             // per flush warp: [32 rows x 32 fp32], 128B swizzle
 constexpr int kSmemStat = kSmemDQ + kFlushWarps * 4096;
 constexpr int kSmemBar = kSmemStat + kStages * kStatBytes;
 constexpr int kSmemTotal = kSmemBar + 256 + 1024;
@@ -175,7 +183,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                   (i | hh | k) != 0);   // A = P^T_hh from TMEM: 16 queries = 8 packed columns per K step
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tm_DK, make_sdesc_sw128(sDST + hh * (BT * 128) + k * 32, 16, 1024),
+          umma_ss(tm_DK, make_sdesc_sw128(sDST + (hh ? kHalf : (i & 1) * 2 * kHalf) + k * 32, 16, 1024),
                   make_sdesc_sw128(sQ + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv, (i | hh | k) != 0);
       };
       mbar_wait(&bars->kv_full, 0);
@@ -203,9 +211,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           mbar_wait(&bars->dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
+        // dQ_i = dS K_j  (reduction over the 128 keys; A = dS^T read MN-major: two 64-query chunks one kHalf apart --
+        // (D0a, D1) for even tiles, (D1, D0b) for odd tiles, whose dQ rows therefore come out half-swapped)
+        const uint32_t sDSq = sDST + (i & 1) * kHalf;
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k)  // dQ_i = dS K_j  (reduction over the 128 keys; A = dS^T read MN-major)
-          umma_ss(tm_DQ, make_sdesc_sw128(sDST + k * 2048, BT * 128, 1024),
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(tm_DQ, make_sdesc_sw128(sDSq + k * 2048, kHalf, 1024),
                   make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
         umma_commit(&bars->dq_full);
         umma_commit(&bars->qdo_empty[i % kStages]);
@@ -244,7 +255,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
+        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + (quarter ^ ((i & 1) << 1)) * 32);
         tma_store_commit();
       }
     };
@@ -302,11 +313,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             dd[t >> 1] = pack_f16x2(d[0], d[1]);
           }
         }
-        if (hh == 0 && i > 0) {
-          // P^T (TMEM) / dS^T (smem), both halves, may be overwritten only after the MMAs of iteration i-1 have retired
-          mbar_wait(&bars->dq_full, (i - 1) & 1);
-        }
-        const uint32_t sub = hh * (BT * 128);
+        // P^T (TMEM) and this dS^T buffer are free: their last readers (dV/dK of the previous tile, dQ of the tile
+        // before that for D0a/D0b, dQ of the previous tile for D1) were issued before S^T/dP^T of this half-step, whose
+        // commit (sdp_full, observed above) covers them.
+        const uint32_t sub = hh ? kHalf : (i & 1) * 2 * kHalf;
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const uint32_t off = sub + sw128_offset(r, colq * 2 + q4);
