@@ -2,18 +2,30 @@
 // as a tcgen05/TMEM kernel. One CTA owns a 128-key tile of one (sample, head) and sweeps the live query tiles:
 //
 //   S^T  = K_j Q_i^T            dP^T = V_j dO_i^T                      (MMAs into TMEM, in two 64-query halves)
-//   P^T  = exp2(S^T*c - LSE_i)  dS^T = P^T o (dP^T - delta_i) / 8      (registers -> swizzled smem, fp16)
+//   P^T  = exp2(S^T*c - LSE_i)  dS^T = P^T o (dP^T - delta_i) / 8      (registers -> TMEM / swizzled smem, fp16)
 //   dV_j += P^T dO_i            dK_j += dS^T Q_i       dQ_i = dS K_j   (MMAs; dQ leaves through a TMA reduce-add)
 //
-// Pipeline: every 128x128 score tile is processed as two 64-query halves with separate TMEM buffers, so the
-// S^T/dP^T MMAs of the next half run while the 8 compute warps do the exponentials of the current one, and the
-// dV/dK/dQ MMAs of half h overlap the compute of half h+1 (TMEM: 2x64 S^T + 2x64 dP^T + dV 64 + dK 64 + dQ 64 = 448
-// columns). dS^T is written to shared memory once and read twice: as a K-major A operand (dK) and as an MN-major
-// A operand (dQ = dS.K needs the transpose). Q_i / dO_i / K_j are consumed as MN-major B operands straight from
-// their natural [row, d] layout; LSE_i / delta_i ride in the same TMA ring stage as Q_i / dO_i (bulk copies).
-// dQ_i (fp32, 128x64) is staged in swizzled smem per warp and added into the fp32 accumulator with
-// cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b] applied in-register, only in
-// boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly 0, as in the reference).
+// Operand placement follows the measured tcgen05.mma costs on B200 (tools/microbench/ub_mma.cu, cta_group::1, K=16,
+// M=128, N=64): 75 cycles with both operands in shared memory (operand-read bound; the math is 32), 42 cycles with
+// the A operand in TMEM. Four of the five products therefore take A from TMEM:
+//   * K_j and V_j (fixed for the CTA's lifetime) are copied once into TMEM as packed fp16 (2 x 32 columns) and are the
+//     A operands of S^T and dP^T;
+//   * P^T and dS^T are written by the compute warps as packed fp16 INTO the S^T / dP^T accumulator columns they were
+//     computed from (the warp that owns S^T columns [16k,16k+16) of a half writes P^T K-step k into columns
+//     [16k,16k+8) -- no cross-warp hazard) and are the A operands of dV and dK. The next S^T/dP^T MMAs into that
+//     half are issued after dV/dK (tcgen05.mma executes in issue order), so the overwrite is safe;
+//   * dQ = dS.K needs dS with queries on the M axis, i.e. the transpose of what the compute warps hold: dS^T also goes
+//     to swizzled shared memory and is read MN-major (the one SS product left, 8 x 75 cycles per tile).
+// Pipeline: every 128x128 score tile is processed as two 64-query halves with separate TMEM accumulators, so the
+// S^T/dP^T MMAs of the next half run while the 16 compute warps do the exponentials of the current one. dS^T in
+// shared memory is double-buffered by tile parity and dQ(i) is issued LAST in iteration i (after S^T/dP^T of tile
+// i+1), so it never sits between a compute step and the MMAs that step is waiting for; every buffer reuse is ordered
+// by the sdp_full barrier the compute warps wait on anyway (tcgen05.commit covers all earlier MMAs of the thread).
+// Q_i / dO_i are consumed as B operands straight from their natural [row, d] layout; LSE_i / delta_i ride in the same
+// TMA ring stage as Q_i / dO_i (bulk copies). dQ_i (fp32, 128x64) is staged in swizzled smem per warp and added into
+// the fp32 accumulator with cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b]
+// applied in-register, only in boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly
+// 0, as in the reference).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -29,23 +41,18 @@ constexpr int HD = 64;
 constexpr int kStages = 3;   // Q_i / dO_i ring: a stage is released when dV/dK of tile i retire; 2 stages left every tile
                              // waiting a full TMA round trip
 constexpr int kTile = BT * HD * 2;   // 16 KB : [128 rows x 64 fp16]
-constexpr int kSq = BT * BT * 2;     // 32 KB : [128 x 128] fp16 as two 64-column sub-tiles
 constexpr int kStatBytes = 2 * BT * 4;  // lse[128] | delta[128] fp32 per ring stage
 
-constexpr int kSmemK = 0;
-constexpr int kSmemV = kSmemK + kTile;
-constexpr int kSmemQ = kSmemV + kTile;
+constexpr int kHalf = BT * 128;                           // 16 KB: one [128 keys x 64 queries] fp16 sub-tile
+constexpr int kSmemK = 0;                                 // K_j: B operand of dQ for the whole sweep
+constexpr int kSmemV = kSmemK + kTile;                    // V_j: only until it has been copied to TMEM, then ...
+// dS^T (shared-memory copy, read MN-major by dQ): two [half 0 | half 1] pairs, alternating with the query tile's
+// parity. Pair 1 starts in the V_j buffer (dead after the copy to TMEM) and runs 16 KB past it.
+constexpr int kSmemDST1 = kSmemV;                         // pair of odd tiles  : 32 KB
+constexpr int kSmemDST0 = kSmemDST1 + 2 * kHalf;          // pair of even tiles : 32 KB
+constexpr int kSmemQ = kSmemDST0 + 2 * kHalf;
 constexpr int kSmemDO = kSmemQ + kStages * kTile;
-// dS^T only (P^T lives in TMEM, A operand of dV): three [128 keys x 64 queries] fp16 sub-tiles  D0a | D1 | D0b.
-// Half 1 has one buffer, half 0 alternates between D0a (even query tiles) and D0b (odd): dQ(i) = dS(i).K reads BOTH
-// halves and is the last MMA of iteration i, so with a single half-0 buffer the compute warps could not store
-// dS^T(i+1, half 0) before dQ(i) had retired -- they sat on that barrier for 13 % of the kernel (profiles/r1g). With the
-// second buffer every overwrite is ordered by the sdp_full barrier the warps wait on anyway (tcgen05.commit covers
-// all earlier MMAs of the issuing thread). dQ of an odd tile reads the pair (D1, D0b), i.e. its M rows come out with
-// the two 64-query halves swapped; the flush undoes that with the row coordinate of the TMA reduce.
-constexpr int kSmemDST = kSmemDO + kStages * kTile;
-constexpr int kHalf = BT * 128;                           // 16 KB: one [128 x 64] fp16 sub-tile
-constexpr int kSmemDQ = kSmemDST + 3 * kHalf;             // per flush warp: [32 rows x 32 fp32], 128B swizzle
+constexpr int kSmemDQ = kSmemDO + kStages * kTile;        // per flush warp: [32 rows x 32 fp32], 128B swizzle
 constexpr int kSmemStat = kSmemDQ + kFlushWarps * 4096;
 constexpr int kSmemBar = kSmemStat + kStages * kStatBytes;
 constexpr int kSmemTotal = kSmemBar + 256 + 1024;
@@ -60,6 +67,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct Bars {
   uint64_t kv_full;
+  uint64_t kv_tmem;      // compute -> MMA : K_j / V_j copied to TMEM (4 warps, one per lane quarter)
   uint64_t qdo_full[kStages], qdo_empty[kStages];
   uint64_t sdp_full[2];  // MMA -> compute : S^T and dP^T of half h in TMEM
   uint64_t pds_full[2];  // compute -> MMA : P^T and dS^T of half h in smem (and the TMEM half is drained)
@@ -108,6 +116,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmDQ);
     mbar_init(&bars->kv_full, 1);
+    mbar_init(&bars->kv_tmem, 4);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->qdo_full[s], 1);
       mbar_init(&bars->qdo_empty[s], 1);
@@ -130,7 +139,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_DV = tmem_base + 256;
   const uint32_t tm_DK = tmem_base + 320;
   const uint32_t tm_DQ = tmem_base + 384;
-  const uint32_t tm_PT = tmem_base + 448;   // [2] x 32 columns: P^T halves as packed fp16 (64 queries = 32 columns)
+  const uint32_t tm_K = tmem_base + 448;    // K_j as packed fp16: 128 keys (lanes) x 64 d = 32 columns
+  const uint32_t tm_V = tmem_base + 480;    // V_j likewise
+  // P^T / dS^T (packed fp16) alias the S^T / dP^T columns: K-step k (16 queries) of half hh at column hh*64 + 16*k
   const size_t stat_base = ((size_t)b * H + h) * T_lse;
 
   if (warp == 0) {
@@ -157,20 +168,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t idesc_s = make_idesc(BT, 64, 0, 0, FMT_F16, FMT_F16);   // S^T_h / dP^T_h : [128 keys x 64 q]
       constexpr uint32_t idesc_kv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV += P^T dO, dK += dS^T Q (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(BT, HD, 1, 1, FMT_F16, FMT_F16);  // dQ   = dS K     (A, B MN-major)
-      const uint32_t sK = smem_u32(smem + kSmemK), sV = smem_u32(smem + kSmemV);
-      const uint32_t sDST = smem_u32(smem + kSmemDST);
-      auto issue_sdp = [&](int i, int hh) {   // S^T_hh(i), dP^T_hh(i)
+      const uint32_t sK = smem_u32(smem + kSmemK);
+      auto issue_sdp = [&](int i, int hh) {   // S^T_hh(i) = K_j Q_i[hh]^T, dP^T_hh(i) = V_j dO_i[hh]^T   (A in TMEM)
         const int st = i % kStages;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile) + hh * 8192;    // 64 query rows = 8192 B
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile) + hh * 8192;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_ST + hh * 64, make_sdesc_sw128(sK + k * 32, 16, 1024), make_sdesc_sw128(sQ + k * 32, 16, 1024),
-                  idesc_s, k != 0);
+          umma_ts(tm_ST + hh * 64, tm_K + k * 8, make_sdesc_sw128(sQ + k * 32, 16, 1024), idesc_s, k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tm_DPT + hh * 64, make_sdesc_sw128(sV + k * 32, 16, 1024), make_sdesc_sw128(sDO + k * 32, 16, 1024),
-                  idesc_s, k != 0);
+          umma_ts(tm_DPT + hh * 64, tm_V + k * 8, make_sdesc_sw128(sDO + k * 32, 16, 1024), idesc_s, k != 0);
         umma_commit(&bars->sdp_full[hh]);
       };
       auto issue_dvdk = [&](int i, int hh) {  // dV += P^T_hh dO_i[hh], dK += dS^T_hh Q_i[hh]  (reduction over 64 queries)
@@ -178,15 +186,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile);
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts(tm_DV, tm_PT + hh * 32 + k * 8, make_sdesc_sw128(sDO + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv,
-                  (i | hh | k) != 0);   // A = P^T_hh from TMEM: 16 queries = 8 packed columns per K step
+        for (int k = 0; k < 4; ++k)   // A = P^T_hh K-step k: 8 packed columns at the head of S^T columns [16k, 16k+16)
+          umma_ts(tm_DV, tm_ST + hh * 64 + k * 16, make_sdesc_sw128(sDO + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv,
+                  (i | hh | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tm_DK, make_sdesc_sw128(sDST + (hh ? kHalf : (i & 1) * 2 * kHalf) + k * 32, 16, 1024),
-                  make_sdesc_sw128(sQ + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv, (i | hh | k) != 0);
+        for (int k = 0; k < 4; ++k)   // A = dS^T_hh K-step k, same placement inside the dP^T columns
+          umma_ts(tm_DK, tm_DPT + hh * 64 + k * 16, make_sdesc_sw128(sQ + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv,
+                  (i | hh | k) != 0);
       };
-      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(&bars->kv_tmem, 0);
       mbar_wait(&bars->qdo_full[0], 0);
       tc_fence_after();
       issue_sdp(0, 0);
@@ -207,20 +215,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(&bars->pds_full[1], ph);
         tc_fence_after();
         issue_dvdk(i, 1);
+        if (more) issue_sdp(i + 1, 1);
         if (i > 0) {
           mbar_wait(&bars->dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
-        // dQ_i = dS K_j  (reduction over the 128 keys; A = dS^T read MN-major: two 64-query chunks one kHalf apart --
-        // (D0a, D1) for even tiles, (D1, D0b) for odd tiles, whose dQ rows therefore come out half-swapped)
-        const uint32_t sDSq = sDST + (i & 1) * kHalf;
+        // dQ_i = dS K_j  (reduction over the 128 keys; A = the shared-memory copy of dS^T read MN-major: the two
+        // 64-query halves are kHalf apart)
+        const uint32_t sDS = smem_u32(smem + ((i & 1) ? kSmemDST1 : kSmemDST0));
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)
-          umma_ss(tm_DQ, make_sdesc_sw128(sDSq + k * 2048, kHalf, 1024),
+          umma_ss(tm_DQ, make_sdesc_sw128(sDS + k * 2048, kHalf, 1024),
                   make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
         umma_commit(&bars->dq_full);
         umma_commit(&bars->qdo_empty[i % kStages]);
-        if (more) issue_sdp(i + 1, 1);
       }
     }
   } else {
@@ -233,8 +241,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int r = quarter * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dK/dV, query row for dQ
     const bool key_ok = (k0 + r) < len;
     const bool key_tile_partial = (k0 + BT) > len;
-    uint8_t* sDST = smem + kSmemDST;
     uint8_t* sDQ = smem + kSmemDQ + (cw & (kFlushWarps - 1)) * 4096;
+
+    if (colq == 0) {
+      // K_j, V_j -> TMEM (A operands of S^T / dP^T): thread = key row = TMEM lane, 64 fp16 = 32 packed columns each.
+      // One warp per lane quarter; the swizzled 16 B chunks of a row are read in logical order.
+      mbar_wait(&bars->kv_full, 0);
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const uint8_t* src = smem + (which == 0 ? kSmemK : kSmemV);
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + sw128_offset(r, c));
+          w[c * 4] = u.x; w[c * 4 + 1] = u.y; w[c * 4 + 2] = u.z; w[c * 4 + 3] = u.w;
+        }
+        tmem_st32(tmem_addr(which == 0 ? tm_K : tm_V, quarter * 32, 0), w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->kv_tmem);
+    }
 
     auto dq_flush = [&](int i) {   // dQ(i): TMEM -> swizzled smem box -> TMA reduce-add into the fp32 accumulator
       mbar_wait(&bars->dq_full, i & 1);
@@ -255,7 +283,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + (quarter ^ ((i & 1) << 1)) * 32);
+        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
         tma_store_commit();
       }
     };
@@ -265,6 +293,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float* st_lse = (const float*)(smem + kSmemStat + st * kStatBytes);
       const float* st_dl = st_lse + BT;
       const bool need_mask = key_tile_partial || (i * BT + BT > len);
+      uint8_t* sDST = smem + ((i & 1) ? kSmemDST1 : kSmemDST0);
       {
         // the ring stage (Q_i, dO_i, lse_i, delta_i) is complete before the MMA warp could issue S^T(i); observing
         // it here orders our generic-proxy reads of lse/delta after the bulk copies.
@@ -279,56 +308,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld16(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dp);
         tmem_ld_wait();
         const int qc0 = hh * 64 + colq * 16;   // first query column (within the 128-query tile) of this thread's run
+        // P^T = p / 8 and dS^T = (p / 8) (dP^T - delta): the exponent carries lse + 3 (log2 units), so the 1/sqrt(d) of
+        // dS costs nothing, and the factor 8 missing from P^T is applied to dV once, when the CTA writes it out (exact
+        // powers of two on both sides). All fp32 math runs as packed pairs (FFMA2 / FMUL2); masked (key, query) pairs
+        // get a score of -inf, which makes both p and dS exactly 0.
         uint32_t pp[8], dd[8];
-        if (!need_mask) {
+        const f32x2_t c2 = f2_pack(scale_log2, scale_log2), m1 = f2_pack(-1.f, -1.f), m3 = f2_pack(-3.f, -3.f);
+        const int n_ok = key_ok ? (len - i * BT - qc0) : 0;   // valid query columns in this thread's run of 16
 #pragma unroll
-          for (int t = 0; t < 16; t += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
-            const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
-            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-            float p[4], d[4];
+        for (int t = 0; t < 16; t += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
+          const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
+          if (need_mask) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              // p/8 straight from the exponential (lse + 3 in log2 units), p = 8 * (p/8) is exact
-              const float p8 = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -(lv[u] + 3.f)));
-              p[u] = p8 * 8.f;
-              d[u] = p8 * (__uint_as_float(dp[t + u]) - dv[u]);
-            }
-            pp[t >> 1] = pack_f16x2(p[0], p[1]); pp[(t >> 1) + 1] = pack_f16x2(p[2], p[3]);
-            dd[t >> 1] = pack_f16x2(d[0], d[1]); dd[(t >> 1) + 1] = pack_f16x2(d[2], d[3]);
+            for (int u = 0; u < 4; ++u)
+              if (t + u >= n_ok) s[t + u] = 0xff800000u;   // -inf
           }
-        } else {
 #pragma unroll
-          for (int t = 0; t < 16; t += 2) {
-            float p[2], d[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int qc = qc0 + t + u;
-              const bool ok = key_ok && (i * BT + qc) < len;
-              const float p8 = ex2_approx(fmaf(__uint_as_float(s[t + u]), scale_log2, -(st_lse[qc] + 3.f)));
-              p[u] = ok ? p8 * 8.f : 0.f;
-              d[u] = ok ? p8 * (__uint_as_float(dp[t + u]) - st_dl[qc]) : 0.f;
-            }
-            pp[t >> 1] = pack_f16x2(p[0], p[1]);
-            dd[t >> 1] = pack_f16x2(d[0], d[1]);
+          for (int u = 0; u < 4; u += 2) {
+            const f32x2_t nl = f2_fma(u == 0 ? f2_pack(l4.x, l4.y) : f2_pack(l4.z, l4.w), m1, m3);   // -(lse + 3)
+            const f32x2_t x = f2_fma(f2_pack(__uint_as_float(s[t + u]), __uint_as_float(s[t + u + 1])), c2, nl);
+            float x0, x1;
+            f2_unpack(x, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const f32x2_t g = f2_fma(u == 0 ? f2_pack(d4.x, d4.y) : f2_pack(d4.z, d4.w), m1,
+                                     f2_pack(__uint_as_float(dp[t + u]), __uint_as_float(dp[t + u + 1])));   // dP^T - delta
+            float d0, d1;
+            f2_unpack(f2_mul(f2_pack(p0, p1), g), d0, d1);
+            pp[(t + u) >> 1] = pack_f16x2(p0, p1);
+            dd[(t + u) >> 1] = pack_f16x2(d0, d1);
           }
         }
-        // P^T (TMEM) and this dS^T buffer are free: their last readers (dV/dK of the previous tile, dQ of the tile
-        // before that for D0a/D0b, dQ of the previous tile for D1) were issued before S^T/dP^T of this half-step, whose
-        // commit (sdp_full, observed above) covers them.
-        const uint32_t sub = hh ? kHalf : (i & 1) * 2 * kHalf;
+        // The S^T / dP^T columns just read become P^T / dS^T (packed fp16, A operands of dV / dK): this warp owns columns
+        // [16 colq, 16 colq + 16) of both accumulators and writes the 8 packed columns of K-step colq at their head.
+        // The shared-memory copy of dS^T (for dQ) goes to the pair of this tile's parity: its last reader, dQ(i-2), was
+        // issued before S^T/dP^T of this half-step, whose commit (sdp_full, observed above) covers it.
+        const uint32_t sub = hh * kHalf;
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const uint32_t off = sub + sw128_offset(r, colq * 2 + q4);
           *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
         }
-        tmem_st8(tmem_addr(tm_PT + hh * 32, quarter * 32, colq * 8), pp);
+        tmem_st8(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), pp);
+        tmem_st8(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dd);
         fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->pds_full[hh]);
-        if (hh == 0 && i > 0 && flusher) dq_flush(i - 1);
+        // dQ(i-1) is the last MMA of iteration i-1 (issued after S^T/dP^T of this tile): it has retired by now
+        if (hh == 1 && i > 0 && flusher) dq_flush(i - 1);
       }
     }
     if (flusher) dq_flush(n_q - 1);
@@ -341,6 +370,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t v[32];
       tmem_ld32(tmem_addr(src, quarter * 32, colhalf * 32), v);
       tmem_ld_wait();
+      if (which == 1) {   // dV was accumulated from P^T / 8
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * 8.f);
+      }
       if (kr < T) {
         uint4* dst = reinterpret_cast<uint4*>(dst_row);
 #pragma unroll

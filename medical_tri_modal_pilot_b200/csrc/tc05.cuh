@@ -283,6 +283,33 @@ __device__ __forceinline__ float2 unpack2_rt(uint32_t v, int fmt) {
                         : make_float2(bf16lo_to_f32(v), bf16hi_to_f32(v));
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of fp32 math). The softmax loops of
+// the attention kernels are issue-bound next to the MUFU pipe, so everything around the exponential is done in pairs.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose rows are
 // 128 bytes (tile base 1024 B aligned). This is the layout TMA SWIZZLE_128B writes and UMMA SW128 reads.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
