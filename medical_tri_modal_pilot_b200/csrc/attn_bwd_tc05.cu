@@ -272,7 +272,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
         mbar_arrive(&bars->dq_empty);
         tma_store_wait_read0();   // previous reduce of this warp has finished reading the staging box
       }
@@ -282,7 +282,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
         tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
         tma_store_commit();
       }
@@ -351,7 +351,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         tmem_st8(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), pp);
         tmem_st8(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dd);
-        fence_proxy_async_smem();
+        // the shared-memory copy is only read by dQ(i), issued after BOTH halves have arrived: one generic->async proxy
+        // fence per tile (in half 1, covering this thread's stores of both halves) instead of one per half-step
+        if (hh == 1) fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -384,7 +386,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                               pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
       }
     }
-    if (lane == 0 && flusher) tma_store_wait_read0();
+    if (flusher && elect_one()) tma_store_wait_read0();
   }
 
   tc_fence_before();
