@@ -68,6 +68,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct Bars {
   uint64_t kv_full;
   uint64_t kv_tmem;      // compute -> MMA : K_j / V_j copied to TMEM (4 warps, one per lane quarter)
+  uint64_t kv_free;      // MMA -> MMA thread : every MMA of the item retired, K_j / V_j shared buffers reusable
   uint64_t qdo_full[kStages], qdo_empty[kStages];
   uint64_t sdp_full[2];  // MMA -> compute : S^T and dP^T of half h in TMEM
   uint64_t pds_full[2];  // compute -> MMA : P^T and dS^T of half h in smem (and the TMEM half is drained)
@@ -76,10 +77,17 @@ struct Bars {
   uint32_t tmem_slot;
 };
 
+// Work item = (key tile jt, head h, sample b), jt fastest. The kernel is PERSISTENT: grid = min(items, SMs) and every CTA
+// walks items blockIdx.x, += gridDim.x. One CTA per item cost ~17 k cycles of launch gap, barrier/TMEM set-up, first
+// TMA round trip and pipeline fill/drain against ~2.7 k cycles per 128x128 tile (T=1005 vs T=2005 timings: 44 % of the
+// kernel at 8 tiles per item); inside the loop only the K_j/V_j round trip and the fill/drain remain: barriers and TMEM
+// are set up once, and the Q/dO ring (its own producer warp) runs ahead into the next item while this one drains.
+// All roles enumerate the same item sequence; ring stages and barrier phases follow running counters (gq = query tiles
+// processed so far, it = live items so far).
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQ, const int32_t* __restrict__ kv_len, int T,
-                const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
+                const __grid_constant__ CUtensorMap tmDQ, const int32_t* __restrict__ kv_len, int T, int n_jt, int H,
+                int n_items, const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
                 uint16_t* __restrict__ dQKV, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -87,29 +95,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int H = gridDim.y;
-  const int k0 = jt * BT;
-  const int len = kv_len ? min(kv_len[b], T) : T;
-  const int row_base = b * T;
-
-  if (k0 >= len) {
-    // masked / padding keys: dK = dV = 0
-    if (warp >= 2 && warp < 6) {
-      const int r = (warp - 2) * 32 + lane;
-      if (k0 + r < T) {
-        uint4* dk = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + k0 + r) * 768 + 256 + h * HD);
-        uint4* dv = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + k0 + r) * 768 + 512 + h * HD);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          dk[i] = make_uint4(0, 0, 0, 0);
-          dv[i] = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-    return;
-  }
-  const int n_q = (len + BT - 1) / BT;  // live query tiles (query rows >= len are padding: dO == 0)
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQKV);
@@ -117,6 +102,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     prefetch_tmap(&tmDQ);
     mbar_init(&bars->kv_full, 1);
     mbar_init(&bars->kv_tmem, 4);
+    mbar_init(&bars->kv_free, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->qdo_full[s], 1);
       mbar_init(&bars->qdo_empty[s], 1);
@@ -142,35 +128,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_K = tmem_base + 448;    // K_j as packed fp16: 128 keys (lanes) x 64 d = 32 columns
   const uint32_t tm_V = tmem_base + 480;    // V_j likewise
   // P^T / dS^T (packed fp16) alias the S^T / dP^T columns: K-step k (16 queries) of half hh at column hh*64 + 16*k
-  const size_t stat_base = ((size_t)b * H + h) * T_lse;
+
+  // item -> (jt, h, b); live length of the sample
+  struct Item { int jt, h, b, k0, len, n_q, row_base; };
+  auto decode = [&](int item) {
+    Item w;
+    w.jt = item % n_jt;
+    const int t = item / n_jt;
+    w.h = t % H;
+    w.b = t / H;
+    w.k0 = w.jt * BT;
+    w.len = kv_len ? min(__ldg(kv_len + w.b), T) : T;
+    w.n_q = (w.len + BT - 1) / BT;   // live query tiles (query rows >= len are padding: dO == 0)
+    w.row_base = w.b * T;
+    return w;
+  };
 
   if (warp == 0) {
+    // ===================== TMA producer: the Q_i / dO_i / lse_i / delta_i ring =====================
     if (elect_one()) {
-      mbar_expect_tx(&bars->kv_full, 2 * kTile);
-      tma_load_2d(smem + kSmemK, &tmQKV, &bars->kv_full, 256 + h * HD, row_base + k0);
-      tma_load_2d(smem + kSmemV, &tmQKV, &bars->kv_full, 512 + h * HD, row_base + k0);
       int st = 0;
       uint32_t ph = 0;
-      for (int i = 0; i < n_q; ++i) {
-        mbar_wait(&bars->qdo_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->qdo_full[st], 2 * kTile + kStatBytes);
-        tma_load_2d(smem + kSmemQ + st * kTile, &tmQKV, &bars->qdo_full[st], h * HD, row_base + i * BT);
-        tma_load_2d(smem + kSmemDO + st * kTile, &tmDO, &bars->qdo_full[st], h * HD, row_base + i * BT);
-        bulk_load_1d(smem + kSmemStat + st * kStatBytes, lse2 + stat_base + i * BT, BT * 4, &bars->qdo_full[st]);
-        bulk_load_1d(smem + kSmemStat + st * kStatBytes + BT * 4, delta + stat_base + i * BT, BT * 4,
-                     &bars->qdo_full[st]);
-        if (++st == kStages) { st = 0; ph ^= 1; }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item w = decode(item);
+        if (w.k0 >= w.len) continue;
+        const size_t stat_base = ((size_t)w.b * H + w.h) * T_lse;
+        for (int i = 0; i < w.n_q; ++i) {
+          mbar_wait(&bars->qdo_empty[st], ph ^ 1);
+          mbar_expect_tx(&bars->qdo_full[st], 2 * kTile + kStatBytes);
+          tma_load_2d(smem + kSmemQ + st * kTile, &tmQKV, &bars->qdo_full[st], w.h * HD, w.row_base + i * BT);
+          tma_load_2d(smem + kSmemDO + st * kTile, &tmDO, &bars->qdo_full[st], w.h * HD, w.row_base + i * BT);
+          bulk_load_1d(smem + kSmemStat + st * kStatBytes, lse2 + stat_base + i * BT, BT * 4, &bars->qdo_full[st]);
+          bulk_load_1d(smem + kSmemStat + st * kStatBytes + BT * 4, delta + stat_base + i * BT, BT * 4,
+                       &bars->qdo_full[st]);
+          if (++st == kStages) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer (also loads K_j / V_j: it is the one that knows when they are dead) =====================
     if (elect_one()) {
       // all operands fp16 (kind::f16 needs A and B in the same format; gradients are fp16 with a host-side scale)
       constexpr uint32_t idesc_s = make_idesc(BT, 64, 0, 0, FMT_F16, FMT_F16);   // S^T_h / dP^T_h : [128 keys x 64 q]
       constexpr uint32_t idesc_kv = make_idesc(BT, HD, 0, 1, FMT_F16, FMT_F16);  // dV += P^T dO, dK += dS^T Q (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(BT, HD, 1, 1, FMT_F16, FMT_F16);  // dQ   = dS K     (A, B MN-major)
       const uint32_t sK = smem_u32(smem + kSmemK);
-      auto issue_sdp = [&](int i, int hh) {   // S^T_hh(i) = K_j Q_i[hh]^T, dP^T_hh(i) = V_j dO_i[hh]^T   (A in TMEM)
-        const int st = i % kStages;
+      auto issue_sdp = [&](uint32_t g, int hh) {   // S^T_hh = K_j Q[hh]^T, dP^T_hh = V_j dO[hh]^T   (A in TMEM)
+        const int st = g % kStages;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile) + hh * 8192;    // 64 query rows = 8192 B
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile) + hh * 8192;
 #pragma unroll
@@ -181,8 +185,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_ts(tm_DPT + hh * 64, tm_V + k * 8, make_sdesc_sw128(sDO + k * 32, 16, 1024), idesc_s, k != 0);
         umma_commit(&bars->sdp_full[hh]);
       };
-      auto issue_dvdk = [&](int i, int hh) {  // dV += P^T_hh dO_i[hh], dK += dS^T_hh Q_i[hh]  (reduction over 64 queries)
-        const int st = i % kStages;
+      auto issue_dvdk = [&](uint32_t g, int i, int hh) {  // dV += P^T_hh dO[hh], dK += dS^T_hh Q[hh]  (reduction over 64 queries)
+        const int st = g % kStages;
         const uint32_t sQ = smem_u32(smem + kSmemQ + st * kTile);
         const uint32_t sDO = smem_u32(smem + kSmemDO + st * kTile);
 #pragma unroll
@@ -194,41 +198,57 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_ts(tm_DK, tm_DPT + hh * 64 + k * 16, make_sdesc_sw128(sQ + (hh * 4 + k) * 2048, BT * 128, 1024), idesc_kv,
                   (i | hh | k) != 0);
       };
-      mbar_wait(&bars->kv_tmem, 0);
-      mbar_wait(&bars->qdo_full[0], 0);
-      tc_fence_after();
-      issue_sdp(0, 0);
-      issue_sdp(0, 1);
-      for (int i = 0; i < n_q; ++i) {
-        const uint32_t ph = i & 1;
-        const bool more = i + 1 < n_q;
-        // ---- half 0 ----
-        mbar_wait(&bars->pds_full[0], ph);
+      uint32_t gq = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item w = decode(item);
+        if (w.k0 >= w.len) continue;
+        // K_j / V_j of this item. Their buffers (V's doubles as dS^T pair 1) are dead once the last dQ of the previous
+        // item has retired.
+        if (it > 0) mbar_wait(&bars->kv_free, (it - 1) & 1);
+        mbar_expect_tx(&bars->kv_full, 2 * kTile);
+        tma_load_2d(smem + kSmemK, &tmQKV, &bars->kv_full, 256 + w.h * HD, w.row_base + w.k0);
+        tma_load_2d(smem + kSmemV, &tmQKV, &bars->kv_full, 512 + w.h * HD, w.row_base + w.k0);
+        mbar_wait(&bars->kv_tmem, it & 1);
+        mbar_wait(&bars->qdo_full[gq % kStages], (gq / kStages) & 1);
         tc_fence_after();
-        issue_dvdk(i, 0);
-        if (more) {
-          mbar_wait(&bars->qdo_full[(i + 1) % kStages], ((i + 1) / kStages) & 1);
+        issue_sdp(gq, 0);
+        issue_sdp(gq, 1);
+        for (int i = 0; i < w.n_q; ++i) {
+          const uint32_t g = gq + i;
+          const uint32_t ph = g & 1;
+          const bool more = i + 1 < w.n_q;
+          // ---- half 0 ----
+          mbar_wait(&bars->pds_full[0], ph);
           tc_fence_after();
-          issue_sdp(i + 1, 0);
-        }
-        // ---- half 1 ----
-        mbar_wait(&bars->pds_full[1], ph);
-        tc_fence_after();
-        issue_dvdk(i, 1);
-        if (more) issue_sdp(i + 1, 1);
-        if (i > 0) {
-          mbar_wait(&bars->dq_empty, (i - 1) & 1);
+          issue_dvdk(g, i, 0);
+          if (more) {
+            mbar_wait(&bars->qdo_full[(g + 1) % kStages], ((g + 1) / kStages) & 1);
+            tc_fence_after();
+            issue_sdp(g + 1, 0);
+          }
+          // ---- half 1 ----
+          mbar_wait(&bars->pds_full[1], ph);
           tc_fence_after();
-        }
-        // dQ_i = dS K_j  (reduction over the 128 keys; A = the shared-memory copy of dS^T read MN-major: the two
-        // 64-query halves are kHalf apart)
-        const uint32_t sDS = smem_u32(smem + ((i & 1) ? kSmemDST1 : kSmemDST0));
+          issue_dvdk(g, i, 1);
+          if (more) issue_sdp(g + 1, 1);
+          if (g > 0) {
+            mbar_wait(&bars->dq_empty, (g - 1) & 1);
+            tc_fence_after();
+          }
+          // dQ = dS K_j  (reduction over the 128 keys; A = the shared-memory copy of dS^T read MN-major: the two
+          // 64-query halves are kHalf apart)
+          const uint32_t sDS = smem_u32(smem + ((g & 1) ? kSmemDST1 : kSmemDST0));
 #pragma unroll
-        for (int k = 0; k < BT / 16; ++k)
-          umma_ss(tm_DQ, make_sdesc_sw128(sDS + k * 2048, kHalf, 1024),
-                  make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
-        umma_commit(&bars->dq_full);
-        umma_commit(&bars->qdo_empty[i % kStages]);
+          for (int k = 0; k < BT / 16; ++k)
+            umma_ss(tm_DQ, make_sdesc_sw128(sDS + k * 2048, kHalf, 1024),
+                    make_sdesc_sw128(sK + k * 2048, BT * 128, 1024), idesc_dq, k != 0);
+          umma_commit(&bars->dq_full);
+          umma_commit(&bars->qdo_empty[g % kStages]);
+        }
+        umma_commit(&bars->kv_free);
+        gq += w.n_q;
+        ++it;
       }
     }
   } else {
@@ -239,152 +259,179 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int colhalf = (cw >> 2) & 1;  // flush warps (cw < 8): which 32 of the 64 dQ / dK / dV columns
     const bool flusher = cw < kFlushWarps;
     const int r = quarter * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dK/dV, query row for dQ
-    const bool key_ok = (k0 + r) < len;
-    const bool key_tile_partial = (k0 + BT) > len;
     uint8_t* sDQ = smem + kSmemDQ + (cw & (kFlushWarps - 1)) * 4096;
+    uint32_t gq = 0;
+    int it = 0;
 
-    if (colq == 0) {
-      // K_j, V_j -> TMEM (A operands of S^T / dP^T): thread = key row = TMEM lane, 64 fp16 = 32 packed columns each.
-      // One warp per lane quarter; the swizzled 16 B chunks of a row are read in logical order.
-      mbar_wait(&bars->kv_full, 0);
-#pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        const uint8_t* src = smem + (which == 0 ? kSmemK : kSmemV);
-        uint32_t w[32];
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item w = decode(item);
+      const int h = w.h, k0 = w.k0, len = w.len, n_q = w.n_q, row_base = w.row_base;
+      if (k0 >= len) {
+        // masked / padding keys: dK = dV = 0
+        if (colq == 0 && k0 + r < T) {
+          uint4* dk = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + k0 + r) * 768 + 256 + h * HD);
+          uint4* dv = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + k0 + r) * 768 + 512 + h * HD);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = *reinterpret_cast<const uint4*>(src + sw128_offset(r, c));
-          w[c * 4] = u.x; w[c * 4 + 1] = u.y; w[c * 4 + 2] = u.z; w[c * 4 + 3] = u.w;
-        }
-        tmem_st32(tmem_addr(which == 0 ? tm_K : tm_V, quarter * 32, 0), w);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->kv_tmem);
-    }
-
-    auto dq_flush = [&](int i) {   // dQ(i): TMEM -> swizzled smem box -> TMA reduce-add into the fp32 accumulator
-      mbar_wait(&bars->dq_full, i & 1);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_addr(tm_DQ, quarter * 32, colhalf * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
-        mbar_arrive(&bars->dq_empty);
-        tma_store_wait_read0();   // previous reduce of this warp has finished reading the staging box
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
-        tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
-        tma_store_commit();
-      }
-    };
-
-    for (int i = 0; i < n_q; ++i) {
-      const int st = i % kStages;
-      const float* st_lse = (const float*)(smem + kSmemStat + st * kStatBytes);
-      const float* st_dl = st_lse + BT;
-      const bool need_mask = key_tile_partial || (i * BT + BT > len);
-      uint8_t* sDST = smem + ((i & 1) ? kSmemDST1 : kSmemDST0);
-      {
-        // the ring stage (Q_i, dO_i, lse_i, delta_i) is complete before the MMA warp could issue S^T(i); observing
-        // it here orders our generic-proxy reads of lse/delta after the bulk copies.
-        mbar_wait(&bars->qdo_full[st], (i / kStages) & 1);
-      }
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        mbar_wait(&bars->sdp_full[hh], i & 1);
-        tc_fence_after();
-        uint32_t s[16], dp[16];
-        tmem_ld16(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), s);
-        tmem_ld16(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dp);
-        tmem_ld_wait();
-        const int qc0 = hh * 64 + colq * 16;   // first query column (within the 128-query tile) of this thread's run
-        // P^T = p / 8 and dS^T = (p / 8) (dP^T - delta): the exponent carries lse + 3 (log2 units), so the 1/sqrt(d) of
-        // dS costs nothing, and the factor 8 missing from P^T is applied to dV once, when the CTA writes it out (exact
-        // powers of two on both sides). All fp32 math runs as packed pairs (FFMA2 / FMUL2); masked (key, query) pairs
-        // get a score of -inf, which makes both p and dS exactly 0.
-        uint32_t pp[8], dd[8];
-        const f32x2_t c2 = f2_pack(scale_log2, scale_log2), m1 = f2_pack(-1.f, -1.f), m3 = f2_pack(-3.f, -3.f);
-        const int n_ok = key_ok ? (len - i * BT - qc0) : 0;   // valid query columns in this thread's run of 16
-#pragma unroll
-        for (int t = 0; t < 16; t += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
-          const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
-          if (need_mask) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (t + u >= n_ok) s[t + u] = 0xff800000u;   // -inf
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-            const f32x2_t nl = f2_fma(u == 0 ? f2_pack(l4.x, l4.y) : f2_pack(l4.z, l4.w), m1, m3);   // -(lse + 3)
-            const f32x2_t x = f2_fma(f2_pack(__uint_as_float(s[t + u]), __uint_as_float(s[t + u + 1])), c2, nl);
-            float x0, x1;
-            f2_unpack(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            const f32x2_t g = f2_fma(u == 0 ? f2_pack(d4.x, d4.y) : f2_pack(d4.z, d4.w), m1,
-                                     f2_pack(__uint_as_float(dp[t + u]), __uint_as_float(dp[t + u + 1])));   // dP^T - delta
-            float d0, d1;
-            f2_unpack(f2_mul(f2_pack(p0, p1), g), d0, d1);
-            pp[(t + u) >> 1] = pack_f16x2(p0, p1);
-            dd[(t + u) >> 1] = pack_f16x2(d0, d1);
+          for (int i = 0; i < 8; ++i) {
+            dk[i] = make_uint4(0, 0, 0, 0);
+            dv[i] = make_uint4(0, 0, 0, 0);
           }
         }
-        // The S^T / dP^T columns just read become P^T / dS^T (packed fp16, A operands of dV / dK): this warp owns columns
-        // [16 colq, 16 colq + 16) of both accumulators and writes the 8 packed columns of K-step colq at their head.
-        // The shared-memory copy of dS^T (for dQ) goes to the pair of this tile's parity: its last reader, dQ(i-2), was
-        // issued before S^T/dP^T of this half-step, whose commit (sdp_full, observed above) covers it.
-        const uint32_t sub = hh * kHalf;
+        continue;
+      }
+      const bool key_ok = (k0 + r) < len;
+      const bool key_tile_partial = (k0 + BT) > len;
+
+      if (colq == 0) {
+        // K_j, V_j -> TMEM (A operands of S^T / dP^T): thread = key row = TMEM lane, 64 fp16 = 32 packed columns each.
+        // One warp per lane quarter; the swizzled 16 B chunks of a row are read in logical order. (tm_K / tm_V are
+        // free: this warp has consumed the last S^T/dP^T of the previous item.)
+        mbar_wait(&bars->kv_full, it & 1);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint8_t* src = smem + (which == 0 ? kSmemK : kSmemV);
+          uint32_t wv[32];
 #pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-          const uint32_t off = sub + sw128_offset(r, colq * 2 + q4);
-          *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(src + sw128_offset(r, c));
+            wv[c * 4] = u.x; wv[c * 4 + 1] = u.y; wv[c * 4 + 2] = u.z; wv[c * 4 + 3] = u.w;
+          }
+          tmem_st32(tmem_addr(which == 0 ? tm_K : tm_V, quarter * 32, 0), wv);
         }
-        tmem_st8(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), pp);
-        tmem_st8(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dd);
-        // the shared-memory copy is only read by dQ(i), issued after BOTH halves have arrived: one generic->async proxy
-        // fence per tile (in half 1, covering this thread's stores of both halves) instead of one per half-step
-        if (hh == 1) fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->pds_full[hh]);
-        // dQ(i-1) is the last MMA of iteration i-1 (issued after S^T/dP^T of this tile): it has retired by now
-        if (hh == 1 && i > 0 && flusher) dq_flush(i - 1);
+        if (lane == 0) mbar_arrive(&bars->kv_tmem);
       }
-    }
-    if (flusher) dq_flush(n_q - 1);
-    // dK_j, dV_j (all MMAs retired: last dq_full). Each flush warp: 32 key rows x 32 of the 64 columns of each.
-    const int kr = k0 + r;
+
+      auto dq_flush = [&](int i) {   // dQ(i): TMEM -> swizzled smem box -> TMA reduce-add into the fp32 accumulator
+        mbar_wait(&bars->dq_full, (gq + i) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_addr(tm_DQ, quarter * 32, colhalf * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
+          mbar_arrive(&bars->dq_empty);
+          tma_store_wait_read0();   // previous reduce of this warp has finished reading the staging box
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
+          tma_store_commit();
+        }
+      };
+
+      for (int i = 0; i < n_q; ++i) {
+        const uint32_t g = gq + i;
+        const int st = g % kStages;
+        const float* st_lse = (const float*)(smem + kSmemStat + st * kStatBytes);
+        const float* st_dl = st_lse + BT;
+        const bool need_mask = key_tile_partial || (i * BT + BT > len);
+        uint8_t* sDST = smem + ((g & 1) ? kSmemDST1 : kSmemDST0);
+        // the ring stage (Q_i, dO_i, lse_i, delta_i) is complete before the MMA warp could issue S^T(i); observing
+        // it here orders our generic-proxy reads of lse/delta after the bulk copies.
+        mbar_wait(&bars->qdo_full[st], (g / kStages) & 1);
 #pragma unroll 1
-    for (int which = 0; which < (flusher ? 2 : 0); ++which) {
-      const uint32_t src = which == 0 ? tm_DK : tm_DV;
-      uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD + colhalf * 32;
-      uint32_t v[32];
-      tmem_ld32(tmem_addr(src, quarter * 32, colhalf * 32), v);
-      tmem_ld_wait();
-      if (which == 1) {   // dV was accumulated from P^T / 8
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&bars->sdp_full[hh], g & 1);
+          tc_fence_after();
+          uint32_t s[16], dp[16];
+          tmem_ld16(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), s);
+          tmem_ld16(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dp);
+          tmem_ld_wait();
+          const int qc0 = hh * 64 + colq * 16;   // first query column (within the 128-query tile) of this thread's run
+          // P^T = p / 8 and dS^T = (p / 8) (dP^T - delta): the exponent carries lse + 3 (log2 units), so the 1/sqrt(d) of
+          // dS costs nothing, and the factor 8 missing from P^T is applied to dV once, when the CTA writes it out (exact
+          // powers of two on both sides). All fp32 math runs as packed pairs (FFMA2 / FMUL2); masked (key, query) pairs
+          // get a score of -inf, which makes both p and dS exactly 0.
+          uint32_t pp[8], dd[8];
+          const f32x2_t c2 = f2_pack(scale_log2, scale_log2), m1 = f2_pack(-1.f, -1.f), m3 = f2_pack(-3.f, -3.f);
+          const int n_ok = key_ok ? (len - i * BT - qc0) : 0;   // valid query columns in this thread's run of 16
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * 8.f);
-      }
-      if (kr < T) {
-        uint4* dst = reinterpret_cast<uint4*>(dst_row);
+          for (int t = 0; t < 16; t += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + qc0 + t);
+            const float4 d4 = *reinterpret_cast<const float4*>(st_dl + qc0 + t);
+            if (need_mask) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
-                              pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
-                              pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
-                              pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
+              for (int u = 0; u < 4; ++u)
+                if (t + u >= n_ok) s[t + u] = 0xff800000u;   // -inf
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const f32x2_t nl = f2_fma(u == 0 ? f2_pack(l4.x, l4.y) : f2_pack(l4.z, l4.w), m1, m3);   // -(lse + 3)
+              const f32x2_t x = f2_fma(f2_pack(__uint_as_float(s[t + u]), __uint_as_float(s[t + u + 1])), c2, nl);
+              float x0, x1;
+              f2_unpack(x, x0, x1);
+              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+              const f32x2_t gd = f2_fma(u == 0 ? f2_pack(d4.x, d4.y) : f2_pack(d4.z, d4.w), m1,
+                                        f2_pack(__uint_as_float(dp[t + u]), __uint_as_float(dp[t + u + 1])));   // dP^T - delta
+              float d0, d1;
+              f2_unpack(f2_mul(f2_pack(p0, p1), gd), d0, d1);
+              pp[(t + u) >> 1] = pack_f16x2(p0, p1);
+              dd[(t + u) >> 1] = pack_f16x2(d0, d1);
+            }
+          }
+          // The S^T / dP^T columns just read become P^T / dS^T (packed fp16, A operands of dV / dK): this warp owns columns
+          // [16 colq, 16 colq + 16) of both accumulators and writes the 8 packed columns of K-step colq at their head.
+          // The shared-memory copy of dS^T (for dQ) goes to the pair of this tile's parity: its last reader, the dQ two
+          // tiles back, was issued before S^T/dP^T of this half-step, whose commit (sdp_full, observed above) covers it.
+          const uint32_t sub = hh * kHalf;
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const uint32_t off = sub + sw128_offset(r, colq * 2 + q4);
+            *reinterpret_cast<uint4*>(sDST + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          }
+          tmem_st8(tmem_addr(tm_ST + hh * 64, quarter * 32, colq * 16), pp);
+          tmem_st8(tmem_addr(tm_DPT + hh * 64, quarter * 32, colq * 16), dd);
+          // the shared-memory copy is only read by dQ(i), issued after BOTH halves have arrived: one generic->async proxy
+          // fence per tile (in half 1, covering this thread's stores of both halves) instead of one per half-step
+          if (hh == 1) fence_proxy_async_smem();
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->pds_full[hh]);
+          // dQ(i-1) is the last MMA of iteration i-1 (issued after S^T/dP^T of this tile): it has retired by now
+          if (hh == 1 && i > 0 && flusher) dq_flush(i - 1);
+        }
       }
+      if (flusher) {
+        dq_flush(n_q - 1);
+        // dK_j, dV_j (all MMAs of the item retired: last dq_full). Each flush warp: 32 key rows x 32 of the 64 columns.
+        const int kr = k0 + r;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t src = which == 0 ? tm_DK : tm_DV;
+          uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD + colhalf * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_addr(src, quarter * 32, colhalf * 32), v);
+          tmem_ld_wait();
+          if (which == 1) {   // dV was accumulated from P^T / 8
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * 8.f);
+          }
+          if (kr < T) {
+            uint4* dst = reinterpret_cast<uint4*>(dst_row);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
+                                  pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
+                                  pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
+                                  pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
+          }
+        }
+        // the accumulators are read: the next item's first dV/dK MMAs (accumulate = 0) are issued only after this warp
+        // has arrived on pds_full of that item's first tile, i.e. after this point in program order
+        tc_fence_before();
+      }
+      gq += n_q;
+      ++it;
     }
     if (flusher && elect_one()) tma_store_wait_read0();
   }
@@ -475,9 +522,11 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     tmp::set_error("attn_bwd memset: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  dim3 grid((T + BT - 1) / BT, H, B);
-  attn_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, kv_len, T, lse2, delta, T_lse, (uint16_t*)dQKV,
-                                                      kLog2e / 8.0f);
+  const int n_jt = (T + BT - 1) / BT;
+  const int n_items = n_jt * H * B;
+  const int sms = tmp::num_sms();
+  attn_bwd_kernel<<<n_items < sms ? n_items : sms, kThreads, kSmemTotal, st>>>(
+      tmQKV, tmDO, tmDQ, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
   rc = tmp::check_launch("attn_bwd_kernel");
   if (rc) return rc;
   const size_t rows = (size_t)B * T;
