@@ -26,6 +26,8 @@
 // the fp32 accumulator with cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b]
 // applied in-register, only in boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly
 // 0, as in the reference).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -86,9 +88,10 @@ struct Bars {
 // processed so far, it = live items so far).
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQ, const int32_t* __restrict__ kv_len, int T, int n_jt, int H,
+                const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
+                const int32_t* __restrict__ kv_len, int T, int n_jt, int H,
                 int n_items, const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
-                uint16_t* __restrict__ dQKV, float scale_log2) {
+                uint16_t* __restrict__ dQKV, float scale_log2, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   Bars* bars = (Bars*)(smem + kSmemBar);
@@ -100,6 +103,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmDQ);
+    prefetch_tmap(&tmDKV);
     mbar_init(&bars->kv_full, 1);
     mbar_init(&bars->kv_tmem, 4);
     mbar_init(&bars->kv_free, 1);
@@ -322,7 +326,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (elect_one()) {
+        if (!(dbg & 1) && elect_one()) {
           tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
           tma_store_commit();
         }
@@ -403,27 +407,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       if (flusher) {
         dq_flush(n_q - 1);
-        // dK_j, dV_j (all MMAs of the item retired: last dq_full). Each flush warp: 32 key rows x 32 of the 64 columns.
+        // dK_j, dV_j (all MMAs of the item retired: last dq_full). Flush warp (quarter, colhalf) writes all 64 columns of
+        // 32 key rows of ONE of the two (colhalf 0: dK, 1: dV): a [32 x 128 B] box, staged in the warp's swizzled dQ
+        // box and written with one TMA store. (Per-thread 16 B stores to 32 different rows per instruction -- 32
+        // partial sectors each -- cost 1.8 us per item, 25 us of the 267 us kernel at T=1005.)
+        const int which = colhalf;
+        const uint32_t src = which == 0 ? tm_DK : tm_DV;
+        const float osc = which == 0 ? 1.f : 8.f;   // dV was accumulated from P^T / 8
         const int kr = k0 + r;
+        const bool full_tile = (k0 + BT) <= T;      // the 2-D map cannot clip at the sample boundary: last tile by hand
+        if (full_tile) {
+          if (elect_one()) tma_store_wait_read0();  // last dQ reduce has finished reading the staging box
+          __syncwarp();
+        }
 #pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-          const uint32_t src = which == 0 ? tm_DK : tm_DV;
-          uint16_t* dst_row = dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD + colhalf * 32;
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tmem_ld32(tmem_addr(src, quarter * 32, colhalf * 32), v);
+          tmem_ld32(tmem_addr(src, quarter * 32, c * 32), v);
           tmem_ld_wait();
-          if (which == 1) {   // dV was accumulated from P^T / 8
+          uint4 u[4];
 #pragma unroll
-            for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * 8.f);
+          for (int t = 0; t < 4; ++t)
+            u[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]) * osc, __uint_as_float(v[t * 8 + 1]) * osc),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 2]) * osc, __uint_as_float(v[t * 8 + 3]) * osc),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 4]) * osc, __uint_as_float(v[t * 8 + 5]) * osc),
+                              pack_f16x2(__uint_as_float(v[t * 8 + 6]) * osc, __uint_as_float(v[t * 8 + 7]) * osc));
+          if (full_tile) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, c * 4 + t)) = u[t];
+          } else if (kr < T && !(dbg & 2)) {
+            uint4* dst = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD +
+                                                  c * 32);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dst[t] = u[t];
           }
-          if (kr < T) {
-            uint4* dst = reinterpret_cast<uint4*>(dst_row);
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              dst[t] = make_uint4(pack_f16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1])),
-                                  pack_f16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3])),
-                                  pack_f16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5])),
-                                  pack_f16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7])));
+        }
+        if (full_tile) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (!(dbg & 2) && elect_one()) {
+            tma_store_2d(&tmDKV, sDQ, (which == 0 ? 256 : 512) + h * HD, row_base + k0 + quarter * 32);
+            tma_store_commit();
           }
         }
         // the accumulators are read: the next item's first dV/dK MMAs (accumulate = 0) are issued only after this warp
@@ -495,6 +519,8 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   TMP_REQUIRE(B > 0 && T > 0 && H == 4 && ld == 256, "attn_bwd: need H==4, ld==256 (B=%d T=%d H=%d ld=%d)", B, T, H, ld);
   TMP_REQUIRE(T_lse % BT == 0 && T_lse >= T, "attn_bwd: T_lse must be a multiple of 128 and >= T");
   cudaStream_t st = (cudaStream_t)stream;
+  // timing experiments only (tools/): 1 = no dQ reduce, 2 = no dK/dV write-out, 4 = main kernel alone (no delta / memset / convert)
+  static const int dbg = getenv("TMP_B200_BWD_DBG") ? atoi(getenv("TMP_B200_BWD_DBG")) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
@@ -504,20 +530,22 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     }
     attr_set = true;
   }
-  CUtensorMap tmQKV, tmDO, tmDQ;
+  CUtensorMap tmQKV, tmDO, tmDQ, tmDKV;
   int rc = tmp::encode_tmap_2d_bf16(&tmQKV, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BT);
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmDO, dO, 256, (uint64_t)B * T, (uint64_t)ld * 2, HD, BT);
   if (rc) return rc;
+  rc = tmp::encode_tmap_2d_bf16(&tmDKV, dQKV, 768, (uint64_t)B * T, 768 * 2, 64, 32);   // dK / dV boxes [32 rows x 64 cols]
+  if (rc) return rc;
   rc = tmp::encode_tmap_2d_f32(&tmDQ, dQ_acc, 256, (uint64_t)B * T, 256 * 4, 32, 32);   // reduce-add boxes [32 rows x 32 fp32]
   if (rc) return rc;
-  {
+  if (!(dbg & 4)) {
     const int rows = B * T_lse;
     attn_bwd_delta_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const uint16_t*)O, (const uint16_t*)dO, ld, B, T, H, delta, T_lse);
     rc = tmp::check_launch("attn_bwd_delta_kernel");
     if (rc) return rc;
   }
-  cudaError_t e = cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
+  cudaError_t e = (dbg & 4) ? cudaSuccess : cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
   if (e != cudaSuccess) {
     tmp::set_error("attn_bwd memset: %s", cudaGetErrorString(e));
     return (int)e;
@@ -526,9 +554,9 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   const int n_items = n_jt * H * B;
   const int sms = tmp::num_sms();
   attn_bwd_kernel<<<n_items < sms ? n_items : sms, kThreads, kSmemTotal, st>>>(
-      tmQKV, tmDO, tmDQ, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
+      tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f, dbg);
   rc = tmp::check_launch("attn_bwd_kernel");
-  if (rc) return rc;
+  if (rc || (dbg & 4)) return rc;
   const size_t rows = (size_t)B * T;
   attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (uint16_t*)dQKV, rows);
   return tmp::check_launch("attn_bwd_dq_convert_kernel");
