@@ -56,7 +56,8 @@ struct Bars {
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __restrict__ kv_len, int T, int ld_o,
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
+                const int32_t* __restrict__ kv_len, int T, int ld_o,
                 uint16_t* __restrict__ O, float* __restrict__ lse2, int T_lse, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -86,6 +87,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQKV);
+    prefetch_tmap(&tmO);
     mbar_init(&bars->q_full, 1);
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&bars->k_full[s], 1);
@@ -259,28 +261,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
     }
-    // epilogue
+    // epilogue: O / l -> fp16. A full query tile is staged as one swizzled [32 rows x 128 B] box per warp in the Q buffer
+    // (dead: the last S MMA retired before this warp read S of the last tile) and leaves through a TMA store; 16 B
+    // stores from 32 threads to 32 different rows per instruction (32 partial sectors each) were ~10 % of the kernel.
     mbar_wait(&bars->o_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
     const int q = q0 + r;
+    const bool full_tile = q0 + BQ <= T;   // the 2-D map cannot clip at the sample boundary: the last tile goes by hand
+    uint8_t* sO = smem + kSmemQ + quarter * 4096;
     uint32_t o[32];
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       tmem_ld32(t_O + c * 32, o);
       tmem_ld_wait();
-      if (q < T) {
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        u[i].x = pack_f16x2(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
+        u[i].y = pack_f16x2(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
+        u[i].z = pack_f16x2(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
+        u[i].w = pack_f16x2(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
+      }
+      if (full_tile) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(sO + sw128_offset(lane, c * 4 + i)) = u[i];
+      } else if (q < T) {
         uint4* dst = reinterpret_cast<uint4*>(O + (size_t)(row_base + q) * ld_o + h * HD + c * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_f16x2(__uint_as_float(o[i * 8 + 0]) * inv_l, __uint_as_float(o[i * 8 + 1]) * inv_l);
-          u.y = pack_f16x2(__uint_as_float(o[i * 8 + 2]) * inv_l, __uint_as_float(o[i * 8 + 3]) * inv_l);
-          u.z = pack_f16x2(__uint_as_float(o[i * 8 + 4]) * inv_l, __uint_as_float(o[i * 8 + 5]) * inv_l);
-          u.w = pack_f16x2(__uint_as_float(o[i * 8 + 6]) * inv_l, __uint_as_float(o[i * 8 + 7]) * inv_l);
-          dst[i] = u;
-        }
+        for (int i = 0; i < 4; ++i) dst[i] = u[i];
       }
+    }
+    if (full_tile) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_2d(&tmO, sO, h * HD, row_base + q0 + quarter * 32);
+        tma_store_commit();
+        tma_store_wait_read0();   // the box must stay valid until the copy engine has read it
+      }
+      __syncwarp();
     }
     if (q < T) lse2[((size_t)b * gridDim.y + h) * T_lse + q] = m_ref * scale_log2 + log2f(l);
   }
@@ -312,12 +332,14 @@ extern "C" int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, i
     }
     attr_set = true;
   }
-  CUtensorMap tm;
+  CUtensorMap tm, tmO;
   int rc = tmp::encode_tmap_2d_bf16(&tm, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BQ);
+  if (rc) return rc;
+  rc = tmp::encode_tmap_2d_bf16(&tmO, O, (uint64_t)ld_o, (uint64_t)B * T, (uint64_t)ld_o * 2, 64, 32);   // O boxes [32 rows x 64 cols]
   if (rc) return rc;
   dim3 grid((T + BQ - 1) / BQ, H, B);
   const float scale_log2 = kLog2e / 8.0f;  // 1/sqrt(d_head=64) in log2 units (attention.py:16,35)
-  attn_fwd_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(tm, kv_len, T, ld_o, (uint16_t*)O, lse2, T_lse,
+  attn_fwd_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(tm, tmO, kv_len, T, ld_o, (uint16_t*)O, lse2, T_lse,
                                                                           scale_log2);
   return tmp::check_launch("attn_fwd_kernel");
 }
