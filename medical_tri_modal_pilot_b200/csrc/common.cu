@@ -31,11 +31,17 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* gaddr, uint64_t inner, uint64_t outer,
-                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer) {
   return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer);
+}
+int encode_tmap_2d_bf16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                             uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer,
+                        CU_TENSOR_MAP_SWIZZLE_64B);
 }
 int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                        uint32_t box_inner, uint32_t box_outer) {
@@ -43,7 +49,7 @@ int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint
 }
 
 static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* gaddr, uint64_t inner, uint64_t outer,
-                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
   auto fn = get_encode();
   if (!fn) return TMP_ERR_DRIVER;
   if (((uintptr_t)gaddr & 15) || (row_stride_bytes & 15)) {
@@ -55,7 +61,7 @@ static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* 
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void*>(gaddr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult=%d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,

@@ -18,8 +18,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 constexpr int kThreadsW = 192;                  // wgrad kernel: 4 epilogue warps
 constexpr int kBiasSmemFloats = 1024;
 
@@ -57,8 +57,9 @@ struct SmemLayout {
   static constexpr int kRingOffset = kBResBytes;
   static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
   static constexpr int kOutOffset = kRingOffset + kStages * kStageBytes;
-  static constexpr int kOutBufs = WS ? 1 : 2;                          // per epilogue warp: [32 rows x 128 B] boxes
-  static constexpr int kOutBytes = kEpiWarps * kOutBufs * 4096;
+  static constexpr int kOutBufs = WS ? 1 : 2;                          // per epilogue warp: [32 rows x 64 B] boxes
+  static constexpr int kOutBoxBytes = 2048;
+  static constexpr int kOutBytes = kEpiWarps * kOutBufs * kOutBoxBytes;
   static constexpr int kBiasOffset = kOutOffset + kOutBytes;
   static constexpr int kBiasFloats = WS ? BN : kBiasSmemFloats;
   static constexpr int kBarOffset = kBiasOffset + kBiasFloats * 4;
@@ -264,16 +265,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // warp -> (TMEM lane quarter it may access, column half of the tile). Each thread owns one output row and walks
-    // BN/2 columns in 32-column chunks; TMEM loads are software-pipelined one chunk ahead; 16-bit results are staged in
-    // 128B-swizzled smem boxes of [32 rows x 64 cols] and written with TMA stores (coalesced, asynchronous, M-tail
-    // clipped by the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B).
+    // ===================== epilogue (warps 2..17) =====================
+    // 16 warps = 4 per scheduler: the fused epilogue is a dependent chain per warp (tcgen05.ld -> bias/activation/dropout
+    // -> pack -> smem -> TMA store) and ran at 43-48 % issue utilisation with 2 warps per scheduler (profiles/r1g).
+    // warp -> (TMEM lane quarter it may access, column quarter of the tile). Each thread owns one output row and BN/4
+    // columns in 32-column chunks; 16-bit results are staged as [32 rows x 32 cols] boxes (64 B rows inside the 128B
+    // swizzle pattern: two rows per 128 B line) and written with TMA stores (coalesced, asynchronous, M-tail clipped by
+    // the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B). The elected lane
+    // issues the stores AND waits on their bulk groups (the groups are per thread; the election is deterministic).
     const int e = warp - 2;
     const int quarter = warp & 3;
-    const int half = e >> 2;
-    constexpr int kChunks = BN / 64;   // 32-column chunks per warp
-    uint8_t* stage_buf = smem + L::kOutOffset + e * (L::kOutBufs * 4096);
+    const int cg = e >> 2;
+    constexpr int kChunks = BN / 128;   // 32-column chunks per warp
+    uint8_t* stage_buf = smem + L::kOutOffset + e * (L::kOutBufs * L::kOutBoxBytes);
     const float* sb_ptr = bias_in_smem ? sbias - n_fixed : nullptr;
     int sbuf = 0;
     int acc = 0;
@@ -285,19 +289,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      const int colw = n0 + half * (BN / 2);
-      const uint32_t taddr = tmem_addr(tmem_base, quarter * 32, acc * BN + half * (BN / 2));
-      // The chunk loop is deliberately NOT unrolled: one copy of the fused epilogue keeps the kernel ~25 KB of SASS
-      // (fully unrolled it was 100 KB and the 8 epilogue warps stalled on instruction fetch: ncu no_instruction 1.2/issue).
-      uint32_t r[32];
-      tmem_ld32(taddr, r);
+      const int colw = n0 + cg * (BN / 4);
+      const uint32_t taddr = tmem_addr(tmem_base, quarter * 32, acc * BN + cg * (BN / 4));
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (c + 1 < kChunks) tmem_ld32(taddr + (c + 1) * 32, r);   // next chunk in flight under this chunk's math
         if (c == kChunks - 1) {
           // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
@@ -312,38 +313,41 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
         if (p.out) {
-          uint8_t* sbox = stage_buf + sbuf * 4096;
-          if ((c & 1) == 0) {
-            // the TMA store that last used this buffer must have finished reading it
-            if (lane == 0) {
-              if (L::kOutBufs == 2) tma_store_wait_read1();
-              else tma_store_wait_read0();
-            }
-            __syncwarp();
+          uint8_t* sbox = stage_buf + sbuf * L::kOutBoxBytes;
+          // the TMA store that last used this buffer must have finished reading it
+          if (elect_one()) {
+            if (L::kOutBufs == 2) tma_store_wait_read1();
+            else tma_store_wait_read0();
           }
+          __syncwarp();
+          uint4 u[4];
+          if (p.out_fmt == FMT_F16) {   // uniform branch: one pack per pair (the ternary form computed both formats)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            u.x = pack2_rt(v[q * 8 + 0], v[q * 8 + 1], p.out_fmt);
-            u.y = pack2_rt(v[q * 8 + 2], v[q * 8 + 3], p.out_fmt);
-            u.z = pack2_rt(v[q * 8 + 4], v[q * 8 + 5], p.out_fmt);
-            u.w = pack2_rt(v[q * 8 + 6], v[q * 8 + 7], p.out_fmt);
-            *reinterpret_cast<uint4*>(sbox + sw128_offset(lane, (c & 1) * 4 + q)) = u;
+            for (int q = 0; q < 4; ++q)
+              u[q] = make_uint4(pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              u[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
           }
-          if ((c & 1) == 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmOut, sbox, colw + (c - 1) * 32, m0 + quarter * 32);
-              tma_store_commit();
-            }
-            if (L::kOutBufs == 2) sbuf ^= 1;
+          // 64B-swizzled box, dense 64 B rows: 16 B chunk q of row `lane` at lane*64 + ((q ^ ((lane >> 1) & 3)) << 4)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(sbox + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u[q];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmOut, sbox, col0, m0 + quarter * 32);
+            tma_store_commit();
           }
+          if (L::kOutBufs == 2) sbuf ^= 1;
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait_read0();
+    if (elect_one()) tma_store_wait_read0();
   }
 
   tc_fence_before();
@@ -593,8 +597,8 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   CUtensorMap tmOut;
   if (out_bf16) {
-    // 16-bit output written by TMA: boxes of [32 rows x 64 cols], 128B swizzle; rows >= M are clipped
-    rc = tmp::encode_tmap_2d_bf16(&tmOut, out_bf16, (uint64_t)N, (uint64_t)M, (uint64_t)ld_out * 2, 64, 32);
+    // 16-bit output written by TMA: boxes of [32 rows x 32 cols], 64B swizzle; rows >= M are clipped
+    rc = tmp::encode_tmap_2d_bf16_sw64(&tmOut, out_bf16, (uint64_t)N, (uint64_t)M, (uint64_t)ld_out * 2, 32, 32);
     if (rc) return rc;
   } else {
     tmOut = tmA;
