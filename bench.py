@@ -348,6 +348,31 @@ def _finish(world, model):
     os._exit(0)
 
 
+def profiled_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel_substr`, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/summarize_profiles.py; captured at the bench shapes by
+    tools/profile_kernels.py). Returns (bytes, file) or (None, None)."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full.csv")), reverse=True):
+        try:
+            with open(path) as f:
+                rows = list(csv.reader(f))
+            hdr = rows[0]
+            ir = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum"))
+            iw = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum"))
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            ur = scale.get(hdr[ir].split("[")[-1].rstrip("]"), 1e6)
+            uw = scale.get(hdr[iw].split("[")[-1].rstrip("]"), 1e6)
+            hits = [r for r in rows[1:] if kernel_substr in r[1]]
+            if hits:
+                r = hits[-1]
+                return float(r[ir]) * ur + float(r[iw]) * uw, os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def dominant_kernel_roofline(a, model, peaks, peak_src, iters=10):
     """Times the kernel that takes the largest share of the step (attn_bwd_kernel on the vslt stream; share per
     profiles/) alone, on the current stream, with CUDA events; algorithmic FLOPs = 10*Sq*Sk*d per (sample, head)
@@ -375,9 +400,12 @@ def dominant_kernel_roofline(a, model, peaks, peak_src, iters=10):
     flops = float((10.0 * lens * lens * 64 * 4).sum().item())
     ach = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    traffic, src = profiled_traffic("attn_bwd_kernel") if (a.tie_len == 1000 and a.batch == 64 and not a.realistic) else (None, None)
     return {"kernel": "attn_bwd_kernel (+delta, dQ convert; vslt stream, one layer)", "bound": "tensor",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src,
-            "ms_per_launch": ms, "flops_per_launch": flops, "traffic": None}
+            "ms_per_launch": ms, "flops_per_launch": flops, "traffic": traffic,
+            "traffic_source": (f"profiles/{src}: dram read+write bytes of attn_bwd_kernel, one launch at these shapes"
+                               if src else None)}
 
 
 if __name__ == "__main__":
