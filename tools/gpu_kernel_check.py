@@ -327,7 +327,9 @@ def case_attn_fwd():
     torch.manual_seed(6)
     dev = "cuda"
     res = {}
-    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (2, 54, [54, 54])]:
+    many = [300, 0, 150, 4, 299, 129, 128, 1] * 5   # 40 samples x 4 heads x 3 tiles = 480 work items (> SM count)
+    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (2, 54, [54, 54]),
+                         (40, 300, many)]:
         qkv = (torch.randn(B * T, 768, device=dev) * 1.5).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
         O = torch.full((B * T, 256), 7.0, device=dev, dtype=ACT)
@@ -347,7 +349,10 @@ def case_attn_bwd():
     torch.manual_seed(7)
     dev = "cuda"
     res = {}
-    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600])]:
+    # last case: 480 (key tile, head, sample) items on 148 persistent CTAs -- several items per CTA, de-selected
+    # samples (kv_len 0), dead and partial key tiles in between
+    many = [300, 0, 150, 4, 299, 129, 128, 1] * 5
+    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (40, 300, many)]:
         qkv = (torch.randn(B * T, 768, device=dev)).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
         live = (torch.arange(T, device=dev)[None, :] < kv[:, None])
