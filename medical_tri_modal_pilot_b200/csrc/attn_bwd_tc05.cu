@@ -26,8 +26,6 @@
 // the fp32 accumulator with cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b]
 // applied in-register, only in boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly
 // 0, as in the reference).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -91,7 +89,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
                 const int32_t* __restrict__ kv_len, int T, int n_jt, int H,
                 int n_items, const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
-                uint16_t* __restrict__ dQKV, float scale_log2, int dbg) {
+                uint16_t* __restrict__ dQKV, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   Bars* bars = (Bars*)(smem + kSmemBar);
@@ -326,7 +324,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (!(dbg & 1) && elect_one()) {
+        if (elect_one()) {
           tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
           tma_store_commit();
         }
@@ -435,7 +433,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           if (full_tile) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, c * 4 + t)) = u[t];
-          } else if (kr < T && !(dbg & 2)) {
+          } else if (kr < T) {
             uint4* dst = reinterpret_cast<uint4*>(dQKV + (size_t)(row_base + kr) * 768 + (which == 0 ? 256 : 512) + h * HD +
                                                   c * 32);
 #pragma unroll
@@ -445,7 +443,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (full_tile) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (!(dbg & 2) && elect_one()) {
+          if (elect_one()) {
             tma_store_2d(&tmDKV, sDQ, (which == 0 ? 256 : 512) + h * HD, row_base + k0 + quarter * 32);
             tma_store_commit();
           }
@@ -519,8 +517,6 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   TMP_REQUIRE(B > 0 && T > 0 && H == 4 && ld == 256, "attn_bwd: need H==4, ld==256 (B=%d T=%d H=%d ld=%d)", B, T, H, ld);
   TMP_REQUIRE(T_lse % BT == 0 && T_lse >= T, "attn_bwd: T_lse must be a multiple of 128 and >= T");
   cudaStream_t st = (cudaStream_t)stream;
-  // timing experiments only (tools/): 1 = no dQ reduce, 2 = no dK/dV write-out, 4 = main kernel alone (no delta / memset / convert)
-  static const int dbg = getenv("TMP_B200_BWD_DBG") ? atoi(getenv("TMP_B200_BWD_DBG")) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
@@ -539,13 +535,13 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_f32(&tmDQ, dQ_acc, 256, (uint64_t)B * T, 256 * 4, 32, 32);   // reduce-add boxes [32 rows x 32 fp32]
   if (rc) return rc;
-  if (!(dbg & 4)) {
+  {
     const int rows = B * T_lse;
     attn_bwd_delta_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const uint16_t*)O, (const uint16_t*)dO, ld, B, T, H, delta, T_lse);
     rc = tmp::check_launch("attn_bwd_delta_kernel");
     if (rc) return rc;
   }
-  cudaError_t e = (dbg & 4) ? cudaSuccess : cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
   if (e != cudaSuccess) {
     tmp::set_error("attn_bwd memset: %s", cudaGetErrorString(e));
     return (int)e;
@@ -554,9 +550,9 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   const int n_items = n_jt * H * B;
   const int sms = tmp::num_sms();
   attn_bwd_kernel<<<n_items < sms ? n_items : sms, kThreads, kSmemTotal, st>>>(
-      tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f, dbg);
+      tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
   rc = tmp::check_launch("attn_bwd_kernel");
-  if (rc || (dbg & 4)) return rc;
+  if (rc) return rc;
   const size_t rows = (size_t)B * T;
   attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (uint16_t*)dQKV, rows);
   return tmp::check_launch("attn_bwd_dq_convert_kernel");
