@@ -314,17 +314,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (elect_one()) {   // the same (deterministically elected) lane owns this warp's bulk groups
-          mbar_arrive(&bars->dq_empty);
-          tma_store_wait_read0();   // previous reduce of this warp has finished reading the staging box
-        }
+        if (lane == 0) mbar_arrive(&bars->dq_empty);
+        tma_store_wait_read0();   // previous reduce / store of this warp has finished reading the staging box (every lane
+                                  // waits: bulk groups are per thread, lanes without any return at once)
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (elect_one()) {
+        if (lane == 0) {
           tma_reduce_add_2d(&tmDQ, sDQ, h * HD + colhalf * 32, row_base + i * BT + quarter * 32);
           tma_store_commit();
         }
@@ -415,7 +414,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int kr = k0 + r;
         const bool full_tile = (k0 + BT) <= T;      // the 2-D map cannot clip at the sample boundary: last tile by hand
         if (full_tile) {
-          if (elect_one()) tma_store_wait_read0();  // last dQ reduce has finished reading the staging box
+          tma_store_wait_read0();  // last dQ reduce has finished reading the staging box
           __syncwarp();
         }
 #pragma unroll 1
@@ -443,7 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (full_tile) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (elect_one()) {
+          if (lane == 0) {
             tma_store_2d(&tmDKV, sDQ, (which == 0 ? 256 : 512) + h * HD, row_base + k0 + quarter * 32);
             tma_store_commit();
           }
@@ -455,7 +454,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       gq += n_q;
       ++it;
     }
-    if (flusher && elect_one()) tma_store_wait_read0();
+    if (flusher) tma_store_wait_read0();
   }
 
   tc_fence_before();

@@ -295,7 +295,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (full_tile) {
       fence_proxy_async_smem();
       __syncwarp();
-      if (elect_one()) {
+      if (lane == 0) {
         tma_store_2d(&tmO, sO, h * HD, row_base + q0 + quarter * 32);
         tma_store_commit();
         tma_store_wait_read0();   // the box must stay valid until the copy engine has read it

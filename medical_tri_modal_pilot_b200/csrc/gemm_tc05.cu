@@ -280,8 +280,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // warp -> (TMEM lane quarter it may access, column quarter of the tile). Each thread owns one output row and BN/4
     // columns in 32-column chunks; 16-bit results are staged as [32 rows x 32 cols] boxes (64 B rows inside the 128B
     // swizzle pattern: two rows per 128 B line) and written with TMA stores (coalesced, asynchronous, M-tail clipped by
-    // the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B). The elected lane
-    // issues the stores AND waits on their bulk groups (the groups are per thread; the election is deterministic).
+    // the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B). Lane 0 issues the
+    // stores; every lane executes the bulk-group waits (groups are per thread, lanes without any return at once).
     const int e = warp - 2;
     const int quarter = warp & 3;
     const int cg = e >> 2;
@@ -324,10 +324,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.out) {
           uint8_t* sbox = stage_buf + sbuf * L::kOutBoxBytes;
           // the TMA store that last used this buffer must have finished reading it
-          if (elect_one()) {
-            if (L::kOutBufs == 2) tma_store_wait_read1();
-            else tma_store_wait_read0();
-          }
+          // (every lane executes the wait: bulk groups are per thread, lanes without any return at once -- no reliance on
+          // elect.sync picking the same lane that committed the store)
+          if (L::kOutBufs == 2) tma_store_wait_read1();
+          else tma_store_wait_read0();
           __syncwarp();
           uint4 u[4];
           if (p.out_fmt == FMT_F16) {   // uniform branch: one pack per pair (the ternary form computed both formats)
@@ -347,7 +347,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(sbox + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u[q];
           fence_proxy_async_smem();
           __syncwarp();
-          if (elect_one()) {
+          if (lane == 0) {   // fixed lane: its bulk groups gate the reuse of this warp's staging boxes
             tma_store_2d(&tmOut, sbox, col0, m0 + quarter * 32);
             tma_store_commit();
           }
@@ -356,7 +356,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (elect_one()) tma_store_wait_read0();
+    tma_store_wait_read0();
   }
 
   tc_fence_before();
