@@ -36,6 +36,9 @@ struct EpiParams {
   int out_fmt, gate_fmt, res_fmt;
   uint32_t drop_thr16;    // 0 = no dropout; else round(p*65536)
   float drop_scale;       // 1/(1-p)
+  int drop_fold;          // 1: 1/(1-p) is already folded into alpha and the bias (every epilogue but GELU is positively
+                          // homogeneous), dropout only zeroes
+  float bias_scale;       // factor on the bias (1/(1-p) when folded, else 1)
   uint32_t drop_seed, drop_salt;   // mask = f(dropout_key(drop_seed + *drop_seed_dev, drop_salt), element index)
   const uint32_t* drop_seed_dev;   // optional device word added to the seed (CUDA-graph replays), or null
   uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
@@ -113,7 +116,8 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        v[j] = fmaf(b.x, p.bias_scale, v[j]); v[j + 1] = fmaf(b.y, p.bias_scale, v[j + 1]);
+        v[j + 2] = fmaf(b.z, p.bias_scale, v[j + 2]); v[j + 3] = fmaf(b.w, p.bias_scale, v[j + 3]);
       }
     }
   }
@@ -140,8 +144,11 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
       }
     }
   }
-  if (p.drop_thr16)
-    dropout_apply_run<32>(v, drop_key, (uint32_t)row * (uint32_t)p.N + (uint32_t)col0, p.drop_thr16, p.drop_scale);
+  if (p.drop_thr16) {
+    const uint32_t idx0 = (uint32_t)row * (uint32_t)p.N + (uint32_t)col0;
+    if (p.drop_fold) dropout_zero_run<32>(v, drop_key, idx0, p.drop_thr16);
+    else dropout_apply_run<32>(v, drop_key, idx0, p.drop_thr16, p.drop_scale);
+  }
   if (p.residual && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
     uint4 u[4];
@@ -207,9 +214,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (bias_in_smem) {
     if (WS) {
-      for (int i = threadIdx.x; i < BN; i += kThreads) sbias[i] = p.bias[n_fixed + i];
+      for (int i = threadIdx.x; i < BN; i += kThreads) sbias[i] = p.bias[n_fixed + i] * p.bias_scale;
     } else {
-      for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i];
+      for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i] * p.bias_scale;
     }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -602,6 +609,9 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.out_fmt = out_fmt; p.gate_fmt = gate_fmt; p.res_fmt = res_fmt;
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_fold = (drop_p > 0.f && relu != 2) ? 1 : 0;
+  p.bias_scale = p.drop_fold ? p.drop_scale : 1.f;
+  if (p.drop_fold) p.alpha = alpha * p.drop_scale;
   p.drop_seed = seed; p.drop_salt = salt; p.drop_seed_dev = seed_dev;
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   CUtensorMap tmOut;

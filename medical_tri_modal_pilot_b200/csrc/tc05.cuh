@@ -326,10 +326,12 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-// Dropout keep-mask: one 32-bit hash per PAIR of consecutive elements, 16 bits each (thr16 = round(p * 65536)).
+// Dropout keep-mask: one hash per PAIR of consecutive elements (thr16 = round(p * 65536)).
 //   key  = dropout_key(seed, salt)                        (uniform per launch)
-//   bits = dropout_bits(key, idx >> 1)                    (IMAD + xorshift + multiply + xorshift)
-//   keep(idx) = 16-bit lane (idx & 1) of bits >= thr16
+//   h    = dropout_bits(key, idx >> 1)                    (IMAD + xorshift)
+//   keep(idx) = top 16 bits of h * C_(idx & 1) >= thr16   (one IMAD + one compare per element)
+// Two odd multipliers give the two elements of a pair independent top halves; the multiplies run on the FMA pipe,
+// which the fused GEMM epilogues leave idle, instead of a second xorshift + mask on the half-rate integer pipe.
 // Forward and backward kernels evaluate the same function of (seed, salt, element index), so no mask is stored.
 __host__ __device__ __forceinline__ uint32_t dropout_key(uint32_t seed, uint32_t salt) {
   return mix32(seed) ^ (salt * 0x85ebca6bU);
@@ -342,12 +344,10 @@ __device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t
 __host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t pair_idx) {
   uint32_t h = pair_idx * 0x9E3779B1U + key;
   h ^= h >> 16;
-  h *= 0x7feb352dU;
-  h ^= h >> 15;
   return h;
 }
-__host__ __device__ __forceinline__ bool dropout_keep_lo(uint32_t bits, uint32_t thr16) { return (bits & 0xffffu) >= thr16; }
-__host__ __device__ __forceinline__ bool dropout_keep_hi(uint32_t bits, uint32_t thr16) { return bits >= (thr16 << 16); }
+__host__ __device__ __forceinline__ bool dropout_keep_lo(uint32_t bits, uint32_t thr16) { return bits * 0x7feb352dU >= (thr16 << 16); }
+__host__ __device__ __forceinline__ bool dropout_keep_hi(uint32_t bits, uint32_t thr16) { return bits * 0x846ca68bU >= (thr16 << 16); }
 // per-element form (elementwise kernels)
 __host__ __device__ __forceinline__ uint32_t dropout_keep(uint32_t seed, uint32_t salt, uint32_t idx, uint32_t thr16) {
   const uint32_t bits = dropout_bits(dropout_key(seed, salt), idx >> 1);
@@ -362,6 +362,17 @@ __device__ __forceinline__ void dropout_apply_run(float (&v)[N], uint32_t key, u
     const uint32_t bits = dropout_bits(key, (idx0 + j) >> 1);
     v[j] = dropout_keep_lo(bits, thr16) ? v[j] * scale : 0.f;
     v[j + 1] = dropout_keep_hi(bits, thr16) ? v[j + 1] * scale : 0.f;
+  }
+}
+
+// same mask, kept elements left unscaled (the caller has folded 1/(1-p) into what it feeds in)
+template <int N>
+__device__ __forceinline__ void dropout_zero_run(float (&v)[N], uint32_t key, uint32_t idx0, uint32_t thr16) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const uint32_t bits = dropout_bits(key, (idx0 + j) >> 1);
+    v[j] = dropout_keep_lo(bits, thr16) ? v[j] : 0.f;
+    v[j + 1] = dropout_keep_hi(bits, thr16) ? v[j + 1] : 0.f;
   }
 }
 
