@@ -396,7 +396,8 @@ struct WgradSmem {
 
 template <int BNW>
 __global__ void __launch_bounds__(kThreadsW, 1)
-gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int ldw,
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmDW, int M, int ldw,
                   float* __restrict__ dW, float* __restrict__ dbias, int rows_per_split, int y_fmt, int x_fmt) {
   using L = WgradSmem<BNW>;
   constexpr int kStages = L::kStages;
@@ -419,6 +420,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmY);
     prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDW);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], do_bias ? 5 : 1);
@@ -504,20 +506,29 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       const int quarter = warp & 3;
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
-      const int row = n0 + quarter * 32 + lane;
-      float* dst = dW + (size_t)row * ldw + k0;
+      // dW tile += accumulators. Each warp stages [32 rows x 32 cols] fp32 boxes (128B swizzle, two per warp, inside the
+      // first pipeline stage: every MMA has retired, the ring is idle) and adds them with cp.reduce.async.bulk.tensor.
+      // Per-thread red.global.add.v4 put 32 different rows (32 partial sectors) into every instruction.
+      uint8_t* sbox0 = smem + (warp - 2) * 8192;
 #pragma unroll 1
       for (int c = 0; c < BNW / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_addr(tmem_base, quarter * 32, c * 32), r);
         tmem_ld_wait();
+        uint8_t* sbox = sbox0 + (c & 1) * 4096;
+        if (c >= 2) tma_store_wait_read1();   // the reduce that last read this box is done with it (groups live in lane 0)
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + j),
-                       "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                       "f"(__uint_as_float(r[j + 3]))
-                       : "memory");
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(sbox + sw128_offset(lane, q)) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmDW, sbox, k0 + c * 32, n0 + quarter * 32);
+          tma_store_commit();
+        }
       }
+      tma_store_wait_read0();
     }
   }
   tc_fence_before();
@@ -547,7 +558,8 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
 }
 
 template <int BNW>
-int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K, float* dW, float* dbias, int y_fmt,
+int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const CUtensorMap& tmDW, int M, int N, int K, float* dW,
+                 float* dbias, int y_fmt,
                  int x_fmt, cudaStream_t st) {
   using L = WgradSmem<BNW>;
   static bool attr_set = false;
@@ -567,7 +579,8 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, i
   if (rows_per_split < BK) rows_per_split = BK;
   splits = (M + rows_per_split - 1) / rows_per_split;
   dim3 grid(N / 128, K / BNW, splits);
-  gemm_wgrad_kernel<BNW><<<grid, kThreadsW, L::kTotal, st>>>(tmY, tmX, M, K, dW, dbias, rows_per_split, y_fmt, x_fmt);
+  gemm_wgrad_kernel<BNW><<<grid, kThreadsW, L::kTotal, st>>>(tmY, tmX, tmDW, M, K, dW, dbias, rows_per_split, y_fmt,
+                                                             x_fmt);
   return tmp::check_launch("gemm_wgrad_kernel");
 }
 
@@ -647,6 +660,9 @@ extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X,
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
   if (rc) return rc;
-  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
-  return launch_wgrad<128>(tmY, tmX, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
+  CUtensorMap tmDW;   // dW [N, K] fp32, reduce-add boxes [32 rows x 32 cols]
+  rc = tmp::encode_tmap_2d_f32(&tmDW, dW, (uint64_t)K, (uint64_t)N, (uint64_t)K * 4, 32, 32);
+  if (rc) return rc;
+  if (K % 256 == 0) return launch_wgrad<256>(tmY, tmX, tmDW, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
+  return launch_wgrad<128>(tmY, tmX, tmDW, M, N, K, dW, dbias, y_fmt, x_fmt, (cudaStream_t)stream);
 }
