@@ -81,14 +81,16 @@ int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const flo
  * out[M,N] = residual + dropout( gate>0 ? act(alpha * A[M,K].B[N,K]^T + bias) : 0 ),  act = relu: 0 none, 1 ReLU, 2 GELU(erf)
  * A, B 16-bit K-major, both fp16 or both bf16 (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70,
  * module.py:74-80; dgrad passes the gradient as A and the transposed weight copy as B).
- * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out16 (in out_fmt) and/or out_f32 get the result. */
+ * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out16 (in out_fmt) and/or out_f32 get the result.
+ * A, B and out16 go through TMA: 16-byte aligned base addresses, leading dimensions multiples of 8 elements. */
 int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N, int K,
                           float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
                           const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
                           const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
 /* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X).
  * dbias (optional, may be NULL): dbias[N] fp32 += column sums of dY (the bias gradient), computed from the dY tiles
- * the kernel stages in shared memory anyway -- replaces a separate tmp_colsum pass over dY. */
+ * the kernel stages in shared memory anyway -- replaces a separate tmp_colsum pass over dY.
+ * dW is contiguous [N,K] and 16-byte aligned (its tiles are added with TMA reduce operations). */
 int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
                    float* dW, float* dbias, void* stream);
 /* out[N] fp32 += column sums of dY[M,N] fp16 (bias gradient) */
