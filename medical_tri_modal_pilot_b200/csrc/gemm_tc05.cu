@@ -3,10 +3,11 @@
 //               Conv1d(k=1) weights as stored by the reference, `[out,in]`). Used for QKV, FFN1, FFN2, the
 //               768->256 projections and (with pre-transposed weights) every dgrad.
 //   * gemm_wgrad : dW[N,K] += dY[M,N]^T . X[M,K]          both operands MN-major (reduction over tokens),
-//               split over M across CTAs, fp32 atomics into the parameter gradient.
-// Warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
-// (TMEM -> registers -> fused bias/ReLU/dropout/residual -> global). Accumulators are double-buffered in TMEM
-// so the epilogue of tile i overlaps the MMAs of tile i+1; the kernel is persistent over output tiles.
+//               split over M across CTAs, fp32 TMA reduce-adds into the parameter gradient.
+// Warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc; both issue through elect.sync, see
+// tc05::elect_one), warps 2-17 = epilogue (TMEM -> registers -> fused bias/activation/gate/dropout/residual -> swizzled
+// smem box -> TMA store). Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile
+// i+1; the kernel is persistent over output tiles.
 #include <stdlib.h>
 
 #include "common.cuh"
