@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import fixture_inputs, fixture_names, fp16_representable, load_fixture
+from golden_util import fixture_inputs, fixture_names, fp16_representable, gpu_fixture_names, load_fixture
 
 pytestmark = pytest.mark.gpu
 LOGIT_RTOL_BF16 = 2e-2
@@ -70,7 +70,7 @@ def _cosines(got, ref, floor=1e-6):
     return rows, float(ga @ gr / (np.linalg.norm(ga) * np.linalg.norm(gr)))
 
 
-@pytest.mark.parametrize("name", fixture_names())
+@pytest.mark.parametrize("name", gpu_fixture_names())
 def test_logits_and_grads(name):
     """Logits vs the reference's own output; gradients vs the pinned fp32 oracle at IDENTICAL (fp16-representable)
     weights. North-star bars: logits 2e-2 relative (16-bit mode), gradient cosine >= 0.999 -- asserted on the median

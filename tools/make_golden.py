@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference model imported from /root/reference (read-only,
 only available in the build container). Commit the outputs; the GPU box and the CPU test-suite replay them.
 
-    python tools/make_golden.py
+    python tools/make_golden.py [case ...]
 
 Import recipe = SURVEY.md Appendix A: stub `monai` (imported, unused), random-init Swin (no network), argv set before
 `control.config` is imported. Inputs and weights are NOT stored: they are regenerated bit-identically from
@@ -27,6 +27,8 @@ CASES = {
     "tri_nl2_multi_B32_L40": (2, 1, 32, 40, 11, 1, "mixed"),
     "tri_nl2_single_B24_L33": (2, 0, 24, 33, 12, 2, "mixed"),
     "tri_nl3_multi_B16_L150": (3, 1, 16, 150, 13, 3, "none"),
+    # the bench depth (6 layers, last layer vslt-only) with three 128-key attention tiles per sample
+    "tri_nl6_multi_B16_L260": (6, 1, 16, 260, 14, 4, "mixed"),
 }
 
 
@@ -59,6 +61,7 @@ def main():
     from oracle import synth, weights
     from oracle import tri_mbt_oracle as O
 
+    only = [a for a in sys.argv[1:] if a in CASES]     # python tools/make_golden.py [case names]; before argv is replaced
     os.chdir("/tmp")
     args, mod, enc_mod = import_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
@@ -73,6 +76,8 @@ def main():
             return self.feats.reshape(-1, 7, 7, 768)
 
     for name, (nl, multi, B, L, bseed, wseed, mmode) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         args.transformer_num_layers = nl
         args.multiimages = multi
