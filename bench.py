@@ -2,7 +2,8 @@
 """bench.py -- training throughput (samples/s) of `tri_mbt_vsltcls` vslt_img_txt on N x B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # B200-native arm (this repo)
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference algorithm on the host CPU cores
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's own code on the host CPU cores
+    python bench.py --impl reference-gpu-eager [--steps K] [--warmup W]  # the reference's own code on one B200, eager
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU (NCCL), weak scaling
 
 A "step" = one optimisation step (frozen Swin-T image encoder forward, fused UMSE/MBT encoder forward + backward,
@@ -33,7 +34,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu-eager"])
     p.add_argument("--batch", type=int, default=64, help="per-GPU batch (--batch-size)")
     p.add_argument("--tie-len", type=int, default=1000)
     p.add_argument("--layers", type=int, default=6)
@@ -41,11 +42,14 @@ def parse():
     p.add_argument("--dropout", type=float, default=0.1)
     p.add_argument("--realistic", action="store_true", help="ragged lengths + mixed missing codes instead of full")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-on-B200 (PyTorch eager) comparator")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU budget of the cpu_baseline sample")
     p.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
-    return p.parse_args()
+    a = p.parse_args()
+    a.cpu_seconds_set = any(x.startswith("--cpu-seconds") for x in sys.argv[1:])
+    return a
 
 
 def load_peaks():
@@ -120,64 +124,117 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference algorithm (CPU oracle port + stock Swin-T) on the host cores
+# reference arms: the reference's OWN modules (oracle/_ref, see oracle/build_ref.py) stepping through the reference's OWN
+# trainer (builder/trainer/trainer.py `missing_trainer`), on the host CPU cores (`--impl reference`, the cpu_baseline) or on
+# one B200 in PyTorch eager under its fp16 autocast (`--impl reference-gpu-eager`, the bar the kernels are measured against)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference(a, steps, warmup, budget_s=None):
-    """Times the CPU restatement of the reference training step (oracle/, kind "port": the Python reference cannot
-    travel to the GPU box) on a bounded sample of the same workload: per-step batch B_s <= --batch, same L / layers /
-    images. Returns (samples_per_s, ms_per_step, info)."""
+class _Sched:
+    def step(self, it):
+        pass
+
+    def get_lr(self):
+        return [1e-4]
+
+
+class _Logger:
+    def log_lr(self, lr, it):
+        pass
+
+
+def config_dict(a, world, graph=True):
+    return {"workload": workload_name(a), "per_gpu_batch": a.batch, "global_batch": a.batch * world,
+            "parallelism": f"dp{world}", "lengths": "ragged+mixed-missing" if a.realistic else "full",
+            "optimizer": a.optimizer, "cuda_graph": bool(graph),
+            "l2": "per-step working set (activations ~5 GB at L=1000) >> 126 MB L2; no explicit flush"}
+
+
+def reference_runner(a, device, Bs):
+    """(step_fn, info): one optimisation step of the UNMODIFIED reference (model + trainer from oracle/_ref) on a seeded
+    batch of Bs samples of the workload (same L / layers / images / dropout). The reference bakes --batch-size into the
+    model (tri_mbt_vsltcls.py:161-165, mbt_encoder.py:675), so the model is built for exactly Bs."""
     import torch
     from medical_tri_modal_pilot_b200 import synth
-    from medical_tri_modal_pilot_b200.model import build_swin_t_m
-    from oracle import tri_mbt_oracle as O
-    from oracle import weights
+    from oracle import ref_loader
+    on_gpu = torch.device(device).type == "cuda"
+    if "control.config" in sys.modules:
+        import control.config as C
+        args = C.args
+        mod = sys.modules["builder.models.8_missing_models.tri_mbt_vsltcls"]
+        tr = sys.modules["builder.trainer"]
+    else:
+        args, mod, tr = ref_loader.load(a.layers, Bs, a.multiimages, a.dropout, device)
+        if not on_gpu:
+            ref_loader.cpu_trainer_shims()
+        torch.autograd.set_detect_anomaly(False)     # the reference leaves it ON (2_train.py:31); off here, stated in DESIGN.md
+    args.batch_size = Bs
+    args.device = torch.device(device)
+    torch.manual_seed(0)
+    model = mod.TRI_MBT_VSLTCLS(args).to(device)
+    model.train()                                    # 2_train.py:128 (this also leaves Swin's StochasticDepth on, as upstream)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-6)       # 2_train.py:110
+    criterion = torch.nn.BCEWithLogitsLoss()                                            # 2_train.py:76
+    n_img = 3 if a.multiimages else 1
+    hb = synth.make_batch(Bs, a.tie_len, n_img=n_img, seed=7, full_length=not a.realistic,
+                          missing_mode="mixed" if a.realistic else "none", with_pixels=True, feats=False)
+    miss = hb["missing"]
+    missing3 = torch.stack([torch.zeros_like(miss), (miss >= 2).long(), (miss % 2).long()], 1).float()
+    static = torch.stack([hb["gen"], hb["age"]], 1)
+    dev = torch.device(device)
+    # 2_train.py:143-169: everything but the times / missing rows is moved by the loop; x is cast to HalfTensor there
+    x = hb["x"].type(torch.HalfTensor).to(dev) if on_gpu else hb["x"]
+    mv = lambda t: t.to(dev)
+    sched, logger = _Sched(), _Logger()
 
+    def step(it=0):
+        _, loss = tr.get_trainer(args, it, x, mv(static), mv(hb["input_lengths"]).clone(), mv(hb["y"]), None, model, logger,
+                                 dev, sched, optimizer, criterion, x_txt=mv(hb["txts"]), x_img=mv(hb["img"]),
+                                 txt_lengths=mv(hb["txt_lengths"]).clone(), imgtxt_time=(hb["img_time"], hb["txt_time"]),
+                                 scaler=None, missing=missing3, flow_type="train", reports_tokens=None,
+                                 reports_lengths=None, criterion_aux=(None, None))
+        return loss
+
+    return step
+
+
+def host_threads():
     threads = os.cpu_count() or 1
     try:
         threads = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    return threads
+
+
+def cpu_reference(a, steps, warmup, budget_s=None):
+    """Times the reference's own training step (oracle/_ref: unmodified model + trainer, fp32 -- torch.cuda.amp.autocast
+    is inert on CPU tensors --, dropout on, anomaly mode off) on the host cores, on a bounded sample of the workload:
+    per-step batch B_s <= --batch, same L / layers / images. Returns (samples_per_s, ms_per_step, info)."""
+    import torch
+    threads = host_threads()
     torch.set_num_threads(threads)
     n_img = 3 if a.multiimages else 1
-    cfg = O.OracleConfig(n_layers=a.layers, multiimages=a.multiimages)
-    sd = weights.make_state_dict(a.layers, seed=0)
-    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point
-              and "running" not in k and "positional_encoding" not in k}
-    full = dict(sd); full.update(leaves)
-    opt = torch.optim.AdamW(list(leaves.values()), lr=1e-4, weight_decay=1e-6)
-    swin = build_swin_t_m().eval()
-
-    def make(Bs, seed):
-        return synth.make_batch(Bs, a.tie_len, n_img=n_img, seed=seed, full_length=not a.realistic,
-                                missing_mode="mixed" if a.realistic else "none", with_pixels=True, feats=False)
-
-    def one_step(batch):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        with torch.no_grad():                                               # tri_mbt_vsltcls.py:205-209
-            f = swin(batch["img"].reshape(-1, 1, 224, 224))
-        batch = dict(batch); batch["img_feats"] = f.reshape(f.shape[0], 49, 768)
-        loss = O.loss_fn(O.forward(full, batch, cfg), batch["y"])
-        loss.backward()
-        opt.step()
-        return time.perf_counter() - t0
-
     # size the sample: probe with B_s = 2, then pick B_s so that (steps + warmup) steps fit the budget
-    probe = one_step(make(2, 100))
-    probe = min(probe, one_step(make(2, 101)))
+    probe_step = reference_runner(a, "cpu", 2)
+    t0 = time.perf_counter(); probe_step(0); t1 = time.perf_counter(); probe_step(1); t2 = time.perf_counter()
+    probe = min(t1 - t0, t2 - t1)
     total = steps + warmup
     if budget_s is None:
         budget_s = 150.0
     per_sample = probe / 2.0
     Bs = int(max(2, min(a.batch, budget_s / max(total, 1) / max(per_sample, 1e-6))))
-    batch = make(Bs, 7)
-    for _ in range(warmup):
-        one_step(batch)
-    ts = [one_step(batch) for _ in range(steps)]
+    step = reference_runner(a, "cpu", Bs)
+    for i in range(warmup):
+        step(i)
+    ts = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step(i)
+        ts.append(time.perf_counter() - t0)
     dt = sum(ts) / len(ts)
-    info = {"cores": threads, "kind": "port",
+    info = {"cores": threads, "kind": "reference",
             "sample": f"{steps} steps of a B={Bs} slice of the workload batch (same L={a.tie_len}, {a.layers} layers, "
-                      f"{n_img} images/sample, fp32 torch-CPU oracle + stock Swin-T + AdamW), {warmup} warm-up"}
+                      f"{n_img} images/sample, dropout {a.dropout}): the reference's own TRI_MBT_VSLTCLS + Swin-T + "
+                      f"missing_trainer + AdamW from oracle/_ref, fp32 on CPU, anomaly mode off, {warmup} warm-up"}
     return Bs / dt, dt * 1e3, info
 
 
@@ -185,15 +242,69 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, ms, info = cpu_reference(a, a.steps, a.warmup)
+    v, ms, info = cpu_reference(a, a.steps, a.warmup, budget_s=a.cpu_seconds if a.cpu_seconds_set else None)
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": v, "unit": "samples/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "device": "host CPU"},
+            "config": config_dict(a, max(1, a.gpus), graph=not a.no_graph and a.optimizer == "fused"),
+            "ran_on": "host CPU (rank 0 only; the other ranks idle)",
             "cpu_baseline": {"value": v, "unit": "samples/s", **info},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu_eager(a):
+    """The unmodified reference modules on ONE B200 in PyTorch eager, stepped by the reference's own trainer under its
+    fp16 autocast (trainer.py:126), anomaly mode off: the honest bar for the hand-written kernels."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    step = reference_runner(a, dev, a.batch)
+    for i in range(max(1, a.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    v = a.batch / (ms * 1e-3)
+    line = {"impl": "reference-gpu-eager", "metric": "train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": 1,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16 autocast (reference trainer.py:126), fp32 master weights", "data": "synthetic",
+            "config": config_dict(a, 1, graph=False),
+            "what": "unmodified reference TRI_MBT_VSLTCLS + Swin-T + missing_trainer + AdamW (oracle/_ref) on one B200, "
+                    "PyTorch eager (cuBLAS / cuDNN / ATen kernels), device-resident batch, loss.item() per step as upstream",
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    print(json.dumps(line), flush=True)
+
+
+def sub_bench(a, impl, steps, warmup, extra=(), timeout=900):
+    """Run another arm of this script in a child process (the reference's `builder` package cannot share a process with the
+    repo's drop-in `builder` shim) and return its JSON line, or {"unavailable": why}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl, "--steps", str(steps), "--warmup", str(warmup),
+           "--batch", str(a.batch), "--tie-len", str(a.tie_len), "--layers", str(a.layers), "--multiimages",
+           str(a.multiimages), "--dropout", str(a.dropout), *extra]
+    if a.realistic:
+        cmd.append("--realistic")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"{impl}: timeout after {timeout}s"}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                pass
+    return {"unavailable": f"{impl}: rc={r.returncode} {r.stderr.strip()[-300:]}"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -319,14 +430,17 @@ def run_b200(a):
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 (tcgen05 kind::f16 operands, fp32 accumulate/params/grads)",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "per_gpu_batch": a.batch, "global_batch": a.batch * world,
-                       "parallelism": f"dp{world}", "lengths": "ragged+mixed-missing" if a.realistic else "full",
-                       "optimizer": a.optimizer, "cuda_graph": bool(args.cuda_graph),
-                       "l2": "per-step working set (activations ~5 GB at L=1000) >> 126 MB L2; no explicit flush"},
+            "config": config_dict(a, world, graph=args.cuda_graph),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
+    if world == 1 and not a.no_gpu_eager:
+        # the reference's own modules on this same B200 in PyTorch eager (child process; our graphs / workspaces stay alive,
+        # so its memory comes on top: ~15 GB of 180)
+        ge = sub_bench(a, "reference-gpu-eager", steps=3, warmup=2)
+        line["gpu_eager_baseline"] = ({k: ge.get(k) for k in ("value", "unit", "ms_per_step", "dtype", "what", "peak_mem_gb")}
+                                      if "value" in ge else ge)
     if world == 1 and not a.no_cpu_baseline:
-        v, ms, info = cpu_reference(a, steps=3, warmup=1, budget_s=a.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", **info}
+        cb = sub_bench(a, "reference", steps=3, warmup=1, extra=("--cpu-seconds", str(a.cpu_seconds)))
+        line["cpu_baseline"] = cb.get("cpu_baseline", cb)
     print(json.dumps(line), flush=True)
     _finish(world, model)
 
@@ -412,5 +526,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-gpu-eager":
+        run_reference_gpu_eager(a)
     else:
         run_b200(a)

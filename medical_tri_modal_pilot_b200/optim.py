@@ -60,3 +60,36 @@ class FlatAdamW(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=True)
+
+    # -- checkpointing: reference builder/utils/logger.py:167 saves optimizer.state_dict() into every checkpoint --------
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict() plus the flat moments, the step count and the head optimizer's state (the
+        base class only knows `self.state`, which this optimizer does not use)."""
+        sd = super().state_dict()
+        sd["flat"] = {"m": self.m.detach().clone(), "v": self.v.detach().clone(), "t": int(self.t),
+                      "n_live": int(self.n_live), "rest": self._rest_opt.state_dict()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("flat", None)
+        super().load_state_dict(state_dict)
+        if flat is None:
+            return
+        if int(flat["n_live"]) != self.n_live:
+            raise ValueError(f"FlatAdamW: checkpoint holds {flat['n_live']} live parameters, model has {self.n_live}")
+        with torch.no_grad():
+            self.m.copy_(flat["m"])
+            self.v.copy_(flat["v"])
+            self.t = int(flat["t"])
+            self.t_dev.fill_(self.t)
+        self._rest_opt.load_state_dict(flat["rest"])
+        lr = float(self.param_groups[0]["lr"])
+        self.lr_dev.fill_(lr)
+        for rg in self._rest_opt.param_groups:          # capturable AdamW keeps lr as a device tensor
+            if torch.is_tensor(rg["lr"]):
+                rg["lr"] = rg["lr"].to(self.lr_dev.device)
+                rg["lr"].fill_(lr)
+            else:
+                rg["lr"] = torch.tensor(lr, device=self.lr_dev.device)
+        self._lr_host = lr

@@ -52,7 +52,8 @@ class FusedPath:
         self.model = model
         self.device = None
         self.step = 0
-        self._ws_key = None
+        self._ws_cache = {}       # (B, L, n_img) -> workspace dict (small LRU; captured graphs pin theirs, see pin())
+        self._ctx_token = 0
         self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
         self.skip_missing = True
         self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
@@ -173,8 +174,17 @@ class FusedPath:
     # workspace
     # ------------------------------------------------------------------------------------------------------------
     def _ensure_workspace(self, B, L, n_img):
+        """Activations / gradient scratch for one input shape. A captured CUDA graph (trainer.GraphedStep) bakes the raw
+        device pointers of these buffers, so a workspace is never freed behind a graph's back: workspaces live in a
+        small LRU keyed by shape (eager calls with ever-changing shapes cannot accumulate more than 3), and every graph
+        additionally pins the workspace object it captured (`pin()`), which keeps the memory alive for as long as the
+        graph exists even after the LRU dropped it."""
         key = (B, L, n_img)
-        if self._ws_key == key:
+        hit = self._ws_cache.pop(key, None)
+        if hit is not None:
+            self._ws_cache[key] = hit
+            self.ws, self.proj, self.g_proj, self.T = hit["ws"], hit["proj"], hit["g_proj"], hit["T"]
+            self._ws_cur = hit
             return
         dev = self.device
         NL = self.model.num_layers
@@ -205,7 +215,13 @@ class FusedPath:
                      torch.empty(B * 128, D, dtype=ACT, device=dev)]
         self.g_proj = [None, torch.empty(B * 49 * n_img, D, dtype=GRD, device=dev),
                        torch.empty(B * 128, D, dtype=GRD, device=dev)]
-        self._ws_key = key
+        self._ws_cur = self._ws_cache[key] = dict(ws=ws, proj=self.proj, g_proj=self.g_proj, T=T)
+        while len(self._ws_cache) > 3:
+            self._ws_cache.pop(next(iter(self._ws_cache)))
+
+    def pin(self):
+        """Everything a captured graph of the current step references by raw pointer (workspace, cast inputs, lengths)."""
+        return (self._ws_cur, getattr(self, "ctx", None))
 
     # ------------------------------------------------------------------------------------------------------------
     def __call__(self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing):
@@ -247,7 +263,11 @@ class FusedPath:
         # is bumped by a device op, so a captured CUDA graph of the step draws fresh masks on every replay
         self.step += 1
         if self.seed_base is None:
-            self.seed_base = (int(torch.initial_seed()) * 1000003) & 0x7FFFFFFF
+            # independent dropout streams per data-parallel rank (the masks are a pure function of the seed)
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            self.seed_base = ((int(torch.initial_seed()) * 1000003) ^ (rank * 0x9E3779B1)) & 0x7FFFFFFF
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=x.device)
         if training:
             self.step_dev.add_(1)
@@ -289,6 +309,9 @@ class FusedPath:
                 break
             ops.bottleneck_mix_fwd(self.ws[0]["X"][l + 1], self.ws[1]["X"][l + 1], self.ws[2]["X"][l + 1], ctx["missing"])
             self._fork()
+        self._ctx_token += 1
+        ctx["token"] = self._ctx_token
+        ctx["ws"] = self._ws_cur
         self.ctx = ctx
         return self.ws[0]["X"][NL][:, 4, :].float()
 
@@ -341,9 +364,22 @@ class FusedPath:
                  seed=seed, salt=(l * 3 + s) * 4 + 2, seed_dev=sd)
 
     # ------------------------------------------------------------------------------------------------------------
-    def backward(self, d_cls):
+    def backward(self, d_cls, token=None):
         m = self.model
         ctx = self.ctx
+        if token is not None and token != ctx["token"]:
+            raise RuntimeError("FusedPath.backward: another forward ran between this backward's forward and now (e.g. an "
+                               "eval probe inside a train step); the saved activations live in per-shape workspaces and "
+                               "were overwritten. Run backward before the next forward.")
+        if ctx["ws"] is not self._ws_cur:
+            self._ensure_workspace(ctx["B"], ctx["L"], ctx["n_img"])
+        # Gradient accumulation (a second backward without zero_grad in between): the kernels WRITE the flat gradient
+        # buffer (and unscale it range by range), so the gradients still attached to the parameters are set aside and
+        # added back at the end. After zero_grad(set_to_none=True) -- the torch default -- this costs nothing.
+        n0, p0 = self.layout[0]
+        acc_prev = None
+        if p0.grad is not None and p0.grad.data_ptr() == self.gviews[n0].data_ptr():
+            acc_prev = self.flat_g[: self.live_end()].clone()
         NL = m.num_layers
         B, p, seed = ctx["B"], ctx["p"], ctx["seed"]
         self.flat_g.zero_()
@@ -390,6 +426,8 @@ class FusedPath:
                                    dbias=self.G("txt_embedding.bias", D))
         self._join()
         self._range_done(*self.grad_range_of_layer(-1))
+        if acc_prev is not None:
+            self.flat_g[: self.live_end()].add_(acc_prev)
         self._publish_grads()
 
     def _range_done(self, a, b):
@@ -476,10 +514,12 @@ class _FusedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trigger, fp, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing):
         ctx.fp = fp
-        return fp.forward(x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing,
-                          training=fp.model.training)
+        out = fp.forward(x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing,
+                         training=fp.model.training)
+        ctx.token = fp.ctx["token"]
+        return out
 
     @staticmethod
     def backward(ctx, d_cls):
-        ctx.fp.backward(d_cls.contiguous())
+        ctx.fp.backward(d_cls.contiguous(), token=ctx.token)
         return (torch.zeros(1, device=d_cls.device),) + (None,) * 9

@@ -74,10 +74,16 @@ class SwinFeed:
                                         w=_pad2(mg.reduction.weight.detach(), Cn, 4 * C)))
         self.norm = dict(g=swin.norm.weight.detach().float().contiguous(), b=swin.norm.bias.detach().float().contiguous())
         self.device = dev
-        self._ws_n = None
+        self._ws_cache = {}      # n_img -> (ws, out); see _workspace
 
     def _workspace(self, n_img):
-        if self._ws_n == n_img:
+        """Workspaces are cached per batch size and NEVER freed while anything can still reference them: a captured CUDA
+        graph (trainer.GraphedStep) bakes their raw device pointers and additionally pins the objects (`pin()`); the
+        small LRU only bounds what eager calls with ever-changing shapes can accumulate."""
+        hit = self._ws_cache.pop(n_img, None)
+        if hit is not None:
+            self._ws_cache[n_img] = hit          # most recently used last
+            self.ws, self.out = hit
             return self.ws
         dev = self.device
         ws = []
@@ -89,8 +95,15 @@ class SwinFeed:
                            y=h16(M, Cp), hn=h16(M, Cp), a=h16(M, 4 * C),
                            mg=h16(M // 4, 4 * C) if H > 7 else None))
         self.out = torch.empty(n_img * 49, 768, dtype=torch.float16, device=dev)
-        self.ws, self._ws_n = ws, n_img
+        self.ws = ws
+        self._ws_cache[n_img] = (ws, self.out)
+        while len(self._ws_cache) > 3:
+            self._ws_cache.pop(next(iter(self._ws_cache)))
         return ws
+
+    def pin(self):
+        """The workspace objects of the most recent call (held by a captured graph so they outlive the LRU)."""
+        return (self.ws, self.out)
 
     @torch.no_grad()
     def __call__(self, img):

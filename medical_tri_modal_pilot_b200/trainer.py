@@ -211,6 +211,10 @@ class GraphedStep:
                 self.launches_per_replay = _lib.launch_count - n0
                 _lib.launch_count = n0
                 self.graph = g
+                # the graph holds raw pointers into the fused-path / image-encoder workspaces of THIS shape: keep those
+                # objects alive for as long as the graph exists (the per-shape caches are LRUs and may drop them)
+                swin = self.model.__dict__.get("_swin_native")
+                self._pinned = (self.model._fused.pin(), swin[1].pin() if swin else None)
         if self.graph is not None:
             self.graph.replay()
             _lib.launch_count += self.launches_per_replay

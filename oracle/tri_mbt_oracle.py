@@ -216,8 +216,14 @@ def forward(sd, batch, cfg: OracleConfig, return_aux=False):
         bottlenecks = allb[missing, idx_order]                                          # :776
     aux["vslt_out"] = enc_outputs[0]
 
-    # ---- classifier (tri_mbt_vsltcls.py:248-255) ------------------------------------------------------------
-    c = F.layer_norm(enc_outputs[0][:, 0, :], (256,), sd["layer_norms_after_concat.weight"], sd["layer_norms_after_concat.bias"], 1e-5)
+    logits = classifier_head(sd, enc_outputs[0][:, 0, :], demo_embedding, cfg)
+    return (logits, aux) if return_aux else logits
+
+
+def classifier_head(sd, cls, demo_embedding, cfg: OracleConfig):
+    """tri_mbt_vsltcls.py:248-255: nn.LayerNorm on the vslt CLS output, concat the demographic embedding, fc_list =
+    Linear(512,256) -> BatchNorm1d (batch statistics in train mode, running statistics in eval mode) -> ReLU -> Linear."""
+    c = F.layer_norm(cls, (256,), sd["layer_norms_after_concat.weight"], sd["layer_norms_after_concat.bias"], 1e-5)
     c = torch.cat([c, demo_embedding], dim=1)
     hdn = F.linear(c, sd["fc_list.0.weight"], sd["fc_list.0.bias"])
     if cfg.training:
@@ -225,8 +231,7 @@ def forward(sd, batch, cfg: OracleConfig, return_aux=False):
     else:
         hdn = F.batch_norm(hdn, sd["fc_list.1.running_mean"], sd["fc_list.1.running_var"], sd["fc_list.1.weight"],
                            sd["fc_list.1.bias"], False, 0.1, 1e-5)
-    logits = F.linear(torch.relu(hdn), sd["fc_list.3.weight"], sd["fc_list.3.bias"])
-    return (logits, aux) if return_aux else logits
+    return F.linear(torch.relu(hdn), sd["fc_list.3.weight"], sd["fc_list.3.bias"])
 
 
 def loss_fn(logits, y):

@@ -11,16 +11,23 @@ def fixture_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
-# Fixtures that pin the ORACLE only (tests/test_oracle_golden.py). The 6-layer fixture was generated at the very end of a
-# session: on B200 its logits and loss pass the bars of test_model_parity_gpu.py::test_logits_and_grads, the end-to-end
-# whole-gradient cosine is 0.987 (the reference algorithm under bf16 autocast: 0.979) against an absolute 0.99 bar that
-# was calibrated on the 2- and 3-layer fixtures, and the remaining legs of that test could not be measured any more --
-# so it is not part of the GPU parametrisation until its bars have been.
-ORACLE_ONLY = {"tri_nl6_multi_B16_L260"}
-
-
 def gpu_fixture_names():
-    return [n for n in fixture_names() if n not in ORACLE_ONLY]
+    """Every fixture is part of the GPU parametrisation (the 6-layer bench depth and the B=64 / TIE-len 1000 bench shape
+    included)."""
+    return fixture_names()
+
+
+def emb_rows(B, L):
+    """(b, l) pairs at which the large fixtures store the embedding rows (same generator as tools/make_golden.py)."""
+    g = np.random.Generator(np.random.PCG64(B * 100003 + L))
+    return g.integers(0, B, 1024), g.integers(0, L, 1024)
+
+
+def fixture_embedding_view(fx, e):
+    """`e` [B,L,256] computed here -> the part the fixture holds (everything, or the seeded rows of a large fixture)."""
+    if "emb_subsampled" in fx and int(fx["emb_subsampled"]):
+        return e[emb_rows(e.shape[0], e.shape[1])]
+    return e
 
 
 def load_fixture(name):

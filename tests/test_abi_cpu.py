@@ -54,3 +54,19 @@ def test_no_cpu_fallback():
     from medical_tri_modal_pilot_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.umse_embed(torch.zeros(4, 3), [torch.zeros(256)] * 4, [torch.zeros(256)] * 4, torch.zeros(20, 256))
+
+
+def test_reference_copy_recipe():
+    """oracle/_ref (the reference's own hot-path files, copied unmodified by oracle/build_ref.py; git-ignored) is present
+    after __graft_entry__.build() and its files match the recorded sha256."""
+    import pytest
+    from oracle import build_ref
+    if not build_ref.available():
+        build_ref.build()
+    if not build_ref.available():
+        pytest.skip("reference not mounted and no oracle/_ref copy")
+    assert build_ref.verify()
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["git", "-C", root, "check-ignore", "oracle/_ref/MANIFEST.json"], capture_output=True, text=True)
+    assert out.returncode == 0, "oracle/_ref must stay out of the history"

@@ -13,7 +13,7 @@ def _trainer_inputs(batch):
     return static, miss3
 
 
-def _run_steps(cuda_graph, n_steps, dropout=0.0, lrs=None):
+def _run_steps(cuda_graph, n_steps, dropout=0.0, lrs=None, probe_at=None):
     from golden_util import fixture_inputs, fixture_names, load_fixture
     from builder.trainer import get_trainer
     from medical_tri_modal_pilot_b200.optim import FlatAdamW
@@ -38,8 +38,118 @@ def _run_steps(cuda_graph, n_steps, dropout=0.0, lrs=None):
                               txt_lengths=batch["txt_lengths"], imgtxt_time=(batch["img_time"], batch["txt_time"]),
                               missing=miss3, flow_type="train")
         losses.append(loss)
+        if probe_at is not None and it == probe_at:
+            # an evaluation batch of ANOTHER shape between two train steps (validation inside the epoch loop): the fused
+            # path switches workspaces; the captured train graph must keep replaying into its own
+            nb, nl = B // 2, batch["x"].shape[1] - 7
+            model.eval()
+            with torch.no_grad():
+                get_trainer(model.args, it, batch["x"][:nb, :nl].contiguous(), static[:nb], batch["input_lengths"][:nb].clamp(max=nl),
+                            batch["y"][:nb], None, model, _Log(), torch.device("cuda"), None, opt, crit,
+                            x_txt=batch["txts"][:nb], x_img=batch["img_feats"][:nb * (3 if cfg.multiimages else 1)],
+                            txt_lengths=batch["txt_lengths"][:nb], imgtxt_time=(batch["img_time"][:nb], batch["txt_time"][:nb]),
+                            missing=miss3[:nb], flow_type="test")
+            model.train()
     params = {k: p.detach().clone() for k, p in model.named_parameters() if not k.startswith("img_encoder.")}
     return losses, params, model
+
+
+class _Log:
+    class evaluator:
+        @staticmethod
+        def add_batch(y, p):
+            pass
+
+
+def test_graph_survives_a_workspace_switch():
+    """a captured graph bakes raw workspace pointers; an eval batch of a different shape used to free
+    and reallocate those workspaces. Same training run with and without an eval probe of another shape after step 3
+    (after the capture): identical losses within the eager run-to-run jitter."""
+    l_a, p_a, _ = _run_steps(True, 6)
+    l_b, p_b, model = _run_steps(True, 6, probe_at=3)
+    assert len(model._fused._ws_cache) == 2
+    for a, b in zip(l_a, l_b):
+        assert abs(a - b) < max(1e-3, 0.03 * a), (l_a, l_b)
+    # and the same probe in eager mode
+    l_c, _, _ = _run_steps(False, 6, probe_at=3)
+    for a, c in zip(l_a, l_c):
+        assert abs(a - c) < max(1e-3, 0.03 * a), (l_a, l_c)
+
+
+def test_backward_after_an_interleaved_forward_raises():
+    from golden_util import fixture_inputs, fixture_names, load_fixture
+    from test_model_parity_gpu import build_model, run_model
+    fx = load_fixture(fixture_names()[0])
+    sd, batch, cfg = fixture_inputs(fx)
+    model = build_model(cfg, sd, batch["x"].shape[0]).train()
+    out, b = run_model(model, batch)
+    with torch.no_grad():
+        run_model(model, batch)                      # e.g. an eval probe before backward
+    with pytest.raises(RuntimeError, match="another forward"):
+        out.sum().backward()
+
+
+def test_gradient_accumulation_adds():
+    """Two backward calls without zero_grad accumulate (used to overwrite silently)."""
+    from golden_util import fixture_inputs, fixture_names, load_fixture
+    from test_model_parity_gpu import build_model, run_model
+    fx = load_fixture(fixture_names()[0])
+    sd, batch, cfg = fixture_inputs(fx)
+    model = build_model(cfg, sd, batch["x"].shape[0]).train()
+    out, b = run_model(model, batch)
+    out.sum().backward()
+    g1 = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    out, b = run_model(model, batch)
+    out.sum().backward()
+    for k, p in model.named_parameters():
+        if p.grad is None or k.startswith("img_encoder."):
+            continue
+        ref = 2 * g1[k]
+        assert (p.grad - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-6, k
+
+
+def test_flat_adamw_state_dict_round_trip():
+    """reference logger.py:167 writes optimizer.state_dict() into every checkpoint; resuming must restore the
+    flat moments and the step count."""
+    import io
+    from medical_tri_modal_pilot_b200.optim import FlatAdamW
+    l1, p1, model = _run_steps(False, 3)
+    # continue two more steps from a checkpoint in a fresh model/optimizer vs in place
+    from golden_util import fixture_inputs, fixture_names, load_fixture
+    from builder.trainer import get_trainer
+    from test_model_parity_gpu import build_model
+    fx = load_fixture(fixture_names()[0])
+    sd, batch, cfg = fixture_inputs(fx)
+    B = batch["x"].shape[0]
+    static, miss3 = _trainer_inputs(batch)
+    crit = torch.nn.BCEWithLogitsLoss()
+
+    def steps(model, opt, n):
+        out = []
+        for it in range(n):
+            _, loss = get_trainer(model.args, it, batch["x"], static, batch["input_lengths"], batch["y"], None, model, None,
+                                  torch.device("cuda"), None, opt, crit, x_txt=batch["txts"], x_img=batch["img_feats"],
+                                  txt_lengths=batch["txt_lengths"], imgtxt_time=(batch["img_time"], batch["txt_time"]),
+                                  missing=miss3, flow_type="train")
+            out.append(loss)
+        return out
+
+    torch.manual_seed(0)
+    m_a = build_model(cfg, sd, B).train(); m_a.args.cuda_graph = False
+    o_a = FlatAdamW(m_a, lr=1e-3, weight_decay=1e-2, eps=1e-3)
+    steps(m_a, o_a, 3)
+    buf = io.BytesIO()
+    torch.save({"model": m_a.state_dict(), "optimizer": o_a.state_dict()}, buf)     # logger.py:166-177 layout
+    buf.seek(0)
+    ck = torch.load(buf, map_location="cuda", weights_only=False)
+    m_b = build_model(cfg, sd, B).train(); m_b.args.cuda_graph = False
+    m_b.load_state_dict(ck["model"])
+    o_b = FlatAdamW(m_b, lr=1e-3, weight_decay=1e-2, eps=1e-3)
+    o_b.load_state_dict(ck["optimizer"])
+    assert o_b.t == 3 and int(o_b.t_dev.item()) == 3 and o_b.m.abs().sum().item() > 0
+    la, lb = steps(m_a, o_a, 2), steps(m_b, o_b, 2)
+    for a, b in zip(la, lb):
+        assert abs(a - b) < max(1e-3, 0.03 * a), (la, lb)
 
 
 def test_graph_replay_matches_eager_steps():
