@@ -408,6 +408,11 @@ def run_b200(a):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / a.steps
     value = world * a.batch / (ms_step * 1e-3)
+    # the work was real: finite loss and finite fused-path parameters after the timed steps (outside the timed region)
+    last_loss = float(step_dev(a.steps).item())
+    params_finite = bool(torch.isfinite(model._fused.flat_w).all().item())
+    if not (last_loss == last_loss and abs(last_loss) < 1e4 and params_finite):
+        raise RuntimeError(f"bench: non-finite training state after the timed steps (loss {last_loss}, finite params {params_finite})")
 
     # ---- e2e: the user call with pinned host tensors ---------------------------------------------------------------
     e2e = None
@@ -431,7 +436,8 @@ def run_b200(a):
             "vs_baseline": None, "dtype": "fp16 (tcgen05 kind::f16 operands, fp32 accumulate/params/grads)",
             "data": "synthetic",
             "config": config_dict(a, world, graph=args.cuda_graph),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "loss_after_timed_steps": last_loss}
     if world == 1 and not a.no_gpu_eager:
         # the reference's own modules on this same B200 in PyTorch eager (child process; our graphs / workspaces stay alive,
         # so its memory comes on top: ~15 GB of 180)

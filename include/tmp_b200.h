@@ -93,7 +93,7 @@ int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int 
  * dW is contiguous [N,K] and 16-byte aligned (its tiles are added with TMA reduce operations). */
 int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,
                    float* dW, float* dbias, void* stream);
-/* out[N] fp32 += column sums of dY[M,N] fp16 (bias gradient) */
+/* out[N] fp32 += column sums of dY[M,N] fp16 (bias gradient; the 16-bit path uses the fused form in tmp_gemm_wgrad) */
 int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream);
 
 /* ---- a10: modality-aware attention (attention.py:24-49, 65-84) ----------------------------------------------
@@ -151,6 +151,47 @@ int tmp_swin_unwindow_add_ln(const void* y, void* x, const float* g, const float
 /* out[(n,i,j), 4C] = LayerNorm(x0|x1|x2|x3) of the 2x2 neighbourhood (PatchMerging), out stride 4C */
 int tmp_swin_merge_ln(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp, void* out,
                       void* stream);
+
+/* ---- fp32 ("precise") mode: north-star's FP32 parity mode of the same path (trainer.py:126 is the only place the
+ * reference drops precision; called outside autocast the reference runs in fp32). Every activation / gradient tensor is
+ * fp32; the *_f32 operators are the kernels above compiled for fp32 storage (same arguments, `float*` tensors).
+ * GEMMs: tmp_split_bf16x3 turns an fp32 operand into three bf16 terms laid out as six blocks along the reduction
+ * dimension (A side: hi|hi|mid|hi|lo|mid, B side: hi|mid|hi|lo|hi|mid), then tmp_gemm_bias_act_fwd / tmp_gemm_wgrad run on
+ * the bf16 blocks (a_fmt = b_fmt = 1) with fp32 accumulation, fp32 output (out_f32) and fp32 gate / residual (format 2):
+ * A . B^T to ~2^-17 relative on the tensor cores. Attention runs on the CUDA cores in fp32 (no atomics: deterministic). */
+int tmp_layernorm_fwd_f32(const float* x, const float* add, const float* gamma, const float* beta, long long rows,
+                          float* sum_out, float* y, void* stream);
+int tmp_layernorm_bwd_f32(const float* dy, const float* x, const float* dres, const float* gamma, long long rows, float* dx,
+                          float* dx_drop, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                          float* dgamma, float* dbeta, void* stream);
+int tmp_bottleneck_mix_fwd_f32(float* Yv, float* Yi, float* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
+                               void* stream);
+int tmp_bottleneck_mix_bwd_f32(float* dYv, float* dYi, float* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
+                               const long long* missing, int B, void* stream);
+int tmp_dropout_apply_f32(const float* in, float* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                          const uint32_t* seed_dev, void* stream);
+int tmp_colsum_f32(const float* dY, int ld, long long M, int N, float* out, void* stream);
+int tmp_stream_prologue_fwd_f32(int kind, int B, int n, const float* x, const float* const* val4, const float* proj,
+                                const float* times, int n_slots, int feat_id, const float* const* tim4,
+                                const float* Wfeat, const float* cls, const float* bottlenecks, const float* ln_g,
+                                const float* ln_b, const float* pe, float drop_p, uint32_t seed, uint32_t salt,
+                                const uint32_t* seed_dev, float* X0, void* stream);
+int tmp_stream_prologue_bwd_f32(int kind, int B, int n, const float* x, const float* const* val4, const float* proj,
+                                const float* times, int n_slots, int feat_id, const float* const* tim4,
+                                const float* Wfeat, const float* cls, const float* bottlenecks, const float* ln_g,
+                                const float* ln_b, const float* pe, float drop_p, uint32_t seed, uint32_t salt,
+                                const uint32_t* seed_dev, const float* dX0, float* g_val, float* g_tim, float* g_feat,
+                                float* g_cls, float* g_bott, float* g_ln, float* dproj, void* stream);
+/* src [R,C] fp32 (row stride ld elements, C % 4 == 0) -> dst bf16 [R,6C] (stack_rows = 0) or [6R,C] (stack_rows = 1);
+ * side_b selects the B-operand term order */
+int tmp_split_bf16x3(const float* src, long long ld, long long R, int C, int side_b, int stack_rows, void* dst,
+                     void* stream);
+/* attention.py:24-49 in fp32: qkv [B*T,768] = Q|K|V, O [B*T,ld_o], lse2 [B,H,T_lse] log2-domain logsumexp */
+int tmp_attn_fwd_f32(const float* qkv, const int32_t* kv_len, int B, int T, int H, float* O, int ld_o, float* lse2,
+                     int T_lse, void* stream);
+/* dQKV [B*T,768] = dQ|dK|dV; delta [B,H,T_lse] workspace */
+int tmp_attn_bwd_f32(const float* qkv, const float* O, const float* dO, int ld_o, const int32_t* kv_len, int B, int T,
+                     int H, const float* lse2, int T_lse, float* delta, float* dQKV, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,20 @@ SIGNATURES = {
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
     "tmp_adamw_step_dev": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _vp],
+    # fp32 ("precise") mode: same operators on fp32-stored tensors, bf16x3 operand split, CUDA-core fp32 attention
+    "tmp_layernorm_fwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
+    "tmp_layernorm_bwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
+    "tmp_bottleneck_mix_fwd_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "tmp_bottleneck_mix_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "tmp_dropout_apply_f32": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
+    "tmp_colsum_f32": [_vp, _i, _ll, _i, _vp, _vp],
+    "tmp_stream_prologue_fwd_f32": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
+                                    _u32, _vp, _vp, _vp],
+    "tmp_stream_prologue_bwd_f32": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,
+                                    _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tmp_split_bf16x3": [_vp, _ll, _ll, _i, _i, _i, _vp, _vp],
+    "tmp_attn_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
+    "tmp_attn_bwd_f32": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
     "tmp_swin_patch_embed_ln": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tmp_swin_ln_window": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "tmp_swin_window_attn": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
@@ -75,7 +89,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (tmp_mma_attn_bwd = delta + main + dQ convert); bench.py reports the total
-_KERNELS_PER_CALL = {"tmp_mma_attn_bwd": 3}
+_KERNELS_PER_CALL = {"tmp_mma_attn_bwd": 3, "tmp_attn_bwd_f32": 2}
 launch_count = 0
 
 

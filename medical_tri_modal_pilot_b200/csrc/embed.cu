@@ -192,7 +192,7 @@ struct PrologueParams {
   const float* x;              // [B, n, 3]
   Branch val;
   // KIND 1
-  const h16* proj;             // [B*n, 256] fp16
+  const void* proj;            // [B*n, 256] fp16 (fp32 in the fp32 mode)
   const float* times;          // [B * n_slots]
   int n_slots, rows_per_slot;  // n = n_slots * rows_per_slot
   int feat_id;
@@ -206,10 +206,10 @@ struct PrologueParams {
   const float* pe;             // [>=T-4, 256] or null
   uint32_t drop_thr16; float drop_scale; uint32_t seed, salt;
   const uint32_t* seed_dev;    // optional device word added to `seed` (per-step counter of a captured CUDA graph)
-  h16* X0;                     // [B, T, 256] fp16
+  void* X0;                    // [B, T, 256] fp16 (fp32 in the fp32 mode)
 };
 
-template <int KIND>
+template <int KIND, int ST>
 __device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, const BranchLane& V, const BranchLane& Tm,
                                                    const float* sW, int b, int t, int lane, float (&e)[8], float& s_val,
                                                    float& s_time, int& fid) {
@@ -228,7 +228,7 @@ __device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, cons
     fid = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19);
     branch_add(V, s_val, branch_rstd(V, s_val), e);
   } else {
-    load8<ACT>(p.proj + ((size_t)b * p.n + j) * D + lane * 8, e);
+    ld8<ST>(p.proj, ((size_t)b * p.n + j) * D + lane * 8, e);
     s_time = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
     fid = p.feat_id;
   }
@@ -240,7 +240,7 @@ __device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, cons
   return true;
 }
 
-template <int KIND>
+template <int KIND, int ST>
 __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams p) {
   __shared__ __align__(16) float sW[20 * D];
   for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
@@ -256,12 +256,12 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
   const long long rows = (long long)p.B * p.T;
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     const int b = (int)(row / p.T), t = (int)(row % p.T);
-    h16* dst = p.X0 + row * D + lane * 8;
+    const size_t dst = (size_t)row * D + lane * 8;
     float e[8], sv = 0.f, st = 0.f;
     int fid = 0;
-    if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
+    if (!prologue_row_embed<KIND, ST>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
       load8_f32(p.bottlenecks + t * D + lane * 8, e);
-      store8<ACT>(dst, e);
+      st8<ST>(p.X0, dst, e);
       continue;
     }
     float s1 = 0.f;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
       const uint32_t base = (uint32_t)row * D + lane * 8;
       dropout_apply_run<8>(y, dropout_key(effective_seed(p.seed, p.seed_dev), p.salt), base, p.drop_thr16, p.drop_scale);
     }
-    store8<ACT>(dst, y);
+    st8<ST>(p.X0, dst, y);
   }
 }
 
@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams
 // ------------------------------------------------------------------------------------------------
 struct PrologueBwdParams {
   PrologueParams f;
-  const h16* dX0;    // [B, T, 256] bf16 (gradient)
+  const void* dX0;   // [B, T, 256] fp16 gradient (fp32 in the fp32 mode)
   float* g_val; float* g_tim; float* g_feat; float* g_cls; float* g_bott; float* g_ln;
-  h16* dproj;        // [B*n, 256] bf16 (gradient)
+  void* dproj;       // [B*n, 256] fp16 gradient (fp32 in the fp32 mode)
 };
 
 struct BranchAcc { float dw[8], db[8], dg[8], dbe[8]; };
@@ -334,7 +334,7 @@ __device__ __forceinline__ void flush8(float* sm, const float (&v)[8], int lane)
   for (int i = 0; i < 8; ++i) atomicAdd(&sm[lane * 8 + i], v[i]);
 }
 
-template <int KIND>
+template <int KIND, int ST>
 __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdParams q) {
   const PrologueParams& p = q.f;
   extern __shared__ __align__(16) float sm[];
@@ -363,10 +363,10 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     const int b = (int)(row / p.T), t = (int)(row % p.T);
     float g[8];
-    load8<GRD>(q.dX0 + row * D + lane * 8, g);
+    ld8<ST>(q.dX0, (size_t)row * D + lane * 8, g);
     float e[8], sv = 0.f, st = 0.f;
     int fid = 0;
-    if (!prologue_row_embed<KIND>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
+    if (!prologue_row_embed<KIND, ST>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
       flush8(sAcc + (9 + t) * D, g, lane);  // bottleneck parameter rows
       continue;
     }
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(&sG[fid * D + lane * 8 + i], de[i]);
     } else {
-      store8<GRD>(q.dproj + ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
+      st8<ST>(q.dproj, ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a_feat[i] += de[i];
     }
@@ -483,7 +483,7 @@ static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float*
   p.B = B; p.n = n; p.T = 5 + n;
   p.x = x;
   if (val4) p.val = Branch{val4[0], val4[1], val4[2], val4[3]}; else p.val = Branch{nullptr, nullptr, nullptr, nullptr};
-  p.proj = (const h16*)proj; p.times = times; p.n_slots = n_slots > 0 ? n_slots : 1;
+  p.proj = proj; p.times = times; p.n_slots = n_slots > 0 ? n_slots : 1;
   p.rows_per_slot = n_slots > 0 ? n / n_slots : n; if (p.rows_per_slot < 1) p.rows_per_slot = 1;
   p.feat_id = feat_id;
   p.tim = Branch{tim4[0], tim4[1], tim4[2], tim4[3]};
@@ -491,8 +491,29 @@ static int fill_prologue(PrologueParams& p, int kind, int B, int n, const float*
   p.drop_thr16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.seed = seed; p.salt = salt; p.seed_dev = seed_dev;
-  p.X0 = (h16*)X0;
+  p.X0 = X0;
   return TMP_OK;
+}
+
+static int prologue_fwd_impl(int stf, int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
+                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
+                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
+                             const float* pe, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                             void* X0, void* stream) {
+  PrologueParams p;
+  int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                         ln_b, pe, drop_p, seed, salt, seed_dev, X0);
+  if (rc) return rc;
+  const int grid = grid_for_rows((long long)B * p.T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (stf == FMT_F32) {
+    if (kind == 0) stream_prologue_fwd_kernel<0, FMT_F32><<<grid, 256, 0, s>>>(p);
+    else stream_prologue_fwd_kernel<1, FMT_F32><<<grid, 256, 0, s>>>(p);
+  } else {
+    if (kind == 0) stream_prologue_fwd_kernel<0, ACT><<<grid, 256, 0, s>>>(p);
+    else stream_prologue_fwd_kernel<1, ACT><<<grid, 256, 0, s>>>(p);
+  }
+  return tmp::check_launch("stream_prologue_fwd_kernel");
 }
 
 extern "C" int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, const float* const* val4,
@@ -501,14 +522,57 @@ extern "C" int tmp_stream_prologue_fwd(int kind, int B, int n, const float* x, c
                                        const float* bottlenecks, const float* ln_g, const float* ln_b, const float* pe,
                                        float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* X0,
                                        void* stream) {
-  PrologueParams p;
-  int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
-                         ln_b, pe, drop_p, seed, salt, seed_dev, X0);
+  return prologue_fwd_impl(ACT, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                           ln_b, pe, drop_p, seed, salt, seed_dev, X0, stream);
+}
+// fp32 mode: proj and X0 are fp32
+extern "C" int tmp_stream_prologue_fwd_f32(int kind, int B, int n, const float* x, const float* const* val4,
+                                           const float* proj, const float* times, int n_slots, int feat_id,
+                                           const float* const* tim4, const float* Wfeat, const float* cls,
+                                           const float* bottlenecks, const float* ln_g, const float* ln_b,
+                                           const float* pe, float drop_p, uint32_t seed, uint32_t salt,
+                                           const uint32_t* seed_dev, float* X0, void* stream) {
+  return prologue_fwd_impl(FMT_F32, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks,
+                           ln_g, ln_b, pe, drop_p, seed, salt, seed_dev, X0, stream);
+}
+
+static int prologue_bwd_impl(int stf, int kind, int B, int n, const float* x, const float* const* val4, const void* proj,
+                             const float* times, int n_slots, int feat_id, const float* const* tim4, const float* Wfeat,
+                             const float* cls, const float* bottlenecks, const float* ln_g, const float* ln_b,
+                             const float* pe, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev,
+                             const void* dX0, float* g_val, float* g_tim, float* g_feat, float* g_cls, float* g_bott,
+                             float* g_ln, void* dproj, void* stream) {
+  PrologueBwdParams q;
+  // X0 is not written by the backward; pass dX0 to satisfy the non-null check
+  int rc = fill_prologue(q.f, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                         ln_b, pe, drop_p, seed, salt, seed_dev, const_cast<void*>(dX0));
   if (rc) return rc;
-  const int grid = grid_for_rows((long long)B * p.T);
-  if (kind == 0) stream_prologue_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  else stream_prologue_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  return tmp::check_launch("stream_prologue_fwd_kernel");
+  TMP_REQUIRE(dX0 && g_tim && g_feat && g_cls && g_bott && g_ln, "prologue_bwd: null gradient buffer");
+  TMP_REQUIRE(kind == 1 || g_val, "prologue_bwd: vslt needs g_val");
+  TMP_REQUIRE(kind == 0 || dproj, "prologue_bwd: img/txt needs dproj");
+  q.dX0 = dX0;
+  q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
+  q.dproj = dproj;
+  const int smem = (20 + 20 + 15) * D * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  long long blocks = ((long long)B * q.f.T + 7) / 8;
+  if (blocks > tmp::num_sms()) blocks = tmp::num_sms();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (stf == FMT_F32) {
+    if (kind == 0) stream_prologue_bwd_kernel<0, FMT_F32><<<(int)blocks, 256, smem, s>>>(q);
+    else stream_prologue_bwd_kernel<1, FMT_F32><<<(int)blocks, 256, smem, s>>>(q);
+  } else {
+    if (kind == 0) stream_prologue_bwd_kernel<0, ACT><<<(int)blocks, 256, smem, s>>>(q);
+    else stream_prologue_bwd_kernel<1, ACT><<<(int)blocks, 256, smem, s>>>(q);
+  }
+  return tmp::check_launch("stream_prologue_bwd_kernel");
 }
 
 extern "C" int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, const float* const* val4,
@@ -519,27 +583,19 @@ extern "C" int tmp_stream_prologue_bwd(int kind, int B, int n, const float* x, c
                                        const void* dX0, float* g_val,
                                        float* g_tim, float* g_feat, float* g_cls, float* g_bott, float* g_ln,
                                        void* dproj, void* stream) {
-  PrologueBwdParams q;
-  // X0 is not written by the backward; pass dX0 to satisfy the non-null check
-  int rc = fill_prologue(q.f, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
-                         ln_b, pe, drop_p, seed, salt, seed_dev, const_cast<void*>(dX0));
-  if (rc) return rc;
-  TMP_REQUIRE(dX0 && g_tim && g_feat && g_cls && g_bott && g_ln, "prologue_bwd: null gradient buffer");
-  TMP_REQUIRE(kind == 1 || g_val, "prologue_bwd: vslt needs g_val");
-  TMP_REQUIRE(kind == 0 || dproj, "prologue_bwd: img/txt needs dproj");
-  q.dX0 = (const h16*)dX0;
-  q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
-  q.dproj = (h16*)dproj;
-  const int smem = (20 + 20 + 15) * D * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
-  long long blocks = ((long long)B * q.f.T + 7) / 8;
-  if (blocks > tmp::num_sms()) blocks = tmp::num_sms();
-  if (kind == 0) stream_prologue_bwd_kernel<0><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(q);
-  else stream_prologue_bwd_kernel<1><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(q);
-  return tmp::check_launch("stream_prologue_bwd_kernel");
+  return prologue_bwd_impl(ACT, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
+                           ln_b, pe, drop_p, seed, salt, seed_dev, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln, dproj,
+                           stream);
+}
+extern "C" int tmp_stream_prologue_bwd_f32(int kind, int B, int n, const float* x, const float* const* val4,
+                                           const float* proj, const float* times, int n_slots, int feat_id,
+                                           const float* const* tim4, const float* Wfeat, const float* cls,
+                                           const float* bottlenecks, const float* ln_g, const float* ln_b,
+                                           const float* pe, float drop_p, uint32_t seed, uint32_t salt,
+                                           const uint32_t* seed_dev, const float* dX0, float* g_val, float* g_tim,
+                                           float* g_feat, float* g_cls, float* g_bott, float* g_ln, float* dproj,
+                                           void* stream) {
+  return prologue_bwd_impl(FMT_F32, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks,
+                           ln_g, ln_b, pe, drop_p, seed, salt, seed_dev, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln,
+                           dproj, stream);
 }

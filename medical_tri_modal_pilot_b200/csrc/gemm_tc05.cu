@@ -129,7 +129,17 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_erf_pair(v[j], v[j + 1]);
   }
-  if (p.gate && row_ok) {
+  if (p.gate && row_ok && p.gate_fmt == FMT_F32) {   // fp32 mode: the gate tensor is stored in fp32
+    const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.gate) + (size_t)row * p.ld_gate + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 u = __ldg(g + q);
+      if (!(u.x > 0.f)) v[q * 4] = 0.f;
+      if (!(u.y > 0.f)) v[q * 4 + 1] = 0.f;
+      if (!(u.z > 0.f)) v[q * 4 + 2] = 0.f;
+      if (!(u.w > 0.f)) v[q * 4 + 3] = 0.f;
+    }
+  } else if (p.gate && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.ld_gate + col0);
     uint4 u[4];
 #pragma unroll
@@ -150,7 +160,14 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
     if (p.drop_fold) dropout_zero_run<32>(v, drop_key, idx0, p.drop_thr16);
     else dropout_apply_run<32>(v, drop_key, idx0, p.drop_thr16, p.drop_scale);
   }
-  if (p.residual && row_ok) {
+  if (p.residual && row_ok && p.res_fmt == FMT_F32) {   // fp32 mode: fp32 residual stream
+    const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)row * p.ld_res + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 u = __ldg(g + q);
+      v[q * 4] += u.x; v[q * 4 + 1] += u.y; v[q * 4 + 2] += u.z; v[q * 4 + 3] += u.w;
+    }
+  } else if (p.residual && row_ok) {
     const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
     uint4 u[4];
 #pragma unroll
@@ -503,6 +520,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         }
         atomicAdd(dbias + n0 + 2 * p, s0);
         atomicAdd(dbias + n0 + 2 * p + 1, s1);
+        // The dW write-out below stages its boxes in the first 32 KB of the ring (stage 0). `tfull_bar` only says that the
+        // MMAs have retired; a summing warp that is still reading the LAST k-block -- which sits in stage 0 whenever
+        // (k_blks - 1) % kStages == 0, e.g. 53 blocks per split at M = 64 320 -- would read another warp's fp32 boxes as
+        // dY (random values, NaN included: found as sporadic non-finite bias gradients at the bench shape). All four
+        // epilogue warps therefore meet here before any of them reuses the ring.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       const int quarter = warp & 3;
       mbar_wait(tfull_bar, 0);
@@ -591,6 +614,7 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const CUtensorM
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static bool fmt_ok(int f) { return f == FMT_F16 || f == FMT_BF16; }
+static bool fmt_ok32(int f) { return fmt_ok(f) || f == FMT_F32; }   // gate / residual may be fp32 (fp32 mode)
 
 extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N,
                                      int K, float alpha, const float* bias, int relu, const void* gate, int gate_fmt,
@@ -599,8 +623,9 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
                                      float* out_f32, int ld_out, void* stream) {
   void* out_bf16 = out16;
   TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
-  TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok(gate_fmt)) &&
-                  (!residual || fmt_ok(res_fmt)), "gemm: formats must be 0 (fp16) or 1 (bf16)");
+  TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok32(gate_fmt)) &&
+                  (!residual || fmt_ok32(res_fmt)),
+              "gemm: operand / output formats must be 0 (fp16) or 1 (bf16); gate / residual may also be 2 (fp32)");
   TMP_REQUIRE(a_fmt == b_fmt, "gemm: tcgen05 kind::f16 needs A and B in the same 16-bit format");
   TMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   TMP_REQUIRE(N % 128 == 0 && K % BK == 0, "gemm: N must be a multiple of 128 and K of 64 (N=%d K=%d)", N, K);

@@ -71,11 +71,11 @@ __device__ __forceinline__ void ln_stats(float (&c)[8], float& r, float& s_std) 
 }
 
 // ADD: h = x + o written to `sum_out`, then normalised.  x,o,sum_out,y: [rows,256] fp16
-template <bool ADD>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const h16* __restrict__ x, const h16* __restrict__ o,
+template <bool ADD, int ST>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ o,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, long long rows,
-                                                            h16* __restrict__ sum_out, h16* __restrict__ y) {
+                                                            void* __restrict__ sum_out, void* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   float g[8], be[8];
   load8_f32(gamma + lane * 8, g);
@@ -83,31 +83,33 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const h16* __restric
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     float c[8];
-    load8<ACT>(x + row * D + lane * 8, c);
+    const size_t at = (size_t)row * D + lane * 8;
+    ld8<ST>(x, at, c);
     if (ADD) {
       float a[8];
-      load8<ACT>(o + row * D + lane * 8, a);
+      ld8<ST>(o, at, a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) c[i] += a[i];
-      store8<ACT>(sum_out + row * D + lane * 8, c);
-      // normalise the fp16-rounded sum: it is what the backward pass and the residual path see
-      load8<ACT>(sum_out + row * D + lane * 8, c);
+      st8<ST>(sum_out, at, c);
+      // normalise the stored (fp16-rounded) sum: it is what the backward pass and the residual path see
+      ld8<ST>(sum_out, at, c);
     }
     float r, sd;
     ln_stats(c, r, sd);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaf(c[i] * r, g[i], be[i]);
-    store8<ACT>(y + row * D + lane * 8, v);
+    st8<ST>(y, at, v);
   }
 }
 
 // dx = dres + LN'(dy; x).  Optionally also writes dx_drop = dropout_mask(seed,salt) * dx / (1-p)
 // (the gradient entering the previous block's FFN2 when its output dropout is active).
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restrict__ dy, const h16* __restrict__ x,
-                                                            const h16* __restrict__ dres,
+template <int ST>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                            const void* __restrict__ dres,
                                                             const float* __restrict__ gamma, long long rows,
-                                                            h16* __restrict__ dx, h16* __restrict__ dx_drop,
+                                                            void* __restrict__ dx, void* __restrict__ dx_drop,
                                                             uint32_t drop_thr16, float drop_scale, uint32_t seed,
                                                             uint32_t salt, const uint32_t* __restrict__ seed_dev,
                                                             float* __restrict__ dgamma,
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restric
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     float c[8], gy[8];
-    load8<ACT>(x + row * D + lane * 8, c);
-    load8<GRD>(dy + row * D + lane * 8, gy);
+    const size_t at = (size_t)row * D + lane * 8;
+    ld8<ST>(x, at, c);
+    ld8<ST>(dy, at, gy);
     float r, sd;
     ln_stats(c, r, sd);
     float gbar = 0.f, gc = 0.f;
@@ -145,15 +148,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const h16* __restric
     for (int i = 0; i < 8; ++i) out[i] = r * (gy[i] - gbar) - k2 * c[i];
     if (dres) {
       float a[8];
-      load8<GRD>(dres + row * D + lane * 8, a);
+      ld8<ST>(dres, at, a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) out[i] += a[i];
     }
-    store8<GRD>(dx + row * D + lane * 8, out);
+    st8<ST>(dx, at, out);
     if (dx_drop) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
       dropout_apply_run<8>(out, dropout_key(effective_seed(seed, seed_dev), salt), base, drop_thr16, drop_scale);
-      store8<GRD>(dx_drop + row * D + lane * 8, out);
+      st8<ST>(dx_drop, at, out);
     }
   }
 #pragma unroll
@@ -181,7 +184,8 @@ __device__ __forceinline__ void mix_weights(long long code, float (&w)[3]) {
   }
 }
 
-__global__ void bottleneck_mix_fwd_kernel(h16* __restrict__ Yv, h16* __restrict__ Yi, h16* __restrict__ Yt, int Tv,
+template <int ST>
+__global__ void bottleneck_mix_fwd_kernel(void* __restrict__ Yv, void* __restrict__ Yi, void* __restrict__ Yt, int Tv,
                                           int Ti, int Tt, const long long* __restrict__ missing, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -189,27 +193,28 @@ __global__ void bottleneck_mix_fwd_kernel(h16* __restrict__ Yv, h16* __restrict_
   const int b = row >> 2, r = row & 3;
   float w[3];
   mix_weights(missing[b], w);
-  h16* pv = Yv + ((size_t)b * Tv + r) * D + lane * 8;
-  h16* pi = Yi + ((size_t)b * Ti + r) * D + lane * 8;
-  h16* pt = Yt + ((size_t)b * Tt + r) * D + lane * 8;
+  const size_t pv = ((size_t)b * Tv + r) * D + lane * 8;
+  const size_t pi = ((size_t)b * Ti + r) * D + lane * 8;
+  const size_t pt = ((size_t)b * Tt + r) * D + lane * 8;
   float acc[8], a[8];
-  load8<ACT>(pv, acc);
+  ld8<ST>(Yv, pv, acc);
   // sum first, scale once: the reference takes torch.mean over the selected stack (mbt_encoder.py:765-768)
-  if (w[1] != 0.f) { load8<ACT>(pi, a);
+  if (w[1] != 0.f) { ld8<ST>(Yi, pi, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
-  if (w[2] != 0.f) { load8<ACT>(pt, a);
+  if (w[2] != 0.f) { ld8<ST>(Yt, pt, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += a[i]; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] *= w[0];
-  store8<ACT>(pv, acc);
-  store8<ACT>(pi, acc);
-  store8<ACT>(pt, acc);
+  st8<ST>(Yv, pv, acc);
+  st8<ST>(Yi, pi, acc);
+  st8<ST>(Yt, pt, acc);
 }
 
 // gradient: g = sum over present dY_m rows; dY_m rows <- w_m * g.  A null pointer = stream absent in the upper layer.
-__global__ void bottleneck_mix_bwd_kernel(h16* __restrict__ dYv, h16* __restrict__ dYi, h16* __restrict__ dYt,
+template <int ST>
+__global__ void bottleneck_mix_bwd_kernel(void* __restrict__ dYv, void* __restrict__ dYi, void* __restrict__ dYt,
                                           int Tv, int Ti, int Tt, int upper_has_it,
                                           const long long* __restrict__ missing, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -218,35 +223,36 @@ __global__ void bottleneck_mix_bwd_kernel(h16* __restrict__ dYv, h16* __restrict
   const int b = row >> 2, r = row & 3;
   float w[3];
   mix_weights(missing[b], w);
-  h16* pv = dYv + ((size_t)b * Tv + r) * D + lane * 8;
-  h16* pi = dYi + ((size_t)b * Ti + r) * D + lane * 8;
-  h16* pt = dYt + ((size_t)b * Tt + r) * D + lane * 8;
+  const size_t pv = ((size_t)b * Tv + r) * D + lane * 8;
+  const size_t pi = ((size_t)b * Ti + r) * D + lane * 8;
+  const size_t pt = ((size_t)b * Tt + r) * D + lane * 8;
   float g[8], a[8], o[8];
-  load8<GRD>(pv, g);
+  ld8<ST>(dYv, pv, g);
   if (upper_has_it) {
-    load8<GRD>(pi, a);
+    ld8<ST>(dYi, pi, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += a[i];
-    load8<GRD>(pt, a);
+    ld8<ST>(dYt, pt, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += a[i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[0];
-  store8<GRD>(pv, o);
+  st8<ST>(dYv, pv, o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[1];
-  store8<GRD>(pi, o);
+  st8<ST>(dYi, pi, o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = g[i] * w[2];
-  store8<GRD>(pt, o);
+  st8<ST>(dYt, pt, o);
 }
 
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (bf16 gradients in, fp32 atomics out)
 // block = 256 threads = (N/8 column groups) x (rows in flight)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const h16* __restrict__ dY, int ld, long long M, int N,
+template <int ST>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ dY, int ld, long long M, int N,
                                                      long long rows_per_block, float* __restrict__ out) {
   extern __shared__ float sacc[];  // [N]
   for (int i = threadIdx.x; i < N; i += blockDim.x) sacc[i] = 0.f;
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const h16* __restrict__ dY,
     const long long r1 = min(M, r0 + rows_per_block);
     for (long long r = r0 + rl; r < r1; r += lanes_r) {
       float v[8];
-      load8<GRD>(dY + r * ld + cg * 8, v);
+      ld8<ST>(dY, (size_t)r * ld + cg * 8, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
@@ -273,16 +279,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const h16* __restrict__ dY,
   for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&out[i], sacc[i]);
 }
 
-__global__ void dropout_apply_kernel(const h16* __restrict__ in, h16* __restrict__ out, long long n8,
+template <int ST>
+__global__ void dropout_apply_kernel(const void* __restrict__ in, void* __restrict__ out, long long n8,
                                      uint32_t thr16, float scale, uint32_t seed, uint32_t salt,
                                      const uint32_t* __restrict__ seed_dev) {
   const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i8 >= n8) return;
   float v[8];
-  load8<GRD>(in + i8 * 8, v);
+  ld8<ST>(in, (size_t)i8 * 8, v);
   const uint32_t base = (uint32_t)(i8 * 8);
   dropout_apply_run<8>(v, dropout_key(effective_seed(seed, seed_dev), salt), base, thr16, scale);
-  store8<GRD>(out + i8 * 8, v);
+  st8<ST>(out, (size_t)i8 * 8, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,24 +386,34 @@ extern "C" int tmp_debug_materialize_mask(const int32_t* kv_len, int B, int T, u
   return tmp::check_launch("materialize_mask_kernel");
 }
 
-extern "C" int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
-                                 void* sum_out, void* y, void* stream) {
+static int layernorm_fwd_impl(int st, const void* x, const void* add, const float* gamma, const float* beta,
+                              long long rows, void* sum_out, void* y, void* stream) {
   TMP_REQUIRE(x && gamma && beta && y && rows >= 0, "layernorm_fwd: bad argument");
   TMP_REQUIRE(!add || sum_out, "layernorm_fwd: fused add needs sum_out");
   if (rows == 0) return TMP_OK;
   const int grid = rows_grid(rows);
-  if (add)
-    layernorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const h16*)x, (const h16*)add, gamma, beta,
-                                                                        rows, (h16*)sum_out, (h16*)y);
-  else
-    layernorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const h16*)x, nullptr, gamma, beta, rows,
-                                                                         nullptr, (h16*)y);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st == FMT_F32) {
+    if (add) layernorm_fwd_kernel<true, FMT_F32><<<grid, 256, 0, s>>>(x, add, gamma, beta, rows, sum_out, y);
+    else layernorm_fwd_kernel<false, FMT_F32><<<grid, 256, 0, s>>>(x, nullptr, gamma, beta, rows, nullptr, y);
+  } else {
+    if (add) layernorm_fwd_kernel<true, ACT><<<grid, 256, 0, s>>>(x, add, gamma, beta, rows, sum_out, y);
+    else layernorm_fwd_kernel<false, ACT><<<grid, 256, 0, s>>>(x, nullptr, gamma, beta, rows, nullptr, y);
+  }
   return tmp::check_launch("layernorm_fwd_kernel");
 }
+extern "C" int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const float* beta, long long rows,
+                                 void* sum_out, void* y, void* stream) {
+  return layernorm_fwd_impl(ACT, x, add, gamma, beta, rows, sum_out, y, stream);
+}
+extern "C" int tmp_layernorm_fwd_f32(const float* x, const float* add, const float* gamma, const float* beta,
+                                     long long rows, float* sum_out, float* y, void* stream) {
+  return layernorm_fwd_impl(FMT_F32, x, add, gamma, beta, rows, sum_out, y, stream);
+}
 
-extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
-                                 void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt,
-                                 const uint32_t* seed_dev, float* dgamma, float* dbeta, void* stream) {
+static int layernorm_bwd_impl(int st, const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
+                              void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt,
+                              const uint32_t* seed_dev, float* dgamma, float* dbeta, void* stream) {
   TMP_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && rows >= 0, "layernorm_bwd: bad argument");
   TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: dropout p out of range");
   if (rows == 0) return TMP_OK;
@@ -404,29 +421,68 @@ extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres
   if (blocks > 2LL * tmp::num_sms()) blocks = 2LL * tmp::num_sms();
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  layernorm_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const h16*)dy, (const h16*)x, (const h16*)dres, gamma, rows, (h16*)dx, thr ? (h16*)dx_drop : nullptr, thr,
-      scale, seed, salt, seed_dev, dgamma, dbeta);
+  if (st == FMT_F32)
+    layernorm_bwd_kernel<FMT_F32><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<ACT><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta);
   return tmp::check_launch("layernorm_bwd_kernel");
 }
+extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
+                                 void* dx, void* dx_drop, float drop_p, uint32_t seed, uint32_t salt,
+                                 const uint32_t* seed_dev, float* dgamma, float* dbeta, void* stream) {
+  return layernorm_bwd_impl(ACT, dy, x, dres, gamma, rows, dx, dx_drop, drop_p, seed, salt, seed_dev, dgamma, dbeta, stream);
+}
+extern "C" int tmp_layernorm_bwd_f32(const float* dy, const float* x, const float* dres, const float* gamma,
+                                     long long rows, float* dx, float* dx_drop, float drop_p, uint32_t seed,
+                                     uint32_t salt, const uint32_t* seed_dev, float* dgamma, float* dbeta,
+                                     void* stream) {
+  return layernorm_bwd_impl(FMT_F32, dy, x, dres, gamma, rows, dx, dx_drop, drop_p, seed, salt, seed_dev, dgamma, dbeta,
+                            stream);
+}
 
-extern "C" int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing,
-                                      int B, void* stream) {
+static int mix_fwd_impl(int st, void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
+                        void* stream) {
   TMP_REQUIRE(Yv && Yi && Yt && missing && B > 0 && Tv >= 4 && Ti >= 4 && Tt >= 4, "bottleneck_mix_fwd: bad argument");
-  bottleneck_mix_fwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>((h16*)Yv, (h16*)Yi, (h16*)Yt, Tv, Ti,
-                                                                              Tt, missing, B);
+  if (st == FMT_F32)
+    bottleneck_mix_fwd_kernel<FMT_F32><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(Yv, Yi, Yt, Tv, Ti, Tt, missing, B);
+  else
+    bottleneck_mix_fwd_kernel<ACT><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(Yv, Yi, Yt, Tv, Ti, Tt, missing, B);
   return tmp::check_launch("bottleneck_mix_fwd_kernel");
 }
-
-extern "C" int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
-                                      const long long* missing, int B, void* stream) {
-  TMP_REQUIRE(dYv && dYi && dYt && missing && B > 0, "bottleneck_mix_bwd: bad argument");
-  bottleneck_mix_bwd_kernel<<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      (h16*)dYv, (h16*)dYi, (h16*)dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B);
-  return tmp::check_launch("bottleneck_mix_bwd_kernel");
+extern "C" int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing,
+                                      int B, void* stream) {
+  return mix_fwd_impl(ACT, Yv, Yi, Yt, Tv, Ti, Tt, missing, B, stream);
+}
+extern "C" int tmp_bottleneck_mix_fwd_f32(float* Yv, float* Yi, float* Yt, int Tv, int Ti, int Tt,
+                                          const long long* missing, int B, void* stream) {
+  return mix_fwd_impl(FMT_F32, Yv, Yi, Yt, Tv, Ti, Tt, missing, B, stream);
 }
 
-extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream) {
+static int mix_bwd_impl(int st, void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
+                        const long long* missing, int B, void* stream) {
+  TMP_REQUIRE(dYv && dYi && dYt && missing && B > 0, "bottleneck_mix_bwd: bad argument");
+  if (st == FMT_F32)
+    bottleneck_mix_bwd_kernel<FMT_F32><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dYv, dYi, dYt, Tv, Ti, Tt,
+                                                                                        upper_has_img_txt, missing, B);
+  else
+    bottleneck_mix_bwd_kernel<GRD><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dYv, dYi, dYt, Tv, Ti, Tt,
+                                                                                    upper_has_img_txt, missing, B);
+  return tmp::check_launch("bottleneck_mix_bwd_kernel");
+}
+extern "C" int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
+                                      const long long* missing, int B, void* stream) {
+  return mix_bwd_impl(GRD, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, stream);
+}
+extern "C" int tmp_bottleneck_mix_bwd_f32(float* dYv, float* dYi, float* dYt, int Tv, int Ti, int Tt,
+                                          int upper_has_img_txt, const long long* missing, int B, void* stream) {
+  return mix_bwd_impl(FMT_F32, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, stream);
+}
+
+// out[N] += column sums of dY [M, N]. The 16-bit path gets its bias gradients from the weight-gradient kernel
+// (gemm_wgrad, fused); this stand-alone form serves the fp32 mode, whose split operands cannot be summed that way.
+static int colsum_impl(int st, const void* dY, int ld, long long M, int N, float* out, void* stream) {
   TMP_REQUIRE(dY && out && M >= 0 && N > 0 && N % 8 == 0 && N <= 2048 && ld % 8 == 0, "colsum: bad argument");
   if (M == 0) return TMP_OK;
   const int groups = N / 8;
@@ -435,19 +491,41 @@ extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out
   long long rpb = (M + blocks - 1) / blocks;
   if (rpb < 32) rpb = 32;
   blocks = (M + rpb - 1) / rpb;
-  colsum_kernel<<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>((const h16*)dY, ld, M, N, rpb, out);
+  if (st == FMT_F32)
+    colsum_kernel<FMT_F32><<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>(dY, ld, M, N, rpb, out);
+  else
+    colsum_kernel<GRD><<<(int)blocks, 256, N * sizeof(float), (cudaStream_t)stream>>>(dY, ld, M, N, rpb, out);
   return tmp::check_launch("colsum_kernel");
 }
+extern "C" int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream) {
+  return colsum_impl(GRD, dY, ld, M, N, out, stream);
+}
+extern "C" int tmp_colsum_f32(const float* dY, int ld, long long M, int N, float* out, void* stream) {
+  return colsum_impl(FMT_F32, dY, ld, M, N, out, stream);
+}
 
-extern "C" int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
-                                 const uint32_t* seed_dev, void* stream) {
+static int dropout_apply_impl(int st, const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                              const uint32_t* seed_dev, void* stream) {
   TMP_REQUIRE(in && out && n >= 0 && n % 8 == 0 && drop_p >= 0.f && drop_p < 1.f, "dropout_apply: bad argument");
   if (n == 0) return TMP_OK;
   const uint32_t thr = (uint32_t)(drop_p * 65536.f + 0.5f);
   const long long n8 = n / 8;
-  dropout_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const h16*)in, (h16*)out, n8, thr, 1.f / (1.f - drop_p), seed, salt, seed_dev);
+  const unsigned grid = (unsigned)((n8 + 255) / 256);
+  if (st == FMT_F32)
+    dropout_apply_kernel<FMT_F32><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, n8, thr, 1.f / (1.f - drop_p), seed, salt,
+                                                                        seed_dev);
+  else
+    dropout_apply_kernel<GRD><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, n8, thr, 1.f / (1.f - drop_p), seed, salt,
+                                                                    seed_dev);
   return tmp::check_launch("dropout_apply_kernel");
+}
+extern "C" int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                                 const uint32_t* seed_dev, void* stream) {
+  return dropout_apply_impl(GRD, in, out, n, drop_p, seed, salt, seed_dev, stream);
+}
+extern "C" int tmp_dropout_apply_f32(const float* in, float* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
+                                     const uint32_t* seed_dev, void* stream) {
+  return dropout_apply_impl(FMT_F32, in, out, n, drop_p, seed, salt, seed_dev, stream);
 }
 
 // descs: device array of n_desc {const float* src; bf16* dst; bf16* dst_t; int R; int C}; max_R/max_C bound the grid

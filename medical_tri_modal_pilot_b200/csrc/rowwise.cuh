@@ -52,5 +52,22 @@ __device__ __forceinline__ void store8_f32(float* __restrict__ p, const float (&
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
+// Storage-format-generic row access: ST = tc05::FMT_F16 (the 16-bit plan) or tc05::FMT_F32 (the fp32 "precise" mode, where
+// every activation / gradient tensor is stored in fp32). `elem` is an ELEMENT offset from `base`.
+template <int ST>
+__device__ __forceinline__ void ld8(const void* __restrict__ base, size_t elem, float (&v)[8]) {
+  if (ST == tc05::FMT_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    load8<ST == tc05::FMT_F32 ? tc05::FMT_F16 : ST>(static_cast<const h16*>(base) + elem, v);
+  }
+}
+template <int ST>
+__device__ __forceinline__ void st8(void* __restrict__ base, size_t elem, const float (&v)[8]) {
+  if (ST == tc05::FMT_F32) store8_f32(static_cast<float*>(base) + elem, v);
+  else store8<ST == tc05::FMT_F32 ? tc05::FMT_F16 : ST>(static_cast<h16*>(base) + elem, v);
+}
 
 }  // namespace rw

@@ -147,7 +147,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 //   bit15=a_major (0=K,1=MN)  bit16=b_major  [17,23)=N>>3  [24,29)=M>>4
 //   a_fmt / b_fmt: 0 = F16, 1 = BF16 (the two operands may differ: forward activations and weights are fp16,
 //   gradient tensors are bf16 -- see DESIGN.md "precision").
-enum : int { FMT_F16 = 0, FMT_BF16 = 1 };
+enum : int { FMT_F16 = 0, FMT_BF16 = 1, FMT_F32 = 2 };   // FMT_F32: storage format of the fp32 ("precise") mode only
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
   return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

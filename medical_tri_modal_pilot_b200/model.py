@@ -159,6 +159,20 @@ class TRI_MBT_VSLTCLS(nn.Module):
         self._fused = FusedPath(self)
         self.native_swin = True      # frozen image encoder through swin_feed.SwinFeed (False: stock torchvision forward)
         self.img_autocast = True     # run the frozen Swin in bf16 (its output feeds an fp16 tensor-core GEMM anyway)
+        # precision mode: "fp16" (tensor-core plan, the reference's autocast dtype) or "fp32" (north-star FP32 parity mode:
+        # fp32 storage, bf16x3-split tensor-core GEMMs, fp32 attention; runtime.FusedPath.precision). Not a reference flag:
+        # `args.precision` if the caller sets it, else env TMP_B200_PRECISION.
+        import os
+        self.set_precision(getattr(args, "precision", None) or os.environ.get("TMP_B200_PRECISION", "fp16"))
+
+    def set_precision(self, precision: str):
+        if precision not in ("fp16", "fp32"):
+            raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
+        self._fused.precision = precision
+        if precision == "fp32":      # the frozen image encoder runs as the stock fp32 torchvision module in this mode
+            self.native_swin = False
+            self.img_autocast = False
+        return self
 
     # -- reference forward contract (tri_mbt_vsltcls.py:167) ----------------------------------------------------
     def forward(self, x, h, m, d, x_m, age, gen, input_lengths, txts, txt_lengths, img, missing, f_indices, img_time,
@@ -195,8 +209,9 @@ class TRI_MBT_VSLTCLS(nn.Module):
     def encode_images(self, img, missing):
         """Frozen image encoder (reference tri_mbt_vsltcls.py:205-209: reshape(-1,1,224,224), torch.no_grad).
         Returns [B*n_img, 49, 768] fp16 (the A operand of the 768->256 projection GEMM)."""
+        f32 = self._fused.precision == "fp32"
         if img.dim() == 3 and img.shape[-1] == 768:      # test hook: pre-computed Swin features
-            return img.to(torch.float16).contiguous()
+            return img.to(torch.float32 if f32 else torch.float16).contiguous()
         if self.multiimages == 1:
             img = img.reshape(-1, 1, 224, 224)
         with torch.no_grad():
@@ -206,7 +221,7 @@ class TRI_MBT_VSLTCLS(nn.Module):
                 f = self._img_encoder_bf16()(img.to(torch.bfloat16))
             else:
                 f = self.img_encoder(img)
-        return f.reshape(f.shape[0], 49, 768).to(torch.float16).contiguous()
+        return f.reshape(f.shape[0], 49, 768).to(torch.float32 if f32 else torch.float16).contiguous()
 
     def _swin_sig(self):
         first = self.img_encoder.features[0][0].weight

@@ -11,7 +11,13 @@ D = 256
 H = 4
 ACT = torch.float16     # forward activations + 16-bit weight copies
 GRD = torch.float16     # gradient tensors (carry runtime.GRAD_SCALE)
-_FMT = {torch.float16: 0, torch.bfloat16: 1}
+_FMT = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}   # 2 (fp32): gate / residual of the fp32 mode only
+F32 = torch.float32
+
+
+def _f32(t):
+    """True when `t` is an fp32-stored activation / gradient tensor, i.e. the call belongs to the fp32 ("precise") mode."""
+    return t is not None and t.dtype == torch.float32
 
 
 def _fmt(t):
@@ -20,7 +26,7 @@ def _fmt(t):
     try:
         return _FMT[t.dtype]
     except KeyError:
-        raise RuntimeError(f"16-bit tensor (fp16 / bf16) required, got {t.dtype}") from None
+        raise RuntimeError(f"fp16 / bf16 (or fp32 in the fp32 mode) tensor required, got {t.dtype}") from None
 
 
 
@@ -74,15 +80,18 @@ def umse_embed(x, val4, tim4, Wfeat, out_dtype=torch.float32):
 
 def stream_prologue_fwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
                         pe, drop_p, seed, salt, X0, seed_dev=None):
-    check(_lib.load().tmp_stream_prologue_fwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
+    fn = _lib.load().tmp_stream_prologue_fwd_f32 if _f32(X0) else _lib.load().tmp_stream_prologue_fwd
+    check(fn(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
                                               ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
                                               ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
                                               salt, ptr(seed_dev), ptr(X0), stream_ptr()), "tmp_stream_prologue_fwd")
 
 
+
 def stream_prologue_bwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g, ln_b,
                         pe, drop_p, seed, salt, dX0, g_val, g_tim, g_feat, g_cls, g_bott, g_ln, dproj, seed_dev=None):
-    check(_lib.load().tmp_stream_prologue_bwd(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
+    fn = _lib.load().tmp_stream_prologue_bwd_f32 if _f32(dX0) else _lib.load().tmp_stream_prologue_bwd
+    check(fn(kind, B, n, ptr(x), ptr_array(val4) if val4 else None, ptr(proj),
                                               ptr(times), n_slots, feat_id, ptr_array(tim4), ptr(Wfeat), ptr(cls),
                                               ptr(bottlenecks), ptr(ln_g), ptr(ln_b), ptr(pe), float(drop_p), seed,
                                               salt, ptr(seed_dev), ptr(dX0), ptr(g_val), ptr(g_tim), ptr(g_feat), ptr(g_cls),
@@ -92,21 +101,43 @@ def stream_prologue_bwd(kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4
 
 def layernorm_fwd(x, gamma, beta, y, add=None, sum_out=None):
     rows = x.numel() // D
-    check(_lib.load().tmp_layernorm_fwd(ptr(x), ptr(add), ptr(gamma), ptr(beta), rows, ptr(sum_out), ptr(y),
-                                        stream_ptr()), "tmp_layernorm_fwd")
+    fn = _lib.load().tmp_layernorm_fwd_f32 if _f32(x) else _lib.load().tmp_layernorm_fwd
+    check(fn(ptr(x), ptr(add), ptr(gamma), ptr(beta), rows, ptr(sum_out), ptr(y), stream_ptr()), "tmp_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, dres, gamma, dx, dgamma, dbeta, dx_drop=None, drop_p=0.0, seed=0, salt=0, seed_dev=None):
     rows = x.numel() // D
-    check(_lib.load().tmp_layernorm_bwd(ptr(dy), ptr(x), ptr(dres), ptr(gamma), rows, ptr(dx), ptr(dx_drop),
-                                        float(drop_p), seed, salt, ptr(seed_dev), ptr(dgamma), ptr(dbeta),
-                                        stream_ptr()),
-          "tmp_layernorm_bwd")
+    fn = _lib.load().tmp_layernorm_bwd_f32 if _f32(x) else _lib.load().tmp_layernorm_bwd
+    check(fn(ptr(dy), ptr(x), ptr(dres), ptr(gamma), rows, ptr(dx), ptr(dx_drop), float(drop_p), seed, salt,
+             ptr(seed_dev), ptr(dgamma), ptr(dbeta), stream_ptr()), "tmp_layernorm_bwd")
+
+
+def split_bf16x3(src, side_b=False, stack_rows=False):
+    """fp32 [R,C] (last-dim contiguous, row stride a multiple of 4) -> bf16 [R,6C] (K-side blocks) or [6R,C] (row-stacked
+    blocks): the bf16x3 operand split of the fp32 mode (csrc/precise.cu)."""
+    C = src.shape[-1]
+    R = src.numel() // C if src.is_contiguous() else src.shape[0]
+    ld = C if src.is_contiguous() else src.stride(0)
+    out = torch.empty((6 * R, C) if stack_rows else (R, 6 * C), dtype=torch.bfloat16, device=src.device)
+    check(_lib.load().tmp_split_bf16x3(ptr(src), ld, R, C, int(side_b), int(stack_rows), ptr(out), stream_ptr()),
+          "tmp_split_bf16x3")
+    return out
 
 
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
          salt=0, M=None, seed_dev=None):
-    """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16."""
+    """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16.
+    fp32 mode (A and Bw fp32): both operands are split into bf16x3 along K and the same tcgen05 kernel accumulates the six
+    partial products in fp32; `out` is then an fp32 tensor, gate / residual are fp32."""
+    if _f32(A):
+        if not _f32(Bw) or (out is not None and not _f32(out)):
+            raise RuntimeError("gemm (fp32 mode): A, Bw and out must all be fp32")
+        K = A.shape[-1]
+        M = A.numel() // K if M is None else M
+        A2 = A.reshape(-1, K)[:M] if A.is_contiguous() else A
+        return gemm(split_bf16x3(A2, side_b=False), split_bf16x3(Bw, side_b=True), out_f32=out if out is not None else out_f32,
+                    bias=bias, relu=relu, gate=gate, residual=residual, alpha=alpha, drop_p=drop_p, seed=seed, salt=salt,
+                    M=M, seed_dev=seed_dev)
     K = A.shape[-1]
     M = A.numel() // K if M is None else M
     N = Bw.shape[0]
@@ -122,9 +153,17 @@ def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residu
 
 
 def gemm_wgrad(dY, X, dW, M=None, dbias=None):
-    """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]; dbias[N] fp32 += column sums of dY when given (fused bias gradient)"""
+    """dW[N,K] fp32 += dY[M,N]^T @ X[M,K]; dbias[N] fp32 += column sums of dY when given (fused bias gradient).
+    fp32 mode (dY, X fp32): bf16x3 blocks stacked along the token dimension (6M rows); the bias gradient is a separate
+    column-sum pass over the fp32 dY."""
     N, K = dY.shape[-1], X.shape[-1]
     M = dY.numel() // N if M is None else M
+    if _f32(dY):
+        if dbias is not None:
+            colsum(dY, dbias, M=M)
+        dY6 = split_bf16x3(dY.reshape(-1, N)[:M], side_b=False, stack_rows=True)
+        X6 = split_bf16x3(X.reshape(-1, K)[:M], side_b=True, stack_rows=True)
+        return gemm_wgrad(dY6, X6, dW, M=6 * M)
     check(_lib.load().tmp_gemm_wgrad(ptr(dY), _fmt(dY), N, ptr(X), _fmt(X), K, M, N, K, ptr(dW),
                                      ptr(dbias) if dbias is not None else None, stream_ptr()), "tmp_gemm_wgrad")
 
@@ -132,15 +171,22 @@ def gemm_wgrad(dY, X, dW, M=None, dbias=None):
 def colsum(dY, out, M=None):
     N = dY.shape[-1]
     M = dY.numel() // N if M is None else M
-    check(_lib.load().tmp_colsum(ptr(dY), N, M, N, ptr(out), stream_ptr()), "tmp_colsum")
+    fn = _lib.load().tmp_colsum_f32 if _f32(dY) else _lib.load().tmp_colsum
+    check(fn(ptr(dY), N, M, N, ptr(out), stream_ptr()), "tmp_colsum")
 
 
 def attn_fwd(qkv, kv_len, B, T, O, lse2):
+    if _f32(qkv):      # fp32 mode: CUDA-core fp32 attention (csrc/precise.cu)
+        return check(_lib.load().tmp_attn_fwd_f32(ptr(qkv), ptr(kv_len), B, T, H, ptr(O), O.shape[-1], ptr(lse2),
+                                                  lse2.shape[-1], stream_ptr()), "tmp_attn_fwd_f32")
     check(_lib.load().tmp_mma_attn_fwd(ptr(qkv), ptr(kv_len), B, T, H, ptr(O), O.shape[-1], ptr(lse2), lse2.shape[-1],
                                        stream_ptr()), "tmp_mma_attn_fwd")
 
 
 def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV):
+    if _f32(qkv):
+        return check(_lib.load().tmp_attn_bwd_f32(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),
+                                                  lse2.shape[-1], ptr(delta), ptr(dQKV), stream_ptr()), "tmp_attn_bwd_f32")
     check(_lib.load().tmp_mma_attn_bwd(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),
                                        lse2.shape[-1], ptr(delta), ptr(dQ_acc), ptr(dQKV), stream_ptr()),
           "tmp_mma_attn_bwd")
@@ -148,21 +194,22 @@ def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV):
 
 def bottleneck_mix_fwd(Yv, Yi, Yt, missing):
     B = Yv.shape[0]
-    check(_lib.load().tmp_bottleneck_mix_fwd(ptr(Yv), ptr(Yi), ptr(Yt), Yv.shape[1], Yi.shape[1], Yt.shape[1],
+    fn = _lib.load().tmp_bottleneck_mix_fwd_f32 if _f32(Yv) else _lib.load().tmp_bottleneck_mix_fwd
+    check(fn(ptr(Yv), ptr(Yi), ptr(Yt), Yv.shape[1], Yi.shape[1], Yt.shape[1],
                                              ptr(missing), B, stream_ptr()), "tmp_bottleneck_mix_fwd")
 
 
 def bottleneck_mix_bwd(dYv, dYi, dYt, upper_has_img_txt, missing):
     B = dYv.shape[0]
-    check(_lib.load().tmp_bottleneck_mix_bwd(ptr(dYv), ptr(dYi), ptr(dYt), dYv.shape[1], dYi.shape[1], dYt.shape[1],
+    fn = _lib.load().tmp_bottleneck_mix_bwd_f32 if _f32(dYv) else _lib.load().tmp_bottleneck_mix_bwd
+    check(fn(ptr(dYv), ptr(dYi), ptr(dYt), dYv.shape[1], dYi.shape[1], dYt.shape[1],
                                              int(upper_has_img_txt), ptr(missing), B, stream_ptr()),
           "tmp_bottleneck_mix_bwd")
 
 
 def dropout_apply(inp, out, drop_p, seed, salt, seed_dev=None):
-    check(_lib.load().tmp_dropout_apply(ptr(inp), ptr(out), inp.numel(), float(drop_p), seed, salt, ptr(seed_dev),
-                                        stream_ptr()),
-          "tmp_dropout_apply")
+    fn = _lib.load().tmp_dropout_apply_f32 if _f32(inp) else _lib.load().tmp_dropout_apply
+    check(fn(ptr(inp), ptr(out), inp.numel(), float(drop_p), seed, salt, ptr(seed_dev), stream_ptr()), "tmp_dropout_apply")
 
 
 def cast_weights(descs_dev, n_desc, max_R, max_C):

@@ -61,6 +61,11 @@ class FusedPath:
         # img / txt modality streams on side CUDA streams (TMP_B200_SINGLE_STREAM=1 serialises them: debugging aid)
         self.multi_stream = os.environ.get("TMP_B200_SINGLE_STREAM", "0") != "1"
         self.grad_scale = GRAD_SCALE
+        # "fp16": the tensor-core plan above. "fp32": north-star's FP32 parity mode -- every activation / gradient tensor in
+        # fp32, GEMM operands split into bf16x3 for the same tcgen05 kernels, attention on the CUDA cores (csrc/precise.cu):
+        # logits within 1e-3 of the reference and every parameter gradient cosine >= 0.999 end to end. Chosen by
+        # `args.precision` / env TMP_B200_PRECISION (model.py); ~10x slower, for validation not throughput.
+        self.precision = "fp16"
         self.seed_base = None     # dropout seed = seed_base + step_dev (device int32 counter, see forward)
         self.step_dev = None
 
@@ -179,7 +184,9 @@ class FusedPath:
         small LRU keyed by shape (eager calls with ever-changing shapes cannot accumulate more than 3), and every graph
         additionally pins the workspace object it captured (`pin()`), which keeps the memory alive for as long as the
         graph exists even after the LRU dropped it."""
-        key = (B, L, n_img)
+        f32 = self.precision == "fp32"
+        ACT = GRD = torch.float32 if f32 else ops.ACT     # noqa: N806 (shadow the module-level dtypes for this workspace)
+        key = (B, L, n_img, self.precision)
         hit = self._ws_cache.pop(key, None)
         if hit is not None:
             self._ws_cache[key] = hit
@@ -280,20 +287,25 @@ class FusedPath:
         ctx["kv_len"] = ops.build_lengths(input_lengths.to(torch.long).contiguous(), txt_lengths.to(torch.long).contiguous(),
                                           ctx["img_time"], n_img, m.multiimages, ctx["missing"], int(self.skip_missing),
                                           T[0], T[1], T[2])
-        # refresh bf16 (+ transposed) parameter copies
-        ops.cast_weights(self.cast_descs, 1, self.total // 256, 256)              # flat fp32 -> bf16
-        ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
+        f32 = self.precision == "fp32"
+        ctx["f32"] = f32
+        if not f32:
+            # refresh fp16 (+ transposed) parameter copies
+            ops.cast_weights(self.cast_descs, 1, self.total // 256, 256)              # flat fp32 -> fp16
+            ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
         # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
-        ctx["txts16"] = txts.reshape(B * 128, 768).to(ACT).contiguous()
-        ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(ACT).contiguous()
+        adt = torch.float32 if f32 else ACT
+        ctx["txts16"] = txts.reshape(B * 128, 768).to(adt).contiguous()
+        ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(adt).contiguous()
+        Wop = self.W if f32 else self.H16       # GEMM weight operand: fp32 master (split in ops.gemm) or the fp16 copy
         # The three modality streams of a layer are independent until the bottleneck exchange (mbt_encoder.py:744-776):
         # vslt runs on the caller's stream, img / txt on two side streams, joined at every exchange.
         self._fork()
         with self._lane(1):
-            ops.gemm(ctx["img16"], self.H16("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
+            ops.gemm(ctx["img16"], Wop("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[1]["X"][0], **self._prologue_args(1, ctx))
         with self._lane(2):
-            ops.gemm(ctx["txts16"], self.H16("txt_embedding.weight", D, 768), out=self.proj[2],
+            ops.gemm(ctx["txts16"], Wop("txt_embedding.weight", D, 768), out=self.proj[2],
                      bias=self.W("txt_embedding.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[2]["X"][0], **self._prologue_args(2, ctx))
         ops.stream_prologue_fwd(X0=self.ws[0]["X"][0], **self._prologue_args(0, ctx))
@@ -351,6 +363,8 @@ class FusedPath:
     def _layer_fwd(self, l, s, ctx):
         st = self.ws[s]
         w, _, h16 = self.blocks[(l, s)]
+        if ctx["f32"]:
+            h16 = w                       # fp32 mode: the fp32 masters are the GEMM operands (split into bf16x3 by ops.gemm)
         B, T, M = ctx["B"], st["T"], st["M"]
         p, seed, sd = ctx["p"], ctx["seed"], ctx["seed_dev"]
         x = st["X"][l]
@@ -385,7 +399,9 @@ class FusedPath:
         self.flat_g.zero_()
         for s in range(3):
             self.ws[s]["g_y"].zero_()
-        self.ws[0]["g_y"][:, 4, :] = (d_cls * self.grad_scale).to(GRD)
+        gscale = 1.0 if ctx["f32"] else self.grad_scale      # fp32 gradients need no scale
+        ctx["gscale"] = gscale
+        self.ws[0]["g_y"][:, 4, :] = (d_cls * gscale).to(self.ws[0]["g_y"].dtype)
         for l in range(NL - 1, -1, -1):
             last = m.vsltonly == 1 and l == NL - 1
             if not last:
@@ -398,7 +414,7 @@ class FusedPath:
                 self._join()
             if self.debug_trace is not None:       # tools/gpu_grad_trace.py: dL/dX[l] per stream (scaled fp16)
                 for s in ([0] if last else [0, 1, 2]):
-                    self.debug_trace[("dX", l, s)] = self.ws[s]["g_y"].float().div(self.grad_scale).cpu()
+                    self.debug_trace[("dX", l, s)] = self.ws[s]["g_y"].float().div(gscale).cpu()
             # after _layer_bwd, g_y of each processed stream holds dX[l] (gradient wrt the layer input)
             if l > 0:
                 upper_has_it = 0 if last else 1
@@ -433,7 +449,8 @@ class FusedPath:
     def _range_done(self, a, b):
         """flat_g[a:b] is complete: remove the fp16 gradient scale and hand the range to the data-parallel hook
         (trainer.GradSync launches its all-reduce on the communication stream while the backward continues)."""
-        self.flat_g[a:b].mul_(1.0 / self.grad_scale)
+        if self.ctx["gscale"] != 1.0:
+            self.flat_g[a:b].mul_(1.0 / self.ctx["gscale"])
         if self.comm_hook is not None:
             self.comm_hook(a, b)
 
@@ -442,6 +459,11 @@ class FusedPath:
         w, g, h16 = self.blocks[(l, s)]
         B, T, M = ctx["B"], st["T"], st["M"]
         p, seed = ctx["p"], ctx["seed"]
+        if ctx["f32"]:       # fp32 mode: transposed fp32 masters (dgrad operands), split into bf16x3 by ops.gemm
+            wT = {k: getattr(w, k).t().contiguous() for k in ("w2", "w1")}
+            wT["qkv"] = w.wqkv.t().contiguous()
+        else:
+            wT = {k: self.wT[(l, s, k)] for k in ("w2", "w1", "qkv")}
         gy = st["g_y"].view(M, D)
         if p > 0:
             ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2, seed_dev=ctx["seed_dev"])
@@ -450,17 +472,17 @@ class FusedPath:
             gyd = gy
         scale = 1.0 / (1.0 - p) if p > 0 else 1.0
         # FFN2: y = h + drop2(a W2^T + b2)
-        ops.gemm(gyd, self.wT[(l, s, "w2")], out=st["g_a"], gate=st["a"][l], alpha=scale)
+        ops.gemm(gyd, wT["w2"], out=st["g_a"], gate=st["a"][l], alpha=scale)
         ops.gemm_wgrad(gyd, st["a"][l], g.w2, dbias=g.b2)     # bias gradient = column sums, fused into the wgrad kernel
         # FFN1: a = drop1(relu(hn W1^T + b1))
-        ops.gemm(st["g_a"], self.wT[(l, s, "w1")], out=st["g_hn"])
+        ops.gemm(st["g_a"], wT["w1"], out=st["g_hn"])
         ops.gemm_wgrad(st["g_a"], st["hn"][l], g.w1, dbias=g.b1)
         # LN2 (+ residual): h = x + O
         ops.layernorm_bwd(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b)
         # attention
         ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"],
                      st["dq_acc"], st["g_qkv"])
-        ops.gemm(st["g_qkv"], self.wT[(l, s, "qkv")], out=st["g_xn"])
+        ops.gemm(st["g_qkv"], wT["qkv"], out=st["g_xn"])
         ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
         # LN1 (+ residual)
         ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)

@@ -232,6 +232,8 @@ def graphs_enabled(args, optimizer, scaler=None) -> bool:
     flag = getattr(args, "cuda_graph", None)
     if flag is None:
         flag = os.environ.get("TMP_B200_GRAPH", "1") != "0"
+    if getattr(getattr(optimizer, "fp", None), "precision", "fp16") != "fp16":
+        return False                       # the fp32 parity mode runs eagerly
     return bool(flag) and scaler is None and hasattr(optimizer, "sync_lr")
 
 

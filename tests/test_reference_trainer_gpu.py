@@ -85,8 +85,10 @@ def test_reference_train_step_drives_the_b200_model(name):
     assert torch.equal(batch["input_lengths"], lens_before)                # the model must not mutate the caller's lengths
     moved = [k for k, p in model.named_parameters() if not torch.equal(p.detach(), before[k])]
     dead = [k for k, p in model.named_parameters() if p.grad is None]
-    assert len(moved) > 200 and all(k.startswith("img_encoder.") or "rmse_layer" in k or "prelu" in k or
-                                    "layer_norms_after_concat" in k or f"layer_stacks.{cfg.n_layers - 1}." in k for k in dead)
+    live = [k for k, p in model.named_parameters() if p.grad is not None]
+    assert len(live) > 70 and len(set(live) - set(moved)) <= 3, sorted(set(live) - set(moved))   # AdamW moved what got a gradient
+    assert all(k.startswith("img_encoder.") or "rmse_layer" in k or "prelu" in k or "layer_norms_after_concat" in k or
+               f"layer_stacks.{cfg.n_layers - 1}." in k for k in dead), dead
     # a second step still works (no stale state between calls) and lowers the loss on the same batch
     _, loss2 = _call(tr, args, model, batch, opt, "train", it=8, sched=sched, logger=logger)
     assert np.isfinite(loss2) and loss2 < loss + 0.05
