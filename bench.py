@@ -504,8 +504,10 @@ def dominant_kernel_roofline(a, model, peaks, peak_src, iters=10):
     kv = fp.ctx["kv_len"][0]
     from medical_tri_modal_pilot_b200 import ops
     l = 0
-    run = lambda: ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], kv, B, T, st["lse"][l], st["delta"], st["dq_acc"],
-                               st["g_qkv"])
+    # the call the training step makes: fused protocol (delta and the dQ zeroing come from the LayerNorm backward that
+    # produces dO, tmp_layernorm_bwd_attn), ONE kernel launch. Repeated launches keep adding into the same dQ columns --
+    # irrelevant for the timing.
+    run = lambda: ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], kv, B, T, st["lse"][l], st["delta"], None, st["g_qkv"])
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -519,9 +521,9 @@ def dominant_kernel_roofline(a, model, peaks, peak_src, iters=10):
     lens = kv.float()
     flops = float((10.0 * lens * lens * 64 * 4).sum().item())
     ach = flops / (ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops_sustained"]
+    peak = peaks["bf16_tflops"]          # the kernel is timed alone for a few ms: the burst figure (B200_PROFILING.md)
     traffic, src = profiled_traffic("attn_bwd_kernel") if (a.tie_len == 1000 and a.batch == 64 and not a.realistic) else (None, None)
-    return {"kernel": "attn_bwd_kernel (+delta, dQ convert; vslt stream, one layer)", "bound": "tensor",
+    return {"kernel": "attn_bwd_kernel (vslt stream, one layer; timed alone -> burst peak)", "bound": "tensor",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src,
             "ms_per_launch": ms, "flops_per_launch": flops, "traffic": traffic,
             "traffic_source": (f"profiles/{src}: dram read+write bytes of attn_bwd_kernel, one launch at these shapes"

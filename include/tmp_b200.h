@@ -76,6 +76,12 @@ int tmp_layernorm_fwd(const void* x, const void* add, const float* gamma, const 
 int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows, void* dx,
                       void* dx_drop, float drop_p, uint32_t seed, uint32_t salt, const uint32_t* seed_dev, float* dgamma,
                       float* dbeta, void* stream);
+/* The LayerNorm backward in front of the attention backward (dx is the attention's dO): additionally writes
+ * delta[B,4,T_lse] = per-head sum_d dO.O (attn_O = attention output of the forward) and zeroes the dQ columns [0,256) of
+ * dQKV [rows,768], so that tmp_mma_attn_bwd can run in its fused protocol (dQ_acc == NULL). rows = B*T. */
+int tmp_layernorm_bwd_attn(const void* dy, const void* x, const void* dres, const float* gamma, long long rows, void* dx,
+                           float* dgamma, float* dbeta, const void* attn_O, int T, int T_lse, float* delta, void* dQKV,
+                           void* stream);
 
 /* ---- a10/a11: tcgen05 GEMMs -------------------------------------------------------------------------------
  * out[M,N] = residual + dropout( gate>0 ? act(alpha * A[M,K].B[N,K]^T + bias) : 0 ),  act = relu: 0 none, 1 ReLU, 2 GELU(erf)
@@ -97,14 +103,19 @@ int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt,
 int tmp_colsum(const void* dY, int ld, long long M, int N, float* out, void* stream);
 
 /* ---- a10: modality-aware attention (attention.py:24-49, 65-84) ----------------------------------------------
+ * tmp_mma_attn_bwd protocols: dQ_acc != NULL -> stand-alone (delta computed inside, dQ accumulated in the fp32 workspace
+ * dQ_acc, converted at the end); dQ_acc == NULL -> fused: delta already written and the dQ columns of dQKV already zeroed
+ * by tmp_layernorm_bwd_attn, dQ tiles are reduce-added in fp16 in place.
  * qkv[B*T,768] fp16 = Q|K|V with head h at columns h*64; kv_len[B] (or NULL = unmasked);
  * O[B*T,ld_o] fp16; lse2[B,H,T_lse] fp32 (log2-domain logsumexp of the scaled scores, kept for backward). */
+/* q_rows (both calls): only the leading q_rows query rows of every sample are computed / carry a gradient (rounded up to
+ * whole 128-row tiles; pass T for all). The last fused layer under --mbt-only-vslt 1 only consumes the CLS row. */
 int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, int T, int H, void* O, int ld_o, float* lse2,
-                     int T_lse, void* stream);
+                     int T_lse, int q_rows, void* stream);
 /* qkv, O, dO fp16; delta[B,H,T_lse] and dQ_acc[B*T,256] fp32 are workspaces; dQKV[B*T,768] fp16 receives
  * dQ|dK|dV. T_lse % 128 == 0. */
 int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B, int T, int H,
-                     const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV, void* stream);
+                     const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV, int q_rows, void* stream);
 
 /* ---- a7: bottleneck exchange (mbt_encoder.py:764-776), in place on rows 0..3 of Y_m[B,T_m,256]
  * (fp16) ---------------------------------------------------------------------------------------------------- */

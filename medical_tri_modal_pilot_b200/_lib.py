@@ -28,12 +28,13 @@ SIGNATURES = {
                                 _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tmp_layernorm_fwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
     "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
+    "tmp_layernorm_bwd_attn": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "tmp_gemm_bias_act_fwd": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _i, _vp, _i, _i, _f, _u32,
                               _u32, _vp, _vp, _i, _vp, _i, _vp],
     "tmp_gemm_wgrad": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
-    "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
-    "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
+    "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "tmp_bottleneck_mix_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
@@ -89,7 +90,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (tmp_mma_attn_bwd = delta + main + dQ convert); bench.py reports the total
-_KERNELS_PER_CALL = {"tmp_mma_attn_bwd": 3, "tmp_attn_bwd_f32": 2}
+_KERNELS_PER_CALL = {"tmp_mma_attn_bwd(standalone)": 3, "tmp_attn_bwd_f32": 2}
 launch_count = 0
 
 

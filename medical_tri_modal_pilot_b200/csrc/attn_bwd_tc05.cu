@@ -84,10 +84,13 @@ struct Bars {
 // are set up once, and the Q/dO ring (its own producer warp) runs ahead into the next item while this one drains.
 // All roles enumerate the same item sequence; ring stages and barrier phases follow running counters (gq = query tiles
 // processed so far, it = live items so far).
+// DQ16: dQ tiles are reduce-added in fp16 straight into the dQ columns of dQKV (pre-zeroed by the caller, see
+// tmp_layernorm_bwd_attn) instead of into an fp32 accumulator that needs a memset before and a convert pass after.
+template <bool DQ16>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
-                const int32_t* __restrict__ kv_len, int T, int n_jt, int H,
+                const int32_t* __restrict__ kv_len, int T, int n_jt, int H, int q_tiles_max,
                 int n_items, const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
                 uint16_t* __restrict__ dQKV, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -141,7 +144,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     w.b = t / H;
     w.k0 = w.jt * BT;
     w.len = kv_len ? min(__ldg(kv_len + w.b), T) : T;
-    w.n_q = (w.len + BT - 1) / BT;   // live query tiles (query rows >= len are padding: dO == 0)
+    w.n_q = min((w.len + BT - 1) / BT, q_tiles_max);   // live query tiles (rows >= len are padding: dO == 0; rows past
+                                                       // q_tiles_max tiles carry no gradient by the caller's contract)
     w.row_base = w.b * T;
     return w;
   };
@@ -318,9 +322,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_store_wait_read0();   // previous reduce / store of this warp has finished reading the staging box (every lane
                                   // waits: bulk groups are per thread, lanes without any return at once)
         __syncwarp();
+        if (DQ16) {
+          // fp16 box [32 rows x 32 cols], 64B swizzle (dense 64 B rows): chunk q of row `lane` at lane*64 + ((q ^ ((lane>>1)&3))<<4)
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(sDQ + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack_f16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])),
+                           pack_f16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
+                           pack_f16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
+                           pack_f16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(sDQ + sw128_offset(lane, q)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -509,16 +524,28 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dQ_acc, uin
 
 // qkv [B*T,768] and O [B*T,ld] fp16 (forward quantities), dO [B*T,ld] fp16 (scaled gradient); lse2 from the forward; delta [B,H,T_lse] and dQ_acc [B*T,256] fp32 are
 // workspaces (dQ_acc is zeroed here); dQKV [B*T,768] fp16 receives dQ|dK|dV.
+// Two protocols:
+//  * dQ_acc != NULL (stand-alone): delta is computed here, dQ is accumulated in the fp32 workspace dQ_acc (zeroed here)
+//    and converted to fp16 at the end -- three extra passes over [B*T, 256] tensors;
+//  * dQ_acc == NULL (fused, what the training step uses): the caller has ALREADY written delta and zeroed the dQ columns
+//    of dQKV (tmp_layernorm_bwd_attn does both while it produces dO); dQ tiles are reduce-added in fp16 in place.
+// q_rows: only the leading q_rows query rows of every sample carry a gradient (rounded up to whole tiles; T = all): the
+// query sweep of every key tile stops there (the last layer of `--mbt-only-vslt 1`: only the CLS row has dO != 0).
 extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B,
                                 int T, int H, const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV,
-                                void* stream) {
-  TMP_REQUIRE(qkv && O && dO && lse2 && delta && dQ_acc && dQKV, "attn_bwd: null operand");
+                                int q_rows, void* stream) {
+  TMP_REQUIRE(q_rows > 0 && q_rows <= T, "attn_bwd: q_rows must be in [1, T]");
+  const int q_tiles_max = (q_rows + BT - 1) / BT;
+  TMP_REQUIRE(qkv && O && dO && lse2 && delta && dQKV, "attn_bwd: null operand");
   TMP_REQUIRE(B > 0 && T > 0 && H == 4 && ld == 256, "attn_bwd: need H==4, ld==256 (B=%d T=%d H=%d ld=%d)", B, T, H, ld);
   TMP_REQUIRE(T_lse % BT == 0 && T_lse >= T, "attn_bwd: T_lse must be a multiple of 128 and >= T");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fused = dQ_acc == nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
       tmp::set_error("cudaFuncSetAttribute(attn_bwd): %s", cudaGetErrorString(e));
       return (int)e;
@@ -532,26 +559,34 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmDKV, dQKV, 768, (uint64_t)B * T, 768 * 2, 64, 32);   // dK / dV boxes [32 rows x 64 cols]
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_f32(&tmDQ, dQ_acc, 256, (uint64_t)B * T, 256 * 4, 32, 32);   // reduce-add boxes [32 rows x 32 fp32]
+  if (fused)   // fp16 reduce-add boxes [32 rows x 32 cols] into dQKV[:, 0:256]
+    rc = tmp::encode_tmap_2d_f16_sw64(&tmDQ, dQKV, 256, (uint64_t)B * T, 768 * 2, 32, 32);
+  else         // fp32 reduce-add boxes [32 rows x 32 fp32]
+    rc = tmp::encode_tmap_2d_f32(&tmDQ, dQ_acc, 256, (uint64_t)B * T, 256 * 4, 32, 32);
   if (rc) return rc;
-  {
+  if (!fused) {
     const int rows = B * T_lse;
     attn_bwd_delta_kernel<<<(rows + 7) / 8, 256, 0, st>>>((const uint16_t*)O, (const uint16_t*)dO, ld, B, T, H, delta, T_lse);
     rc = tmp::check_launch("attn_bwd_delta_kernel");
     if (rc) return rc;
-  }
-  cudaError_t e = cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
-  if (e != cudaSuccess) {
-    tmp::set_error("attn_bwd memset: %s", cudaGetErrorString(e));
-    return (int)e;
+    cudaError_t e = cudaMemsetAsync(dQ_acc, 0, (size_t)B * T * 256 * sizeof(float), st);
+    if (e != cudaSuccess) {
+      tmp::set_error("attn_bwd memset: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
   }
   const int n_jt = (T + BT - 1) / BT;
   const int n_items = n_jt * H * B;
   const int sms = tmp::num_sms();
-  attn_bwd_kernel<<<n_items < sms ? n_items : sms, kThreads, kSmemTotal, st>>>(
-      tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, n_items, lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
+  const int grid = n_items < sms ? n_items : sms;
+  if (fused)
+    attn_bwd_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, q_tiles_max, n_items,
+                                                              lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
+  else
+    attn_bwd_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, q_tiles_max, n_items,
+                                                               lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
   rc = tmp::check_launch("attn_bwd_kernel");
-  if (rc) return rc;
+  if (rc || fused) return rc;
   const size_t rows = (size_t)B * T;
   attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (uint16_t*)dQKV, rows);
   return tmp::check_launch("attn_bwd_dq_convert_kernel");

@@ -318,11 +318,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 // qkv: [B*T, 768] bf16.  kv_len: [B] int32 or NULL (= unmasked, reference `mask=None`).
 // O: [B*T, ld_o] bf16 (head h at columns h*64).  lse2: [B, H, T_lse] fp32, log2-domain logsumexp of the scaled scores.
+// q_rows: only the leading q_rows query rows of every sample are computed (rounded up to whole 128-row tiles; T = all).
+// The last fused layer of `--mbt-only-vslt 1` only consumes the CLS row (row 4): its O / lse rows past the first tile are
+// never read, so they are not produced.
 extern "C" int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, int T, int H, void* O, int ld_o,
-                                float* lse2, int T_lse, void* stream) {
+                                float* lse2, int T_lse, int q_rows, void* stream) {
   TMP_REQUIRE(qkv && O && lse2, "attn_fwd: null operand");
   TMP_REQUIRE(B > 0 && T > 0 && H == 4, "attn_fwd: need B>0,T>0,H==4 (B=%d T=%d H=%d)", B, T, H);
   TMP_REQUIRE(T_lse >= T && ld_o % 8 == 0, "attn_fwd: T_lse >= T and ld_o %% 8 == 0 required");
+  TMP_REQUIRE(q_rows > 0 && q_rows <= T, "attn_fwd: q_rows must be in [1, T]");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
@@ -337,7 +341,7 @@ extern "C" int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, i
   if (rc) return rc;
   rc = tmp::encode_tmap_2d_bf16(&tmO, O, (uint64_t)ld_o, (uint64_t)B * T, (uint64_t)ld_o * 2, 64, 32);   // O boxes [32 rows x 64 cols]
   if (rc) return rc;
-  dim3 grid((T + BQ - 1) / BQ, H, B);
+  dim3 grid((q_rows + BQ - 1) / BQ, H, B);
   const float scale_log2 = kLog2e / 8.0f;  // 1/sqrt(d_head=64) in log2 units (attention.py:16,35)
   attn_fwd_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(tm, tmO, kv_len, T, ld_o, (uint16_t*)O, lse2, T_lse,
                                                                           scale_log2);

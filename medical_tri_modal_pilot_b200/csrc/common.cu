@@ -43,6 +43,12 @@ int encode_tmap_2d_bf16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner
   return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer,
                         CU_TENSOR_MAP_SWIZZLE_64B);
 }
+// IEEE fp16 element type (matters for TMA reduce-add, where the copy engine does arithmetic on the elements), 64B swizzle
+int encode_tmap_2d_f16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                            uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer,
+                        CU_TENSOR_MAP_SWIZZLE_64B);
+}
 int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                        uint32_t box_inner, uint32_t box_outer) {
   return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer);
@@ -84,4 +90,4 @@ int num_sms() {
 }  // namespace tmp
 
 extern "C" const char* tmp_last_error(void) { return tmp::g_err; }
-extern "C" int tmp_abi_version(void) { return 2; }   // 2: seed_dev words, tmp_adamw_step_dev
+extern "C" int tmp_abi_version(void) { return 3; }   // 3: q_rows of the attention calls, fused attn_bwd protocol, fp32 mode

@@ -24,6 +24,10 @@ int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uin
 int encode_tmap_2d_bf16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                              uint32_t box_inner, uint32_t box_outer);
 
+// IEEE fp16 elements (element type matters for TMA reduce-add), 64B swizzle, box_inner = 32
+int encode_tmap_2d_f16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                            uint32_t box_inner, uint32_t box_outer);
+
 // fp32 elements, 128B swizzle (box_inner <= 32 floats): used for TMA reduce-add of fp32 accumulators.
 int encode_tmap_2d_f32(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                        uint32_t box_inner, uint32_t box_outer);

@@ -105,7 +105,18 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restri
 
 // dx = dres + LN'(dy; x).  Optionally also writes dx_drop = dropout_mask(seed,salt) * dx / (1-p)
 // (the gradient entering the previous block's FFN2 when its output dropout is active).
-template <int ST>
+// ATTN (the LayerNorm in front of the FFN, whose input gradient dx IS the attention's dO): the same pass also produces
+// what the attention backward needs before it can start -- delta[b,h,q] = sum_d dO.O per head (8 lanes x 8 channels = one
+// head) and zeroed dQ columns of dQKV (the kernel reduce-adds its dQ tiles there) -- instead of a delta kernel (reads O and
+// dO again), a memset and an fp32 -> fp16 convert pass.
+struct LnAttnArgs {
+  const void* O;     // [rows, 256] attention output of the forward
+  float* delta;      // [B, 4, T_lse]
+  void* dQKV;        // [rows, 768]: columns [0, 256) are zeroed
+  int T, T_lse;
+};
+
+template <int ST, bool ATTN>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                             const void* __restrict__ dres,
                                                             const float* __restrict__ gamma, long long rows,
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             uint32_t drop_thr16, float drop_scale, uint32_t seed,
                                                             uint32_t salt, const uint32_t* __restrict__ seed_dev,
                                                             float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta) {
+                                                            float* __restrict__ dbeta, LnAttnArgs at_) {
   __shared__ float sAcc[2 * D];
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sAcc[i] = 0.f;
   __syncthreads();
@@ -153,6 +164,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       for (int i = 0; i < 8; ++i) out[i] += a[i];
     }
     st8<ST>(dx, at, out);
+    if (ATTN) {
+      float o[8];
+      ld8<ST>(at_.O, at, o);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(out[i], o[i], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      const long long b = row / at_.T;
+      const int q = (int)(row - b * at_.T);
+      if ((lane & 7) == 0) at_.delta[(b * 4 + (lane >> 3)) * at_.T_lse + q] = acc;
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st8<ST>(at_.dQKV, (size_t)row * 768 + lane * 8, z);
+    }
     if (dx_drop) {
       const uint32_t base = (uint32_t)row * D + lane * 8;
       dropout_apply_run<8>(out, dropout_key(effective_seed(seed, seed_dev), salt), base, drop_thr16, drop_scale);
@@ -421,12 +447,29 @@ static int layernorm_bwd_impl(int st, const void* dy, const void* x, const void*
   if (blocks > 2LL * tmp::num_sms()) blocks = 2LL * tmp::num_sms();
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const LnAttnArgs none{nullptr, nullptr, nullptr, 1, 1};
   if (st == FMT_F32)
-    layernorm_bwd_kernel<FMT_F32><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta);
+    layernorm_bwd_kernel<FMT_F32, false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta, none);
   else
-    layernorm_bwd_kernel<ACT><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta);
+    layernorm_bwd_kernel<ACT, false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        dy, x, dres, gamma, rows, dx, thr ? dx_drop : nullptr, thr, scale, seed, salt, seed_dev, dgamma, dbeta, none);
+  return tmp::check_launch("layernorm_bwd_kernel");
+}
+
+// LayerNorm backward in front of the attention backward (16-bit path): dx (= dO of the attention), plus delta[B,4,T_lse] and
+// zeroed dQ columns of dQKV [rows,768] -- see LnAttnArgs. rows = B*T.
+extern "C" int tmp_layernorm_bwd_attn(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,
+                                      void* dx, float* dgamma, float* dbeta, const void* attn_O, int T, int T_lse,
+                                      float* delta, void* dQKV, void* stream) {
+  TMP_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && attn_O && delta && dQKV && rows >= 0, "layernorm_bwd_attn: bad argument");
+  TMP_REQUIRE(T > 0 && T_lse >= T && rows % T == 0, "layernorm_bwd_attn: rows must be B*T and T_lse >= T");
+  if (rows == 0) return TMP_OK;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 2LL * tmp::num_sms()) blocks = 2LL * tmp::num_sms();
+  const LnAttnArgs a{attn_O, delta, dQKV, T, T_lse};
+  layernorm_bwd_kernel<ACT, true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, dres, gamma, rows, dx, nullptr, 0u, 1.f,
+                                                                                0u, 0u, nullptr, dgamma, dbeta, a);
   return tmp::check_launch("layernorm_bwd_kernel");
 }
 extern "C" int tmp_layernorm_bwd(const void* dy, const void* x, const void* dres, const float* gamma, long long rows,

@@ -183,8 +183,9 @@ class TRI_MBT_VSLTCLS(nn.Module):
         demographic = torch.cat([age.unsqueeze(1), gen.unsqueeze(1)], dim=1).float()
         demo_embedding = self.ie_demo(demographic)
         missing = self.tri_missing_code(missing, B, x.device)
-        img_feats = self.encode_images(img, missing)
-        cls_out = self._fused(x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing)
+        # the frozen image encoder runs INSIDE the fused path, on the img modality's CUDA stream (FusedPath.forward calls
+        # encode_images there), so the vslt / txt streams of layer 0 overlap it
+        cls_out = self._fused(x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing)
         classInput = self.layer_norms_after_concat(cls_out)
         classInput = torch.cat([classInput, demo_embedding], dim=1)
         if "rmse" in getattr(self.args, "auxiliary_loss_type", "none"):
@@ -206,17 +207,25 @@ class TRI_MBT_VSLTCLS(nn.Module):
         m = (missing.to(torch.long) != 0).to(torch.long)
         return 2 + m if self.input_types == "vslt_txt" else 1 + 2 * m
 
-    def encode_images(self, img, missing):
+    def encode_images(self, img, missing=None, ready=None):
         """Frozen image encoder (reference tri_mbt_vsltcls.py:205-209: reshape(-1,1,224,224), torch.no_grad).
-        Returns [B*n_img, 49, 768] fp16 (the A operand of the 768->256 projection GEMM)."""
+        Returns [B*n_img, 49, 768] fp16 (the A operand of the 768->256 projection GEMM). `ready`: optional per-chunk CUDA
+        events of a staged upload (swin_feed.SwinFeed.__call__)."""
         f32 = self._fused.precision == "fp32"
+
+        def wait_all():
+            for ev in (ready or ()):
+                torch.cuda.current_stream().wait_event(ev)
+
         if img.dim() == 3 and img.shape[-1] == 768:      # test hook: pre-computed Swin features
+            wait_all()
             return img.to(torch.float32 if f32 else torch.float16).contiguous()
         if self.multiimages == 1:
             img = img.reshape(-1, 1, 224, 224)
         with torch.no_grad():
             if self.native_swin:
-                return self._swin_feed()(img)                  # sm_100a kernels (swin_feed.py), fp16 [N,49,768]
+                return self._swin_feed()(img, ready=ready)     # sm_100a kernels (swin_feed.py), fp16 [N,49,768]
+            wait_all()
             if self.img_autocast:
                 f = self._img_encoder_bf16()(img.to(torch.bfloat16))
             else:

@@ -124,6 +124,15 @@ def split_bf16x3(src, side_b=False, stack_rows=False):
     return out
 
 
+def layernorm_bwd_attn(dy, x, dres, gamma, dx, dgamma, dbeta, attn_O, T, delta, dQKV):
+    """layernorm_bwd whose dx is the attention's dO: also writes delta [B,4,T_lse] and zeroes dQKV[:, :256] (the fused
+    protocol of attn_bwd, dQ_acc=None)."""
+    rows = x.numel() // D
+    check(_lib.load().tmp_layernorm_bwd_attn(ptr(dy), ptr(x), ptr(dres), ptr(gamma), rows, ptr(dx), ptr(dgamma),
+                                             ptr(dbeta), ptr(attn_O), T, delta.shape[-1], ptr(delta), ptr(dQKV),
+                                             stream_ptr()), "tmp_layernorm_bwd_attn")
+
+
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
          salt=0, M=None, seed_dev=None):
     """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16.
@@ -175,21 +184,22 @@ def colsum(dY, out, M=None):
     check(fn(ptr(dY), N, M, N, ptr(out), stream_ptr()), "tmp_colsum")
 
 
-def attn_fwd(qkv, kv_len, B, T, O, lse2):
+def attn_fwd(qkv, kv_len, B, T, O, lse2, q_rows=None):
     if _f32(qkv):      # fp32 mode: CUDA-core fp32 attention (csrc/precise.cu)
         return check(_lib.load().tmp_attn_fwd_f32(ptr(qkv), ptr(kv_len), B, T, H, ptr(O), O.shape[-1], ptr(lse2),
                                                   lse2.shape[-1], stream_ptr()), "tmp_attn_fwd_f32")
     check(_lib.load().tmp_mma_attn_fwd(ptr(qkv), ptr(kv_len), B, T, H, ptr(O), O.shape[-1], ptr(lse2), lse2.shape[-1],
-                                       stream_ptr()), "tmp_mma_attn_fwd")
+                                       T if q_rows is None else q_rows, stream_ptr()), "tmp_mma_attn_fwd")
 
 
-def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV):
+def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV, q_rows=None):
     if _f32(qkv):
         return check(_lib.load().tmp_attn_bwd_f32(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),
                                                   lse2.shape[-1], ptr(delta), ptr(dQKV), stream_ptr()), "tmp_attn_bwd_f32")
     check(_lib.load().tmp_mma_attn_bwd(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),
-                                       lse2.shape[-1], ptr(delta), ptr(dQ_acc), ptr(dQKV), stream_ptr()),
-          "tmp_mma_attn_bwd")
+                                       lse2.shape[-1], ptr(delta), ptr(dQ_acc), ptr(dQKV),
+                                       T if q_rows is None else q_rows, stream_ptr()),
+          "tmp_mma_attn_bwd" if dQ_acc is None else "tmp_mma_attn_bwd(standalone)")
 
 
 def bottleneck_mix_fwd(Yv, Yi, Yt, missing):

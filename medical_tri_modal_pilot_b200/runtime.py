@@ -66,6 +66,12 @@ class FusedPath:
         # logits within 1e-3 of the reference and every parameter gradient cosine >= 0.999 end to end. Chosen by
         # `args.precision` / env TMP_B200_PRECISION (model.py); ~10x slower, for validation not throughput.
         self.precision = "fp16"
+        self.input_ready = None   # set by trainer.GraphedStep around a step whose inputs are still being uploaded
+        # last fused layer under --mbt-only-vslt 1: only the vslt CLS row of its output reaches the classifier
+        # (mbt_encoder.py:757-763, tri_mbt_vsltcls.py:248), so the rows the reference computes and then drops are not
+        # computed here: attention for the first query tile only, LayerNorm2 / FFN on the B CLS rows, and the mirror image
+        # in the backward (exact: those rows have no consumer and receive no gradient). False = the reference's full layer.
+        self.cls_only = os.environ.get("TMP_B200_FULL_LAST_LAYER", "0") != "1"
         self.seed_base = None     # dropout seed = seed_base + step_dev (device int32 counter, see forward)
         self.step_dev = None
 
@@ -214,8 +220,14 @@ class FusedPath:
                 # backward scratch (reused by every layer of the stream)
                 "g_y": g(B, T[s], D), "g_x": g(B, T[s], D), "g_yd": g(B, T[s], D), "g_a": g(M, FF), "g_hn": g(M, D),
                 "g_h": g(M, D), "g_qkv": g(M, 768), "g_xn": g(M, D),
-                "dq_acc": e(M, D, dt=torch.float32), "delta": e(B, 4, Tl, dt=torch.float32),
+                # delta rows in [T, Tl) are never written and must stay finite (they meet masked, exactly-zero P entries)
+                "delta": torch.zeros(B, 4, Tl, dtype=torch.float32, device=dev),
             }
+            if s == 0:
+                # compact CLS-row buffers of the last fused layer (--mbt-only-vslt 1: only the vslt CLS row of its output
+                # is consumed, so its LayerNorm2 / FFN run on B rows instead of B*T, see _layer_fwd_cls)
+                st.update({"c_x": e(B, D), "c_o": e(B, D), "c_h": e(B, D), "c_hn": e(B, D), "c_a": e(B, FF), "c_y": e(B, D),
+                           "c_gy": g(B, D), "c_gyd": g(B, D), "c_ga": g(B, FF), "c_ghn": g(B, D), "c_gh": g(B, D)})
             ws.append(st)
         self.ws = ws
         self.proj = [None, torch.empty(B * 49 * n_img, D, dtype=ACT, device=dev),
@@ -231,10 +243,11 @@ class FusedPath:
         return (self._ws_cur, getattr(self, "ctx", None))
 
     # ------------------------------------------------------------------------------------------------------------
-    def __call__(self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing):
+    def __call__(self, x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing):
+        """img: raw pixels [B,(n_img,)1,224,224] (encoded here, on the img lane, by model.encode_images) or precomputed
+        encoder features [B*n_img,49,768] (tests)."""
         self._ensure_params(x.device)
-        return _FusedFn.apply(self._trigger, self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time,
-                              missing)
+        return _FusedFn.apply(self._trigger, self, x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing)
 
     # ------------------------------------------------------------------------------------------------------------
     def _branch(self, prefix, grads=False):
@@ -259,9 +272,15 @@ class FusedPath:
         return dict(kind=1, B=B, n=n, x=None, val4=None, proj=self.proj[s], times=times,
                     n_slots=(ctx["n_img"] if s == 1 else 1), feat_id=(18 if s == 1 else 19), **common)
 
-    def forward(self, x, input_lengths, txts, txt_lengths, img_feats, img_time, txt_time, missing, training):
+    def forward(self, x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing, training):
         m = self.model
         B, L = x.shape[0], x.shape[1]
+        # staged upload (trainer.GraphedStep.load): events that fire when the small tensors / the text embeddings / each
+        # chunk of pixels have landed in their device buffers; None = everything is already resident
+        ready = self.input_ready or {}
+        cur = torch.cuda.current_stream()
+        if "small" in ready:
+            cur.wait_event(ready["small"])
         n_img = 3 if m.multiimages == 1 else 1
         self._ensure_workspace(B, L, n_img)
         NL = m.num_layers
@@ -295,16 +314,20 @@ class FusedPath:
             ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
         # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
         adt = torch.float32 if f32 else ACT
-        ctx["txts16"] = txts.reshape(B * 128, 768).to(adt).contiguous()
-        ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(adt).contiguous()
         Wop = self.W if f32 else self.H16       # GEMM weight operand: fp32 master (split in ops.gemm) or the fp16 copy
         # The three modality streams of a layer are independent until the bottleneck exchange (mbt_encoder.py:744-776):
-        # vslt runs on the caller's stream, img / txt on two side streams, joined at every exchange.
+        # vslt runs on the caller's stream, img / txt on two side streams, joined at every exchange. The frozen image
+        # encoder runs at the head of the img lane.
         self._fork()
         with self._lane(1):
+            img_feats = m.encode_images(img, ready=ready.get("img"))
+            ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(adt).contiguous()
             ops.gemm(ctx["img16"], Wop("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[1]["X"][0], **self._prologue_args(1, ctx))
         with self._lane(2):
+            if "txt" in ready:
+                torch.cuda.current_stream().wait_event(ready["txt"])
+            ctx["txts16"] = txts.reshape(B * 128, 768).to(adt).contiguous()
             ops.gemm(ctx["txts16"], Wop("txt_embedding.weight", D, 768), out=self.proj[2],
                      bias=self.W("txt_embedding.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[2]["X"][0], **self._prologue_args(2, ctx))
@@ -315,7 +338,10 @@ class FusedPath:
                 for s in (1, 2):
                     with self._lane(s):
                         self._layer_fwd(l, s, ctx)
-            self._layer_fwd(l, 0, ctx)
+            if last and self.cls_only and not f32:
+                self._layer_fwd_cls(l, ctx)
+            else:
+                self._layer_fwd(l, 0, ctx)
             self._join()
             if l == NL - 1:
                 break
@@ -377,6 +403,55 @@ class FusedPath:
         ops.gemm(st["a"][l], h16.w2, out=st["X"][l + 1].view(M, D), bias=w.b2, residual=st["h"][l], drop_p=p,
                  seed=seed, salt=(l * 3 + s) * 4 + 2, seed_dev=sd)
 
+    def _layer_fwd_cls(self, l, ctx):
+        """The last fused layer of the vslt stream when only its CLS row is consumed (see `cls_only`)."""
+        st = self.ws[0]
+        w, _, h16 = self.blocks[(l, 0)]
+        B, T, M = ctx["B"], st["T"], st["M"]
+        p, seed, sd = ctx["p"], ctx["seed"], ctx["seed_dev"]
+        x = st["X"][l]
+        ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, st["xn"][l])                       # K and V need every row
+        ops.gemm(st["xn"][l], h16.wqkv, out=st["qkv"][l], bias=w.bqkv)
+        ops.attn_fwd(st["qkv"][l], ctx["kv_len"][0], B, T, st["O"][l], st["lse"][l], q_rows=5)   # first query tile only
+        st["c_x"].copy_(x[:, 4, :])
+        st["c_o"].copy_(st["O"][l].view(B, T, D)[:, 4, :])
+        ops.layernorm_fwd(st["c_x"], w.ln2_g, w.ln2_b, st["c_hn"], add=st["c_o"], sum_out=st["c_h"])
+        ops.gemm(st["c_hn"], h16.w1, out=st["c_a"], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3) * 4 + 1,
+                 seed_dev=sd)
+        ops.gemm(st["c_a"], h16.w2, out=st["c_y"], bias=w.b2, residual=st["c_h"], drop_p=p, seed=seed,
+                 salt=(l * 3) * 4 + 2, seed_dev=sd)
+        st["X"][l + 1][:, 4, :] = st["c_y"]
+
+    def _layer_bwd_cls(self, l, d_cls, ctx):
+        st = self.ws[0]
+        w, g, h16 = self.blocks[(l, 0)]
+        B, T, M = ctx["B"], st["T"], st["M"]
+        p, seed = ctx["p"], ctx["seed"]
+        st["c_gy"].copy_(d_cls * ctx["gscale"])
+        if p > 0:
+            ops.dropout_apply(st["c_gy"], st["c_gyd"], p, seed, (l * 3) * 4 + 2, seed_dev=ctx["seed_dev"])
+            gyd = st["c_gyd"]
+        else:
+            gyd = st["c_gy"]
+        scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+        ops.gemm(gyd, self.wT[(l, 0, "w2")], out=st["c_ga"], gate=st["c_a"], alpha=scale)
+        ops.gemm_wgrad(gyd, st["c_a"], g.w2, dbias=g.b2)
+        ops.gemm(st["c_ga"], self.wT[(l, 0, "w1")], out=st["c_ghn"])
+        ops.gemm_wgrad(st["c_ga"], st["c_hn"], g.w1, dbias=g.b1)
+        ops.layernorm_bwd(st["c_ghn"], st["c_h"], st["c_gy"], w.ln2_g, st["c_gh"], g.ln2_g, g.ln2_b)
+        # the attention's dO / delta / dQ are zero everywhere but in the CLS rows
+        st["g_h"].zero_()
+        st["g_h"].view(B, T, D)[:, 4, :] = st["c_gh"]
+        st["delta"].zero_()
+        st["delta"][:, :, 4] = (st["c_gh"].float().view(B, 4, 64) * st["c_o"].float().view(B, 4, 64)).sum(-1)
+        st["g_qkv"][:, :D].zero_()
+        ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][0], B, T, st["lse"][l], st["delta"], None,
+                     st["g_qkv"], q_rows=5)
+        ops.gemm(st["g_qkv"], self.wT[(l, 0, "qkv")], out=st["g_xn"])
+        ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
+        ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
+        st["g_y"], st["g_x"] = st["g_x"], st["g_y"]
+
     # ------------------------------------------------------------------------------------------------------------
     def backward(self, d_cls, token=None):
         m = self.model
@@ -397,11 +472,15 @@ class FusedPath:
         NL = m.num_layers
         B, p, seed = ctx["B"], ctx["p"], ctx["seed"]
         self.flat_g.zero_()
-        for s in range(3):
-            self.ws[s]["g_y"].zero_()
         gscale = 1.0 if ctx["f32"] else self.grad_scale      # fp32 gradients need no scale
         ctx["gscale"] = gscale
-        self.ws[0]["g_y"][:, 4, :] = (d_cls * gscale).to(self.ws[0]["g_y"].dtype)
+        cls_last = m.vsltonly == 1 and self.cls_only and not ctx["f32"]
+        for s in range(3):
+            if s == 0 and cls_last:
+                continue                 # the CLS-only last layer takes dL/dCLS directly and overwrites g_y
+            self.ws[s]["g_y"].zero_()
+        if not cls_last:
+            self.ws[0]["g_y"][:, 4, :] = (d_cls * gscale).to(self.ws[0]["g_y"].dtype)
         for l in range(NL - 1, -1, -1):
             last = m.vsltonly == 1 and l == NL - 1
             if not last:
@@ -409,7 +488,10 @@ class FusedPath:
                 for s in (1, 2):
                     with self._lane(s):
                         self._layer_bwd(l, s, ctx)
-            self._layer_bwd(l, 0, ctx)
+            if last and cls_last:
+                self._layer_bwd_cls(l, d_cls, ctx)
+            else:
+                self._layer_bwd(l, 0, ctx)
             if not last:
                 self._join()
             if self.debug_trace is not None:       # tools/gpu_grad_trace.py: dL/dX[l] per stream (scaled fp16)
@@ -478,10 +560,16 @@ class FusedPath:
         ops.gemm(st["g_a"], wT["w1"], out=st["g_hn"])
         ops.gemm_wgrad(st["g_a"], st["hn"][l], g.w1, dbias=g.b1)
         # LN2 (+ residual): h = x + O
-        ops.layernorm_bwd(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b)
-        # attention
-        ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"],
-                     st["dq_acc"], st["g_qkv"])
+        if ctx["f32"]:
+            ops.layernorm_bwd(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b)
+            ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"], None,
+                         st["g_qkv"])
+        else:
+            # g_h is the attention's dO: the same pass writes delta and zeroes the dQ columns (fused attn_bwd protocol)
+            ops.layernorm_bwd_attn(st["g_hn"], st["h"][l], gy, w.ln2_g, st["g_h"], g.ln2_g, g.ln2_b, st["O"][l], T,
+                                   st["delta"], st["g_qkv"])
+            ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][s], B, T, st["lse"][l], st["delta"], None,
+                         st["g_qkv"])
         ops.gemm(st["g_qkv"], wT["qkv"], out=st["g_xn"])
         ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
         # LN1 (+ residual)

@@ -74,29 +74,31 @@ class SwinFeed:
                                         w=_pad2(mg.reduction.weight.detach(), Cn, 4 * C)))
         self.norm = dict(g=swin.norm.weight.detach().float().contiguous(), b=swin.norm.bias.detach().float().contiguous())
         self.device = dev
-        self._ws_cache = {}      # n_img -> (ws, out); see _workspace
+        self._ws_cache = {}      # (n_total, n_chunk) -> (ws, out); see _workspace
 
-    def _workspace(self, n_img):
-        """Workspaces are cached per batch size and NEVER freed while anything can still reference them: a captured CUDA
-        graph (trainer.GraphedStep) bakes their raw device pointers and additionally pins the objects (`pin()`); the
-        small LRU only bounds what eager calls with ever-changing shapes can accumulate."""
-        hit = self._ws_cache.pop(n_img, None)
+    def _workspace(self, n_total, n_chunk):
+        """Stage workspaces sized for one CHUNK of images plus the full feature output. Cached per batch size and NEVER
+        freed while anything can still reference them: a captured CUDA graph (trainer.GraphedStep) bakes their raw device
+        pointers and additionally pins the objects (`pin()`); the small LRU only bounds what eager calls with
+        ever-changing shapes can accumulate."""
+        key = (n_total, n_chunk)
+        hit = self._ws_cache.pop(key, None)
         if hit is not None:
-            self._ws_cache[n_img] = hit          # most recently used last
+            self._ws_cache[key] = hit          # most recently used last
             self.ws, self.out = hit
             return self.ws
         dev = self.device
         ws = []
         for (C, heads, H, depth, Cp) in STAGES:
-            M = n_img * H * H
+            M = n_chunk * H * H
             h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
             ws.append(dict(M=M, x=h16(M, Cp), xw=h16(M, Cp), qkv=h16(M, _up(3 * C)),
                            ao=torch.zeros(M, Cp, dtype=torch.float16, device=dev),      # pad columns stay zero
                            y=h16(M, Cp), hn=h16(M, Cp), a=h16(M, 4 * C),
                            mg=h16(M // 4, 4 * C) if H > 7 else None))
-        self.out = torch.empty(n_img * 49, 768, dtype=torch.float16, device=dev)
+        self.out = torch.empty(n_total * 49, 768, dtype=torch.float16, device=dev)
         self.ws = ws
-        self._ws_cache[n_img] = (ws, self.out)
+        self._ws_cache[key] = (ws, self.out)
         while len(self._ws_cache) > 3:
             self._ws_cache.pop(next(iter(self._ws_cache)))
         return ws
@@ -105,12 +107,38 @@ class SwinFeed:
         """The workspace objects of the most recent call (held by a captured graph so they outlive the LRU)."""
         return (self.ws, self.out)
 
+    @staticmethod
+    def n_chunks(n_img):
+        """Large batches are encoded in 3 chunks (every GEMM still has >= 10^5 rows): the host->device upload of chunk c+1
+        then overlaps the encoder of chunk c (trainer.GraphedStep stages the upload per chunk), and the stage workspaces
+        shrink to a third."""
+        import os
+        k = int(os.environ.get("TMP_B200_SWIN_CHUNKS", "3"))     # 1 = whole batch at once (A/B measurements)
+        return k if (k > 1 and n_img >= 32 * k and n_img % k == 0) else 1
+
     @torch.no_grad()
-    def __call__(self, img):
-        """img fp32 [N,1,224,224] (or [N,224,224]) in [0,1] -> features fp16 [N,49,768] = norm(features(img))."""
+    def __call__(self, img, ready=None):
+        """img fp32 [N,1,224,224] (or [N,224,224]) in [0,1] -> features fp16 [N,49,768] = norm(features(img)).
+        ready: optional list of CUDA events, one per chunk (`n_chunks(N)` of them): chunk c is not touched before
+        ready[c] has fired (its pixels are still being uploaded)."""
         n_img = img.numel() // (224 * 224)
-        img = img.reshape(n_img, 224, 224).float().contiguous()
-        ws = self._workspace(n_img)
+        if img.dtype != torch.float32 or not img.is_contiguous():
+            if ready is not None:                       # a cast reads every pixel: all chunks must have landed
+                for ev in ready:
+                    torch.cuda.current_stream().wait_event(ev)
+                ready = None
+            img = img.float().contiguous()
+        img = img.reshape(n_img, 224, 224)
+        k = self.n_chunks(n_img)
+        nc = n_img // k
+        ws = self._workspace(n_img, nc)
+        for c in range(k):
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready[c] if len(ready) == k else ready[-1])
+            self._encode(img[c * nc:(c + 1) * nc], nc, ws, self.out[c * nc * 49:(c + 1) * nc * 49])
+        return self.out.view(n_img, 49, 768)
+
+    def _encode(self, img, n_img, ws, out):
         e = self.embed
         ops.swin_patch_embed_ln(img, e["Wt"], e["b"], e["g"], e["be"], ws[0]["x"], STAGES[0][4])
         for si, (C, heads, H, depth, Cp) in enumerate(STAGES):
@@ -128,5 +156,4 @@ class SwinFeed:
                 m = self.merges[si]
                 ops.swin_merge_ln(w["x"], m["g"], m["b"], n_img, H, C, Cp, w["mg"])
                 ops.gemm(w["mg"], m["w"], out=ws[si + 1]["x"])
-        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, self.out)
-        return self.out.view(n_img, 49, 768)
+        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, out)

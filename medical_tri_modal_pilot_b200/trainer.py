@@ -167,6 +167,16 @@ class GraphedStep:
         self.device = dev
         self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in raw.items()}
         self.stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        # "external" events: captured as event-wait NODES that refer to the real event (recorded by load() on the copy stream
+        # before every replay), not as capture-internal dependencies
+        from .swin_feed import SwinFeed
+        x_img = raw["x_img"]
+        n_images = x_img.numel() // (224 * 224) if x_img.shape[-1] == 224 else 0
+        k = SwinFeed.n_chunks(n_images) if n_images else 1
+        ev = lambda: torch.cuda.Event(external=True)
+        self.ready = {"small": ev(), "txt": ev(), "img": [ev() for _ in range(k)]}
+        self._loaded = False
         self.graph = None
         self.loss = None
         self.calls = 0
@@ -177,21 +187,64 @@ class GraphedStep:
         return (tuple((k, tuple(v.shape), v.dtype) for k, v in raw.items()), id(optimizer), bool(model.training))
 
     def load(self, raw):
-        """Host (pinned) or device tensors of one batch -> the static input buffers (asynchronous copies)."""
-        for k, v in raw.items():
-            if v.data_ptr() != self.static[k].data_ptr():
-                self.static[k].copy_(v, non_blocking=True)
+        """Host (pinned) or device tensors of one batch -> the static input buffers, as a STAGED asynchronous upload on a
+        copy stream: pixels of image chunk 0, the small tensors, the remaining image chunks, the text embeddings -- each
+        group followed by an event that the captured step waits for exactly where it first touches that data
+        (FusedPath.forward / SwinFeed). The image encoder of chunk c therefore overlaps the upload of everything behind it;
+        only the first chunk (a third of the pixels) is exposed. Reference: 2_train.py:143-169 issues the same copies up
+        front, in the compute stream."""
+        cs = self.copy_stream
+        cs.wait_stream(torch.cuda.current_stream())       # the previous step may still be reading the static buffers
+        img_src, img_dst = raw["x_img"], self.static["x_img"]
+        n_flat = img_dst.numel()
+        k = len(self.ready["img"])
+        bounds = [n_flat * c // k for c in range(k + 1)]
+
+        def put(key):
+            v = raw[key]
+            if v.data_ptr() != self.static[key].data_ptr():
+                self.static[key].copy_(v, non_blocking=True)
+
+        def put_img(c):
+            if img_src.data_ptr() == img_dst.data_ptr():
+                return
+            if img_src.is_contiguous() and img_src.dtype == img_dst.dtype:
+                img_dst.view(-1)[bounds[c]:bounds[c + 1]].copy_(img_src.view(-1)[bounds[c]:bounds[c + 1]], non_blocking=True)
+            elif c == 0:
+                img_dst.copy_(img_src, non_blocking=True)
+
+        with torch.cuda.stream(cs):
+            put_img(0)
+            self.ready["img"][0].record(cs)
+            for key in raw:
+                if key not in ("x_img", "x_txt"):
+                    put(key)
+            self.ready["small"].record(cs)
+            for c in range(1, k):
+                put_img(c)
+                self.ready["img"][c].record(cs)
+            put("x_txt")
+            self.ready["txt"].record(cs)
+        self._loaded = True
 
     def _eager(self):
         s = self.static
-        b = prepare_batch(self.args, self.device, s["train_x"], s["static_x"], s["input_lengths"], s["train_y"], s["x_img"],
-                          s["x_txt"], s["txt_lengths"], (s["img_time"], s["txt_time"]), s["missing"])
-        return train_step(self.args, self.model, self.optimizer, self.criterion, b)
+        fp = self.model._fused
+        fp.input_ready = self.ready
+        try:
+            torch.cuda.current_stream().wait_event(self.ready["small"])
+            b = prepare_batch(self.args, self.device, s["train_x"], s["static_x"], s["input_lengths"], s["train_y"], s["x_img"],
+                              s["x_txt"], s["txt_lengths"], (s["img_time"], s["txt_time"]), s["missing"])
+            return train_step(self.args, self.model, self.optimizer, self.criterion, b)
+        finally:
+            fp.input_ready = None
 
     def step(self, scheduler=None, iteration=0, logger=None):
         """One optimisation step on the batch currently in the static buffers; returns the loss (device tensor)."""
         from . import _lib
         self.calls += 1
+        if not self._loaded:
+            raise RuntimeError("GraphedStep.step() before load(): the static input buffers are empty")
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()
         if self.graph is None:

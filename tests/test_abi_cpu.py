@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in funcs:
         assert hasattr(lib, name), f"{name} declared in include/tmp_b200.h but not exported"
     lib.tmp_abi_version.restype = ctypes.c_int
-    assert lib.tmp_abi_version() == 2
+    assert lib.tmp_abi_version() == 3
 
 
 def test_ctypes_table_matches_header():
@@ -40,7 +40,7 @@ def test_argument_errors_are_reported_not_crashed():
     rc = lib.tmp_gemm_bias_act_fwd(None, 0, 0, None, 0, 0, 1, 1, 1, 1.0, None, 0, None, 0, 0, None, 0, 0, 0.0, 0, 0, None,
                                    None, 0, None, 0, None)
     assert rc < 0 and "null operand" in _lib.last_error()
-    rc = lib.tmp_mma_attn_fwd(1, None, 1, 1, 3, 1, 8, 1, 128, None)
+    rc = lib.tmp_mma_attn_fwd(1, None, 1, 1, 3, 1, 8, 1, 128, 1, None)
     assert rc < 0 and "H==4" in _lib.last_error()
     rc = lib.tmp_adamw_step(1, 1, 1, 1, 6, 0.1, 0.9, 0.999, 1e-8, 0.0, 1, None)
     assert rc < 0

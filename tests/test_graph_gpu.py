@@ -222,3 +222,66 @@ def test_adamw_dev_equals_host_scalars():
         lr_dev.fill_(lr); t_dev.fill_(t)
         ops.adamw_step_dev(w2, g, m2, v2, lr_dev, 0.9, 0.999, 1e-8, 1e-2, t_dev)
     assert (w1 - w2).abs().max().item() < 1e-6
+
+
+def test_staged_upload_feeds_every_replay_with_the_new_batch():
+    """trainer.GraphedStep uploads each batch on a copy stream in stages (pixel chunk 0, small tensors, pixel chunks 1..,
+    text) and the captured graph waits on EXTERNAL events exactly where it first touches each group. The test poisons the
+    static input buffers with NaN before every upload (in the compute stream, which the copy stream waits for): a kernel
+    that read a chunk before its upload had landed would read NaN and the loss would be NaN. Two different pinned-host
+    batches alternate through the user call for 8 steps (2 eager warm-ups, capture, 5 replays); the losses must also equal
+    those of the plain eager step (copies issued in the compute stream)."""
+    import math
+    from builder.models import get_model
+    from builder.trainer import get_trainer
+    from medical_tri_modal_pilot_b200 import synth, trainer
+    from medical_tri_modal_pilot_b200.config import make_args
+    from medical_tri_modal_pilot_b200.optim import FlatAdamW
+    B, L, NL = 32, 200, 2
+
+    def run(cuda_graph):
+        torch.manual_seed(0)
+        args = make_args(transformer_num_layers=NL, multiimages=1, mbt_only_vslt=1, input_types="vslt_img_txt", imgtxt_time=1,
+                         dropout=0.0, batch_size=B, img_pretrain="No")
+        args.device = torch.device("cuda")
+        args.cuda_graph = cuda_graph
+        model = get_model(args)(args).to(args.device).train()
+        opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-6, eps=1e-3)
+        crit = torch.nn.BCEWithLogitsLoss()
+        batches = []
+        for seed in (5, 6):
+            hb = synth.make_batch(B, L, n_img=3, seed=seed, missing_mode="none", with_pixels=True, feats=False)
+            if seed == 6:
+                hb["y"] = 1.0 - hb["y"]               # the two batches are distinguishable by their loss
+            miss = hb["missing"]
+            hb["missing3"] = torch.stack([torch.zeros_like(miss), (miss >= 2).long(), (miss % 2).long()], 1).float()
+            hb["static"] = torch.stack([hb["gen"], hb["age"]], 1)
+            batches.append({k: v.pin_memory() for k, v in hb.items()})
+        orig_load = trainer.GraphedStep.load
+
+        def poisoned_load(self, raw):
+            for k in ("x_img", "x_txt", "train_x"):
+                self.static[k].fill_(float("nan"))
+            return orig_load(self, raw)
+        trainer.GraphedStep.load = poisoned_load
+        try:
+            losses = []
+            for it in range(8):
+                src = batches[it % 2]
+                _, loss = get_trainer(args, it, src["x"], src["static"], src["input_lengths"], src["y"], None, model, None,
+                                      args.device, None, opt, crit, x_txt=src["txts"], x_img=src["img"],
+                                      txt_lengths=src["txt_lengths"], imgtxt_time=(src["img_time"], src["txt_time"]),
+                                      missing=src["missing3"], flow_type="train")
+                losses.append(loss)
+        finally:
+            trainer.GraphedStep.load = orig_load
+        return losses, model
+
+    l_e, _ = run(False)
+    l_g, model = run(True)
+    gs = next(iter(model.__dict__["_graphed_steps"].values()))
+    assert gs.graph is not None and len(gs.ready["img"]) == 3
+    assert all(math.isfinite(v) for v in l_g), l_g
+    assert abs(l_e[0] - l_e[1]) > 1e-2
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) < max(1e-3, 0.02 * abs(a)), (l_e, l_g)

@@ -420,7 +420,7 @@ def case_attn_fwd():
     res = {}
     many = [300, 0, 150, 4, 299, 129, 128, 1] * 5   # 40 samples x 4 heads x 3 tiles = 480 work items (> SM count)
     for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (2, 54, [54, 54]),
-                         (40, 300, many)]:
+                         (40, 300, many), (3, 2005, [2005, 0, 1203]), (2, 2048, [2048, 777]), (2, 4096, [4096, 2500])]:
         qkv = (torch.randn(B * T, 768, device=dev) * 1.5).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
         O = torch.full((B * T, 256), 7.0, device=dev, dtype=ACT)
@@ -443,7 +443,9 @@ def case_attn_bwd():
     # last case: 480 (key tile, head, sample) items on 148 persistent CTAs -- several items per CTA, de-selected
     # samples (kv_len 0), dead and partial key tiles in between
     many = [300, 0, 150, 4, 299, 129, 128, 1] * 5
-    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (40, 300, many)]:
+    # T = 2005 (BASELINE config 4) and S = 2048 / 4096 (config 5) with ragged and zero kv_len are checked too
+    for (B, T, lens) in [(2, 128, [128, 77]), (3, 300, [300, 150, 4]), (2, 1005, [1005, 600]), (40, 300, many),
+                         (3, 2005, [2005, 0, 1203]), (2, 2048, [2048, 777]), (2, 4096, [4096, 2500])]:
         qkv = (torch.randn(B * T, 768, device=dev)).half()
         kv = torch.tensor(lens, device=dev, dtype=torch.int32)
         live = (torch.arange(T, device=dev)[None, :] < kv[:, None])
@@ -463,6 +465,25 @@ def case_attn_bwd():
         res[f"dQ_B{B}_T{T}"] = _err(dQKV[:, :256], g[:, :256])
         res[f"dK_B{B}_T{T}"] = _err(dQKV[:, 256:512], g[:, 256:512])
         res[f"dV_B{B}_T{T}"] = _err(dQKV[:, 512:], g[:, 512:])
+        # fused protocol (what the training step runs): the LayerNorm backward that produces dO also writes delta and
+        # zeroes the dQ columns; the attention kernel reduce-adds its dQ tiles in fp16 in place
+        gam = torch.ones(256, device=dev)
+        xin = torch.randn(B * T, 256, device=dev).half()
+        dy = torch.zeros(B * T, 256, device=dev, dtype=GRD)       # LN'(0) = 0  ->  dx = dres = dO
+        dx = torch.empty(B * T, 256, device=dev, dtype=GRD)
+        dgm = torch.zeros(256, device=dev); dbt = torch.zeros(256, device=dev)
+        delta2 = torch.zeros(B, 4, Tl, device=dev)
+        dQKV2 = torch.full((B * T, 768), 3.0, device=dev, dtype=GRD)
+        ops.layernorm_bwd_attn(dy, xin, dO.view(B * T, 256), gam, dx, dgm, dbt, O, T, delta2, dQKV2)
+        dref = (dO.view(B, T, 4, 64).float() * O.view(B, T, 4, 64).float()).sum(-1).permute(0, 2, 1)
+        res[f"fused_delta_B{B}_T{T}"] = _err(delta2[:, :, :T], dref)
+        res[f"fused_dx_B{B}_T{T}"] = _err(dx, dO.view(B * T, 256))
+        zero_ok = bool((dQKV2[:, :256] == 0).all().item()) and bool((dQKV2[:, 256:] == 3.0).all().item())
+        ops.attn_bwd(qkv, O, dx, kv, B, T, lse, delta2, None, dQKV2)
+        res[f"fused_dQ_B{B}_T{T}"] = _err(dQKV2[:, :256], g[:, :256])
+        res[f"fused_dK_B{B}_T{T}"] = _err(dQKV2[:, 256:512], g[:, 256:512])
+        res[f"fused_dV_B{B}_T{T}"] = _err(dQKV2[:, 512:], g[:, 512:])
+        res[f"fused_zero_B{B}_T{T}"] = {"rel_to_max": 0.0 if zero_ok else 1.0, "finite": True}
     res["ok"] = all(v["rel_to_max"] < 5e-3 and v["finite"] for v in res.values() if isinstance(v, dict))
     return res
 

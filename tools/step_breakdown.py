@@ -77,8 +77,8 @@ def main():
                 dY, X = args_[0], args_[1]
                 label = f"wgrad M={dY.numel() // dY.shape[-1]} N={dY.shape[-1]} K={X.shape[-1]}"
             elif name in ("attn_fwd", "attn_bwd"):
-                label = f"{name} T={args_[3] if name == 'attn_fwd' else args_[5]}"
-            elif name in ("layernorm_fwd", "layernorm_bwd", "colsum", "dropout_apply"):
+                label = f"{name} T={args_[3] if name == 'attn_fwd' else args_[5]}" + (" q_rows=5" if kw.get("q_rows") else "")
+            elif name in ("layernorm_fwd", "layernorm_bwd", "layernorm_bwd_attn", "colsum", "dropout_apply"):
                 t = args_[0]
                 label = f"{name} rows={t.numel() // t.shape[-1]} N={t.shape[-1]}"
             e0.record()
@@ -88,7 +88,7 @@ def main():
             return out
         setattr(ops, name, f)
 
-    for n in ("gemm", "gemm_wgrad", "colsum", "attn_fwd", "attn_bwd", "layernorm_fwd", "layernorm_bwd",
+    for n in ("gemm", "gemm_wgrad", "colsum", "attn_fwd", "attn_bwd", "layernorm_fwd", "layernorm_bwd", "layernorm_bwd_attn",
               "stream_prologue_fwd", "stream_prologue_bwd", "bottleneck_mix_fwd", "bottleneck_mix_bwd", "dropout_apply",
               "cast_weights", "adamw_step", "build_lengths", "swin_patch_embed_ln", "swin_ln_window", "swin_window_attn",
               "swin_unwindow_add_ln", "swin_merge_ln"):
