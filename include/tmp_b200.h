@@ -88,11 +88,15 @@ int tmp_layernorm_bwd_attn(const void* dy, const void* x, const void* dres, cons
  * A, B 16-bit K-major, both fp16 or both bf16 (B = nn.Linear / Conv1d(k=1) weight `[out,in]`: attention.py:68-70,
  * module.py:74-80; dgrad passes the gradient as A and the transposed weight copy as B).
  * N % 128 == 0, K % 64 == 0. Any of bias/gate/residual may be NULL; out16 (in out_fmt) and/or out_f32 get the result.
+ * mask_out (optional, [M, N/32] uint32): bit c%32 of word (row, c/32) = (result before the residual > 0) -- the ReLU /
+ * dropout pattern in one bit per element. A later call passes it back as `gate` with gate_fmt = 3 and ld_gate = N/32
+ * (the FFN2 input gradient) instead of re-reading the 16-bit activation. gate_fmt / res_fmt 2 = fp32 tensors (fp32 mode).
  * A, B and out16 go through TMA: 16-byte aligned base addresses, leading dimensions multiples of 8 elements. */
 int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N, int K,
                           float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
                           const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
-                          const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out, void* stream);
+                          const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out,
+                          uint32_t* mask_out, void* stream);
 /* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X).
  * dbias (optional, may be NULL): dbias[N] fp32 += column sums of dY (the bias gradient), computed from the dY tiles
  * the kernel stages in shared memory anyway -- replaces a separate tmp_colsum pass over dY.

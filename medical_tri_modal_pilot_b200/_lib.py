@@ -30,7 +30,7 @@ SIGNATURES = {
     "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
     "tmp_layernorm_bwd_attn": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "tmp_gemm_bias_act_fwd": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _i, _vp, _i, _i, _f, _u32,
-                              _u32, _vp, _vp, _i, _vp, _i, _vp],
+                              _u32, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "tmp_gemm_wgrad": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
     "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],

@@ -17,6 +17,7 @@ using namespace tc05;
 
 namespace {
 
+constexpr int FMT_MASK = 3;   // gate given as the bit mask written by `mask_out` (uint32 words, ld_gate words per row)
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kEpiWarps = 16;
@@ -42,6 +43,8 @@ struct EpiParams {
   float bias_scale;       // factor on the bias (1/(1-p) when folded, else 1)
   uint32_t drop_seed, drop_salt;   // mask = f(dropout_key(drop_seed + *drop_seed_dev, drop_salt), element index)
   const uint32_t* drop_seed_dev;   // optional device word added to the seed (CUDA-graph replays), or null
+  uint32_t* mask_out;     // optional [M, N/32] bit mask of (result > 0) -- the ReLU/dropout gate of the backward pass in 1 bit per
+                          // element instead of re-reading the 16-bit activation (gate_fmt == FMT_MASK consumes it)
   uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
   float* out_f32;         // [M, ld_out] fp32 (or null) -- direct stores
   int ld_out;
@@ -129,7 +132,12 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_erf_pair(v[j], v[j + 1]);
   }
-  if (p.gate && row_ok && p.gate_fmt == FMT_F32) {   // fp32 mode: the gate tensor is stored in fp32
+  if (p.gate && row_ok && p.gate_fmt == FMT_MASK) {  // 1 bit per element: one 4-byte load per 32-column chunk
+    const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(p.gate) + (size_t)row * p.ld_gate + (col0 >> 5));
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!((m >> j) & 1u)) v[j] = 0.f;
+  } else if (p.gate && row_ok && p.gate_fmt == FMT_F32) {   // fp32 mode: the gate tensor is stored in fp32
     const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.gate) + (size_t)row * p.ld_gate + col0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -159,6 +167,12 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
     const uint32_t idx0 = (uint32_t)row * (uint32_t)p.N + (uint32_t)col0;
     if (p.drop_fold) dropout_zero_run<32>(v, drop_key, idx0, p.drop_thr16);
     else dropout_apply_run<32>(v, drop_key, idx0, p.drop_thr16, p.drop_scale);
+  }
+  if (p.mask_out && row_ok) {     // before the residual: the gate is the ReLU / dropout pattern of this GEMM's own result
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+    p.mask_out[(size_t)row * (p.N >> 5) + (col0 >> 5)] = m;
   }
   if (p.residual && row_ok && p.res_fmt == FMT_F32) {   // fp32 mode: fp32 residual stream
     const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)row * p.ld_res + col0);
@@ -620,17 +634,18 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
                                      int K, float alpha, const float* bias, int relu, const void* gate, int gate_fmt,
                                      int ld_gate, const void* residual, int res_fmt, int ld_res, float drop_p,
                                      uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* out16, int out_fmt,
-                                     float* out_f32, int ld_out, void* stream) {
+                                     float* out_f32, int ld_out, uint32_t* mask_out, void* stream) {
   void* out_bf16 = out16;
   TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
-  TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok32(gate_fmt)) &&
+  TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok32(gate_fmt) || gate_fmt == FMT_MASK) &&
                   (!residual || fmt_ok32(res_fmt)),
               "gemm: operand / output formats must be 0 (fp16) or 1 (bf16); gate / residual may also be 2 (fp32)");
   TMP_REQUIRE(a_fmt == b_fmt, "gemm: tcgen05 kind::f16 needs A and B in the same 16-bit format");
   TMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   TMP_REQUIRE(N % 128 == 0 && K % BK == 0, "gemm: N must be a multiple of 128 and K of 64 (N=%d K=%d)", N, K);
-  TMP_REQUIRE(ld_out % 8 == 0 && (!gate || ld_gate % 8 == 0) && (!residual || ld_res % 8 == 0),
+  TMP_REQUIRE(ld_out % 8 == 0 && (!gate || gate_fmt == FMT_MASK || ld_gate % 8 == 0) && (!residual || ld_res % 8 == 0),
               "gemm: leading dimensions must be multiples of 8");
+  TMP_REQUIRE(!gate || gate_fmt != FMT_MASK || ld_gate == N / 32, "gemm: a bit-mask gate has N/32 words per row");
   TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p out of range");
   const int sms = tmp::num_sms();
   const int m_blks = (M + BM - 1) / BM;
@@ -653,6 +668,7 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   if (p.drop_fold) p.alpha = alpha * p.drop_scale;
   p.drop_seed = seed; p.drop_salt = salt; p.drop_seed_dev = seed_dev;
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
+  p.mask_out = mask_out;
   CUtensorMap tmOut;
   if (out_bf16) {
     // 16-bit output written by TMA: boxes of [32 rows x 32 cols], 64B swizzle; rows >= M are clipped

@@ -134,8 +134,9 @@ def layernorm_bwd_attn(dy, x, dres, gamma, dx, dgamma, dbeta, attn_O, T, delta, 
 
 
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
-         salt=0, M=None, seed_dev=None):
+         salt=0, M=None, seed_dev=None, mask_out=None):
     """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16.
+    mask_out (int32 [M, N/32]): receives the (result > 0) bit pattern; an int32 `gate` is read as such a bit mask.
     fp32 mode (A and Bw fp32): both operands are split into bf16x3 along K and the same tcgen05 kernel accumulates the six
     partial products in fp32; `out` is then an fp32 tensor, gate / residual are fp32."""
     if _f32(A):
@@ -151,13 +152,13 @@ def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residu
     M = A.numel() // K if M is None else M
     N = Bw.shape[0]
     ld_out = (out if out is not None else out_f32).shape[-1]
+    gate_fmt = 3 if (gate is not None and gate.dtype == torch.int32) else _fmt(gate)
     check(_lib.load().tmp_gemm_bias_act_fwd(ptr(A), _fmt(A), A.stride(-2) if A.dim() > 1 else K, ptr(Bw), _fmt(Bw),
                                             Bw.stride(0), M, N, K, float(alpha), ptr(bias), int(relu), ptr(gate),
-                                            _fmt(gate), gate.shape[-1] if gate is not None else 0, ptr(residual),
+                                            gate_fmt, gate.shape[-1] if gate is not None else 0, ptr(residual),
                                             _fmt(residual), residual.shape[-1] if residual is not None else 0,
                                             float(drop_p), seed, salt, ptr(seed_dev), ptr(out), _fmt(out), ptr(out_f32),
-                                            ld_out,
-                                            stream_ptr()),
+                                            ld_out, ptr(mask_out), stream_ptr()),
           "tmp_gemm_bias_act_fwd")
 
 

@@ -216,6 +216,8 @@ class FusedPath:
                 "xn": [e(M, D) for _ in range(nl_s)], "qkv": [e(M, 768) for _ in range(nl_s)],
                 "O": [e(M, D) for _ in range(nl_s)], "h": [e(M, D) for _ in range(nl_s)],
                 "hn": [e(M, D) for _ in range(nl_s)], "a": [e(M, FF) for _ in range(nl_s)],
+                # ReLU / dropout pattern of the FFN hidden activation, 1 bit per element (gate of the FFN2 input gradient)
+                "am": [torch.empty(M, FF // 32, dtype=torch.int32, device=dev) for _ in range(nl_s)],
                 "lse": [e(B, 4, Tl, dt=torch.float32) for _ in range(nl_s)],
                 # backward scratch (reused by every layer of the stream)
                 "g_y": g(B, T[s], D), "g_x": g(B, T[s], D), "g_yd": g(B, T[s], D), "g_a": g(M, FF), "g_hn": g(M, D),
@@ -227,6 +229,7 @@ class FusedPath:
                 # compact CLS-row buffers of the last fused layer (--mbt-only-vslt 1: only the vslt CLS row of its output
                 # is consumed, so its LayerNorm2 / FFN run on B rows instead of B*T, see _layer_fwd_cls)
                 st.update({"c_x": e(B, D), "c_o": e(B, D), "c_h": e(B, D), "c_hn": e(B, D), "c_a": e(B, FF), "c_y": e(B, D),
+                           "c_am": torch.empty(B, FF // 32, dtype=torch.int32, device=dev),
                            "c_gy": g(B, D), "c_gyd": g(B, D), "c_ga": g(B, FF), "c_ghn": g(B, D), "c_gh": g(B, D)})
             ws.append(st)
         self.ws = ws
@@ -399,7 +402,7 @@ class FusedPath:
         ops.attn_fwd(st["qkv"][l], ctx["kv_len"][s], B, T, st["O"][l], st["lse"][l])
         ops.layernorm_fwd(x, w.ln2_g, w.ln2_b, st["hn"][l], add=st["O"][l], sum_out=st["h"][l])
         ops.gemm(st["hn"][l], h16.w1, out=st["a"][l], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3 + s) * 4 + 1,
-                 seed_dev=sd)
+                 seed_dev=sd, mask_out=None if ctx["f32"] else st["am"][l])
         ops.gemm(st["a"][l], h16.w2, out=st["X"][l + 1].view(M, D), bias=w.b2, residual=st["h"][l], drop_p=p,
                  seed=seed, salt=(l * 3 + s) * 4 + 2, seed_dev=sd)
 
@@ -417,7 +420,7 @@ class FusedPath:
         st["c_o"].copy_(st["O"][l].view(B, T, D)[:, 4, :])
         ops.layernorm_fwd(st["c_x"], w.ln2_g, w.ln2_b, st["c_hn"], add=st["c_o"], sum_out=st["c_h"])
         ops.gemm(st["c_hn"], h16.w1, out=st["c_a"], bias=w.b1, relu=True, drop_p=p, seed=seed, salt=(l * 3) * 4 + 1,
-                 seed_dev=sd)
+                 seed_dev=sd, mask_out=st["c_am"])
         ops.gemm(st["c_a"], h16.w2, out=st["c_y"], bias=w.b2, residual=st["c_h"], drop_p=p, seed=seed,
                  salt=(l * 3) * 4 + 2, seed_dev=sd)
         st["X"][l + 1][:, 4, :] = st["c_y"]
@@ -434,7 +437,7 @@ class FusedPath:
         else:
             gyd = st["c_gy"]
         scale = 1.0 / (1.0 - p) if p > 0 else 1.0
-        ops.gemm(gyd, self.wT[(l, 0, "w2")], out=st["c_ga"], gate=st["c_a"], alpha=scale)
+        ops.gemm(gyd, self.wT[(l, 0, "w2")], out=st["c_ga"], gate=st["c_am"], alpha=scale)
         ops.gemm_wgrad(gyd, st["c_a"], g.w2, dbias=g.b2)
         ops.gemm(st["c_ga"], self.wT[(l, 0, "w1")], out=st["c_ghn"])
         ops.gemm_wgrad(st["c_ga"], st["c_hn"], g.w1, dbias=g.b1)
@@ -554,7 +557,7 @@ class FusedPath:
             gyd = gy
         scale = 1.0 / (1.0 - p) if p > 0 else 1.0
         # FFN2: y = h + drop2(a W2^T + b2)
-        ops.gemm(gyd, wT["w2"], out=st["g_a"], gate=st["a"][l], alpha=scale)
+        ops.gemm(gyd, wT["w2"], out=st["g_a"], gate=st["a"][l] if ctx["f32"] else st["am"][l], alpha=scale)
         ops.gemm_wgrad(gyd, st["a"][l], g.w2, dbias=g.b2)     # bias gradient = column sums, fused into the wgrad kernel
         # FFN1: a = drop1(relu(hn W1^T + b1))
         ops.gemm(st["g_a"], wT["w1"], out=st["g_hn"])

@@ -77,9 +77,10 @@ class SwinFeed:
         self._ws_cache = {}      # (n_total, n_chunk) -> (ws, out); see _workspace
 
     def _workspace(self, n_total, n_chunk):
-        """Stage workspaces sized for one CHUNK of images plus the full feature output. Cached per batch size and NEVER
-        freed while anything can still reference them: a captured CUDA graph (trainer.GraphedStep) bakes their raw device
-        pointers and additionally pins the objects (`pin()`); the small LRU only bounds what eager calls with
+        """Stage workspaces: stages 1-2 (the high-resolution stages, >= 10^5 token rows even for a third of the batch) are
+        sized for one CHUNK of images, stages 3-4 and the feature output for the whole batch. Cached per batch size and
+        NEVER freed while anything can still reference them: a captured CUDA graph (trainer.GraphedStep) bakes their raw
+        device pointers and additionally pins the objects (`pin()`); the small LRU only bounds what eager calls with
         ever-changing shapes can accumulate."""
         key = (n_total, n_chunk)
         hit = self._ws_cache.pop(key, None)
@@ -89,8 +90,8 @@ class SwinFeed:
             return self.ws
         dev = self.device
         ws = []
-        for (C, heads, H, depth, Cp) in STAGES:
-            M = n_chunk * H * H
+        for si, (C, heads, H, depth, Cp) in enumerate(STAGES):
+            M = (n_chunk if si < 2 else n_total) * H * H
             h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
             ws.append(dict(M=M, x=h16(M, Cp), xw=h16(M, Cp), qkv=h16(M, _up(3 * C)),
                            ao=torch.zeros(M, Cp, dtype=torch.float16, device=dev),      # pad columns stay zero
@@ -109,9 +110,11 @@ class SwinFeed:
 
     @staticmethod
     def n_chunks(n_img):
-        """Large batches are encoded in 3 chunks (every GEMM still has >= 10^5 rows): the host->device upload of chunk c+1
-        then overlaps the encoder of chunk c (trainer.GraphedStep stages the upload per chunk), and the stage workspaces
-        shrink to a third."""
+        """Large batches run the two high-resolution stages (patch embedding, stages 1-2: 56x56 and 28x28 tokens per image,
+        60 % of the encoder's time) in 3 chunks of images: the host->device upload of chunk c+1 then overlaps the encoder
+        of chunk c (trainer.GraphedStep stages the upload per chunk), and their workspaces shrink to a third. Stages 3-4
+        (14x14 / 7x7 tokens) run on the whole batch: their kernels are too small to split (measured: +0.9 ms per step
+        when all four stages were chunked)."""
         import os
         k = int(os.environ.get("TMP_B200_SWIN_CHUNKS", "3"))     # 1 = whole batch at once (A/B measurements)
         return k if (k > 1 and n_img >= 32 * k and n_img % k == 0) else 1
@@ -132,16 +135,23 @@ class SwinFeed:
         k = self.n_chunks(n_img)
         nc = n_img // k
         ws = self._workspace(n_img, nc)
+        rows3 = nc * 14 * 14                            # stage-3 input rows produced by one chunk
         for c in range(k):
             if ready is not None:
                 torch.cuda.current_stream().wait_event(ready[c] if len(ready) == k else ready[-1])
-            self._encode(img[c * nc:(c + 1) * nc], nc, ws, self.out[c * nc * 49:(c + 1) * nc * 49])
+            self._stages(img[c * nc:(c + 1) * nc], nc, ws, 0, 2, ws[2]["x"][c * rows3:(c + 1) * rows3])
+        self._stages(None, n_img, ws, 2, 4, None)
+        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, self.out)
         return self.out.view(n_img, 49, 768)
 
-    def _encode(self, img, n_img, ws, out):
-        e = self.embed
-        ops.swin_patch_embed_ln(img, e["Wt"], e["b"], e["g"], e["be"], ws[0]["x"], STAGES[0][4])
-        for si, (C, heads, H, depth, Cp) in enumerate(STAGES):
+    def _stages(self, img, n_img, ws, s0, s1, x_next):
+        """Stages [s0, s1) on n_img images. Stage 0 starts from the pixels; the merged output of stage s1-1 goes to `x_next`
+        (a slice of the next stage's input) when s1 < 4."""
+        if s0 == 0:
+            e = self.embed
+            ops.swin_patch_embed_ln(img, e["Wt"], e["b"], e["g"], e["be"], ws[0]["x"], STAGES[0][4])
+        for si in range(s0, s1):
+            C, heads, H, depth, Cp = STAGES[si]
             w = ws[si]
             for b in self.blocks[si]:
                 sh = b["shift"]
@@ -155,5 +165,4 @@ class SwinFeed:
             if si < 3:
                 m = self.merges[si]
                 ops.swin_merge_ln(w["x"], m["g"], m["b"], n_img, H, C, Cp, w["mg"])
-                ops.gemm(w["mg"], m["w"], out=ws[si + 1]["x"])
-        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, out)
+                ops.gemm(w["mg"], m["w"], out=(x_next if si == s1 - 1 and x_next is not None else ws[si + 1]["x"]))

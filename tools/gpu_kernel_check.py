@@ -283,9 +283,25 @@ def case_gemm():
     res["drop_keep"] = kept.float().mean().item()
     res["drop_det"] = bool(torch.equal(o1, o2))
     res["drop_scale"] = _err(o1[kept], (o0.float() / 0.9)[kept])
+    # 1-bit ReLU/dropout gate: the FFN1 epilogue writes (result > 0) as a bit mask, the FFN2 input gradient consumes it
+    mask_ok = True
+    for (M, N, K) in [(300, 1024, 256), (40001, 1024, 256), (64, 1024, 256)]:
+        A = torch.randn(M, K, device=dev).half(); Bw = (torch.randn(N, K, device=dev) / 16).half()
+        bias = torch.randn(N, device=dev)
+        a = torch.empty(M, N, device=dev, dtype=ACT)
+        am = torch.full((M, N // 32), -1, device=dev, dtype=torch.int32)
+        ops.gemm(A, Bw, out=a, bias=bias, relu=True, drop_p=0.1, seed=5, salt=2, mask_out=am)
+        bits = ((am.unsqueeze(-1) >> torch.arange(32, device=dev)) & 1).reshape(M, N).bool()
+        mask_ok = mask_ok and bool(torch.equal(bits, a > 0))
+        G = torch.randn(M, 256, device=dev).half(); Wt = (torch.randn(N, 256, device=dev) / 16).half()
+        g1 = torch.empty(M, N, device=dev, dtype=ACT); g2 = torch.empty_like(g1)
+        ops.gemm(G, Wt, out=g1, gate=a, alpha=1.0 / 0.9)
+        ops.gemm(G, Wt, out=g2, gate=am, alpha=1.0 / 0.9)
+        mask_ok = mask_ok and bool(torch.equal(g1, g2))
+    res["mask_gate_ok"] = mask_ok
     tol = lambda k: 2.5e-3 if k.startswith("fwd") else 1.5e-2
     res["ok"] = all(v["rel_to_max"] < tol(k) and v["finite"] for k, v in res.items() if isinstance(v, dict)) and \
-        abs(res["drop_keep"] - 0.9) < 5e-3 and res["drop_det"]
+        abs(res["drop_keep"] - 0.9) < 5e-3 and res["drop_det"] and mask_ok
     return res
 
 

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--B", type=int, default=64)
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE config 5: attention alone, seq 256..4096, full / ragged / de-selected samples")
+    ap.add_argument("--flush", action="store_true",
+                    help="time every launch separately with an L2 flush (256 MB write) in between: cold-L2 figures for the "
+                         "HBM-bound kernels, as they run inside the step")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_times.json"))
     a = ap.parse_args()
     dev = "cuda"
@@ -63,9 +66,10 @@ def main():
                 f_fwd = float((lens.double() ** 2).sum()) * 4.0 * 64 * 4
                 add(f"sweep_attn_fwd_S{T}_{pat}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, Bs=Bs:
                     ops.attn_fwd(qkv, kv, Bs, T, O, lse), f_fwd, None, f"B={Bs} H=4 S={T} d=64 kv_len={pat}")
+                delta.zero_()
                 add(f"sweep_attn_bwd_S{T}_{pat}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, dO=dO, delta=delta, dq=dq,
-                    dqkv=dqkv, Bs=Bs: ops.attn_bwd(qkv, O, dO, kv, Bs, T, lse, delta, dq, dqkv), 2.5 * f_fwd, None,
-                    f"B={Bs} H=4 S={T} d=64 kv_len={pat}")
+                    dqkv=dqkv, Bs=Bs: ops.attn_bwd(qkv, O, dO, kv, Bs, T, lse, delta, None, dqkv), 2.5 * f_fwd, None,
+                    f"B={Bs} H=4 S={T} d=64 kv_len={pat} (fused protocol: delta / dQ zeroing by the LayerNorm backward)")
     for T in (() if a.sweep else (1005, 2005, 152, 133)):
         M = B * T
         Tl = ops.lse_len(T)
@@ -80,8 +84,13 @@ def main():
         f_fwd = 4.0 * T * T * 64 * 4 * B
         add(f"attn_fwd_T{T}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse: ops.attn_fwd(qkv, kv, B, T, O, lse), f_fwd, None,
             f"B={B} H=4 T={T} d=64")
+        delta.zero_()
         add(f"attn_bwd_T{T}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, dO=dO, delta=delta, dq=dq, dqkv=dqkv:
-            ops.attn_bwd(qkv, O, dO, kv, B, T, lse, delta, dq, dqkv), 2.5 * f_fwd, None, f"B={B} H=4 T={T} d=64")
+            ops.attn_bwd(qkv, O, dO, kv, B, T, lse, delta, None, dqkv), 2.5 * f_fwd, None,
+            f"B={B} H=4 T={T} d=64 (fused protocol, one launch)")
+        add(f"attn_bwd_standalone_T{T}", lambda qkv=qkv, kv=kv, T=T, O=O, lse=lse, dO=dO, delta=delta, dq=dq, dqkv=dqkv:
+            ops.attn_bwd(qkv, O, dO, kv, B, T, lse, delta, dq, dqkv), 2.5 * f_fwd, None,
+            f"B={B} H=4 T={T} d=64 (stand-alone: delta + memset + main + dQ convert)")
         if T == 2005:
             continue
         # GEMMs of one encoder block at this stream length
@@ -112,6 +121,34 @@ def main():
         dx = torch.empty_like(x); dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
         add(f"layernorm_bwd_T{T}", lambda x=x, dx=dx: ops.layernorm_bwd(x, x, x, g, dx, dg, db), None,
             M * 256 * 2 * 4.0, f"rows={M}")
+        # the LayerNorm backward in front of the attention backward: + O read, + dQ columns zeroed, + delta written
+        add(f"layernorm_bwd_attn_T{T}", lambda x=x, dx=dx, O=O, delta=delta, dqkv=dqkv:
+            ops.layernorm_bwd_attn(x, x, x, g, dx, dg, db, O, T, delta, dqkv), None, M * 256 * 2 * 6.0 + B * 4 * T * 4.0,
+            f"rows={M} (x, dy, dres, O read; dx + zeroed dQ written)")
+        # encoder prologue of this stream length as the step runs it: UMSE (T=1005) or projected rows (152 / 133) -> X0
+        n = T - 5
+        X0 = torch.empty(B, T, 256, device=dev, dtype=torch.float16)
+        br = lambda: [torch.randn(256, device=dev), torch.randn(256, device=dev), torch.ones(256, device=dev),
+                      torch.zeros(256, device=dev)]
+        val4, tim4 = br(), br()
+        Wfe = torch.randn(20, 256, device=dev); cls = torch.randn(256, device=dev); bott = torch.randn(4, 256, device=dev)
+        common = dict(tim4=tim4, Wfeat=Wfe, cls=cls, bottlenecks=bott, ln_g=g, ln_b=b, pe=None, drop_p=0.1, seed=3, salt=7)
+        if T == 1005:
+            xv = torch.rand(B, n, 3, device=dev); xv[:, :, 2] = torch.randint(0, 18, (B, n), device=dev).float()
+            pa = dict(kind=0, B=B, n=n, x=xv, val4=val4, proj=None, times=None, n_slots=0, feat_id=0, **common)
+            byt = B * n * 12.0 + B * T * 512.0
+        else:
+            pr = torch.randn(B * n, 256, device=dev).half(); tm = -torch.rand(B, device=dev)
+            pa = dict(kind=1, B=B, n=n, x=None, val4=None, proj=pr, times=tm, n_slots=1, feat_id=19, **common)
+            byt = B * n * 512.0 + B * T * 512.0
+        add(f"stream_prologue_fwd_T{T}", lambda pa=pa, X0=X0: ops.stream_prologue_fwd(X0=X0, **pa), None, byt, f"B={B} n={n}")
+        gX = torch.randn(B, T, 256, device=dev).half()
+        gacc = lambda *s_: torch.zeros(*s_, device=dev)
+        gb = dict(g_val=gacc(4, 256) if T == 1005 else None, g_tim=gacc(4, 256), g_feat=gacc(20, 256), g_cls=gacc(256),
+                  g_bott=gacc(4, 256), g_ln=gacc(2, 256),
+                  dproj=None if T == 1005 else torch.empty(B * n, 256, device=dev, dtype=torch.float16))
+        add(f"stream_prologue_bwd_T{T}", lambda pa=pa, gX=gX, gb=gb: ops.stream_prologue_bwd(dX0=gX, **pa, **gb), None,
+            B * T * 512.0 + (B * n * 12.0 if T == 1005 else 2 * B * n * 512.0), f"B={B} n={n}")
     # UMSE embedding at >= 512k tokens (stable HBM figure), 12 B in + 512 B fp16 out per token
     n_tok = 0 if a.sweep else 1 << 20
     xt = torch.empty(n_tok, 3, device=dev)
@@ -122,10 +159,20 @@ def main():
     v4, t4 = mk(), mk()
     Wf = torch.randn(20, 256, device=dev)
     if not a.sweep:
+      Bbig, nbig = 512, 1019                     # 524 288 rows of T = 1024: the step's prologue kernel at >= 512 k tokens
+      xb = torch.rand(Bbig, nbig, 3, device=dev); xb[:, :, 2] = torch.randint(0, 18, (Bbig, nbig), device=dev).float()
+      X0b = torch.empty(Bbig, nbig + 5, 256, device=dev, dtype=torch.float16)
+      gln, bln = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+      pab = dict(kind=0, B=Bbig, n=nbig, x=xb, val4=v4, proj=None, times=None, n_slots=0, feat_id=0, tim4=t4, Wfeat=Wf,
+                 cls=torch.randn(256, device=dev), bottlenecks=torch.randn(4, 256, device=dev), ln_g=gln, ln_b=bln, pe=None,
+                 drop_p=0.1, seed=3, salt=7)
+      add("stream_prologue_fwd_512k", lambda: ops.stream_prologue_fwd(X0=X0b, **pab), None,
+          Bbig * nbig * 12.0 + Bbig * (nbig + 5) * 512.0, f"B={Bbig} n={nbig} ({Bbig * (nbig + 5)} rows)")
       add("umse_embed_fwd_1M", lambda: ops.umse_embed(xt, v4, t4, Wf, torch.float16), None, n_tok * 524.0,
         f"tokens={n_tok}")
 
     results = []
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if a.flush else None
     for name, fn, flops, bytes_, shape in cases:
         fn()
         if not a.time:
@@ -134,13 +181,23 @@ def main():
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.iters
+        if a.flush:
+            tot = 0.0
+            for _ in range(a.iters):
+                flush_buf.fill_(1)                       # evict the 126 MB L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            ms = tot / a.iters
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.iters
         r = {"kernel": name, "shape": shape, "ms": round(ms, 4)}
         if flops:
             r["tflops"] = round(flops / ms / 1e9, 1)
