@@ -218,7 +218,11 @@ class FusedPath:
                 "hn": [e(M, D) for _ in range(nl_s)], "a": [e(M, FF) for _ in range(nl_s)],
                 # ReLU / dropout pattern of the FFN hidden activation, 1 bit per element (gate of the FFN2 input gradient)
                 "am": [torch.empty(M, FF // 32, dtype=torch.int32, device=dev) for _ in range(nl_s)],
-                "lse": [e(B, 4, Tl, dt=torch.float32) for _ in range(nl_s)],
+                # rows [T, Tl) of lse (like those of delta below) are never written by the kernels but ARE loaded by the
+                # attention backward together with the last query tile, where they meet masked (-inf) scores: they must be
+                # finite, so the buffers start as zeros (torch.empty handed back NaN patterns from earlier allocations:
+                # sporadic NaN gradients in a long-lived process)
+                "lse": [torch.zeros(B, 4, Tl, dtype=torch.float32, device=dev) for _ in range(nl_s)],
                 # backward scratch (reused by every layer of the stream)
                 "g_y": g(B, T[s], D), "g_x": g(B, T[s], D), "g_yd": g(B, T[s], D), "g_a": g(M, FF), "g_hn": g(M, D),
                 "g_h": g(M, D), "g_qkv": g(M, 768), "g_xn": g(M, D),

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_kernel_case(case):
     out = kc.run_case(case)
     bad = {k: v for k, v in out.items() if isinstance(v, dict) and not v.get("finite", True)}
-    assert out["ok"], {k: v for k, v in out.items() if k != "kv"}
+    assert out["ok"], (out.get("bad"), {k: v for k, v in out.items() if k != "kv" and not isinstance(v, dict)})
     assert not bad
 
 

@@ -122,7 +122,7 @@ def main():
         add(f"layernorm_bwd_T{T}", lambda x=x, dx=dx: ops.layernorm_bwd(x, x, x, g, dx, dg, db), None,
             M * 256 * 2 * 4.0, f"rows={M}")
         # the LayerNorm backward in front of the attention backward: + O read, + dQ columns zeroed, + delta written
-        add(f"layernorm_bwd_attn_T{T}", lambda x=x, dx=dx, O=O, delta=delta, dqkv=dqkv:
+        add(f"layernorm_bwd_attn_T{T}", lambda x=x, dx=dx, O=O, delta=delta, dqkv=dqkv, T=T:
             ops.layernorm_bwd_attn(x, x, x, g, dx, dg, db, O, T, delta, dqkv), None, M * 256 * 2 * 6.0 + B * 4 * T * 4.0,
             f"rows={M} (x, dy, dres, O read; dx + zeroed dQ written)")
         # encoder prologue of this stream length as the step runs it: UMSE (T=1005) or projected rows (152 / 133) -> X0
