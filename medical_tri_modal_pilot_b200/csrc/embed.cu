@@ -209,83 +209,142 @@ struct PrologueParams {
   void* X0;                    // [B, T, 256] fp16 (fp32 in the fp32 mode)
 };
 
-template <int KIND, int ST>
-__device__ __forceinline__ bool prologue_row_embed(const PrologueParams& p, const BranchLane& V, const BranchLane& Tm,
-                                                   const float* sW, int b, int t, int lane, float (&e)[8], float& s_val,
-                                                   float& s_time, int& fid) {
-  // returns false for bottleneck rows (t < 4)
-  if (t < 4) return false;
-  if (t == 4) {
-    load8_f32(p.cls + lane * 8, e);
-    return true;
-  }
-  const int j = t - 5;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) e[i] = 0.f;
-  if (KIND == 0) {
-    const float* xr = p.x + ((size_t)b * p.n + j) * 3;
-    s_time = __ldg(xr); s_val = __ldg(xr + 1);
-    fid = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19);
-    branch_add(V, s_val, branch_rstd(V, s_val), e);
-  } else {
-    ld8<ST>(p.proj, ((size_t)b * p.n + j) * D + lane * 8, e);
-    s_time = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
-    fid = p.feat_id;
-  }
-  branch_add(Tm, s_time, branch_rstd(Tm, s_time), e);
-  const float4 f0 = *reinterpret_cast<const float4*>(&sW[fid * D + lane * 8]);
-  const float4 f1 = *reinterpret_cast<const float4*>(&sW[fid * D + lane * 8 + 4]);
-  e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w;
-  e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
-  return true;
-}
+// Forward. A warp takes 32 consecutive rows of the [B*T, 256] output at a time, in the manner of umse_embed_fwd_kernel: lane j
+// turns row j's inputs (the (time, value, feature) triple, or the slot time of an img / txt row) into the two per-token
+// scalars of each rank-1 LayerNorm branch and parks them in the warp's shared-memory slot; the row loop then runs on
+// broadcast reads and packed fp32 math (FFMA2), two rows at a time so that the two shuffle trees of the row LayerNorm (sum and
+// sum of squares, one pass) overlap. The first version walked one row per warp iteration with every load, both branch
+// evaluations and two dependent warp reductions in one serial chain: 0.65 TB/s cold at the bench shape, 0.97 TB/s at 512 k rows.
+struct RowMeta { int code; int proj_row; int t; int pad; };   // code: >= 0 feature-table offset (fid*D), -1..-4 bottleneck row, -5 CLS
 
 template <int KIND, int ST>
-__global__ void __launch_bounds__(256) stream_prologue_fwd_kernel(PrologueParams p) {
+__global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_kernel(PrologueParams p) {
   __shared__ __align__(16) float sW[20 * D];
+  __shared__ __align__(16) float4 sTok[8][32];
+  __shared__ __align__(16) RowMeta sMeta[8][32];
   for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
-  const int lane = threadIdx.x & 31;
-  BranchLane V, Tm;
-  if (KIND == 0) branch_setup(p.val, lane, V);
-  branch_setup(p.tim, lane, Tm);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  BranchFwd V, Tm;
+  if (KIND == 0) branch_fwd_setup(p.val, lane, V);
+  branch_fwd_setup(p.tim, lane, Tm);
   float lg[8], lb[8];
   load8_f32(p.ln_g + lane * 8, lg);
   load8_f32(p.ln_b + lane * 8, lb);
   __syncthreads();
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long rows = (long long)p.B * p.T;
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
-    const int b = (int)(row / p.T), t = (int)(row % p.T);
-    const size_t dst = (size_t)row * D + lane * 8;
-    float e[8], sv = 0.f, st = 0.f;
-    int fid = 0;
-    if (!prologue_row_embed<KIND, ST>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
-      load8_f32(p.bottlenecks + t * D + lane * 8, e);
-      st8<ST>(p.X0, dst, e);
-      continue;
+  const long long n_grp = (rows + 31) / 32;
+  const uint32_t dkey = p.drop_thr16 ? dropout_key(effective_seed(p.seed, p.seed_dev), p.salt) : 0u;
+  const float* sWl = sW + lane * 8;
+
+  // e <- [CLS ; E] row `j` of the group (before the input LayerNorm); returns false for a bottleneck row (copied verbatim)
+  auto embed = [&](int j, long long row, float (&e)[8]) -> bool {
+    const RowMeta m = sMeta[wid][j];
+    if (m.code < 0 && m.code > -5) {
+      load8_f32(p.bottlenecks + (-m.code - 1) * D + lane * 8, e);
+      st8<ST>(p.X0, (size_t)row * D + lane * 8, e);
+      return false;
     }
-    float s1 = 0.f;
+    if (m.code == -5) {
+      load8_f32(p.cls + lane * 8, e);
+      return true;
+    }
+    const float4 t4 = sTok[wid][j];
+    const float4 f0 = *reinterpret_cast<const float4*>(sWl + m.code);
+    const float4 f1 = *reinterpret_cast<const float4*>(sWl + m.code + 4);
+    f32x2 acc[4] = {pk2(f0.x, f0.y), pk2(f0.z, f0.w), pk2(f1.x, f1.y), pk2(f1.z, f1.w)};
+    const f32x2 at = pk2(t4.z, t4.z), rtt = pk2(t4.w, t4.w);
+    if (KIND == 0) {
+      const f32x2 av = pk2(t4.x, t4.x), rvv = pk2(t4.y, t4.y);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s1 += e[i];
-    const float mean = warp_sum(s1) * (1.f / D);
-    float s2 = 0.f;
+      for (int i = 0; i < 4; ++i) acc[i] = fadd2(fadd2(branch_fwd_pair(V, i, av, rvv), branch_fwd_pair(Tm, i, at, rtt)), acc[i]);
+    } else {
+      float pr[8];
+      ld8<ST>(p.proj, (size_t)m.proj_row * D + lane * 8, pr);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { e[i] -= mean; s2 += e[i] * e[i]; }
-    const float rstd = rsqrtf(warp_sum(s2) * (1.f / D) + 1e-5f);
+      for (int i = 0; i < 4; ++i)
+        acc[i] = fadd2(fadd2(pk2(pr[2 * i], pr[2 * i + 1]), branch_fwd_pair(Tm, i, at, rtt)), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk2(acc[i], e[2 * i], e[2 * i + 1]);
+    return true;
+  };
+  // layer_norms_in (nn.LayerNorm, eps 1e-5) + PE + dropout + store, given the row's sum and sum of squares
+  auto finish = [&](int j, long long row, float (&e)[8], float s1, float s2) {
+    const float mean = s1 * (1.f / D);
+    const float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mean * mean, 0.f) + 1e-5f);
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = fmaf(e[i] * rstd, lg[i], lb[i]);
+    for (int i = 0; i < 8; ++i) y[i] = fmaf((e[i] - mean) * rstd, lg[i], lb[i]);
     if (p.pe) {
       float pe[8];
-      load8_f32(p.pe + (size_t)(t - 4) * D + lane * 8, pe);
+      load8_f32(p.pe + (size_t)(sMeta[wid][j].t - 4) * D + lane * 8, pe);
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] += pe[i];
     }
-    if (p.drop_thr16) {
-      const uint32_t base = (uint32_t)row * D + lane * 8;
-      dropout_apply_run<8>(y, dropout_key(effective_seed(p.seed, p.seed_dev), p.salt), base, p.drop_thr16, p.drop_scale);
+    if (p.drop_thr16) dropout_apply_run<8>(y, dkey, (uint32_t)row * D + lane * 8, p.drop_thr16, p.drop_scale);
+    st8<ST>(p.X0, (size_t)row * D + lane * 8, y);
+  };
+  auto sums = [&](const float (&e)[8], float& s1, float& s2) {
+    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += e[i]; s2 = fmaf(e[i], e[i], s2); }
+  };
+
+  for (long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_grp; grp += warps) {
+    const long long row0 = grp * 32;
+    {   // lane j prepares row row0 + j
+      const long long r = row0 + lane;
+      RowMeta m{-1, 0, 0, 0};
+      float4 tok = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const int b = (int)(r / p.T), t = (int)(r - (long long)b * p.T);
+        m.t = t;
+        if (t < 4) m.code = -1 - t;
+        else if (t == 4) m.code = -5;
+        else {
+          const int j = t - 5;
+          float st;
+          if (KIND == 0) {
+            const float* xr = p.x + ((size_t)b * p.n + j) * 3;
+            st = __ldg(xr);
+            const float sv = __ldg(xr + 1);
+            m.code = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19) * D;   // C truncation == .type(torch.IntTensor)
+            const float rv = branch_fwd_rstd(V, sv);
+            tok.x = rv * sv; tok.y = rv;
+          } else {
+            m.proj_row = b * p.n + j;
+            st = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
+            m.code = p.feat_id * D;
+          }
+          const float rt = branch_fwd_rstd(Tm, st);
+          tok.z = rt * st; tok.w = rt;
+        }
+      }
+      __syncwarp();
+      sTok[wid][lane] = tok;
+      sMeta[wid][lane] = m;
+      __syncwarp();
     }
-    st8<ST>(p.X0, dst, y);
+    const int cnt = (int)min(32LL, rows - row0);
+    for (int j = 0; j < cnt; j += 2) {
+      float e0[8], e1[8];
+      const bool two = j + 1 < cnt;
+      const bool n0 = embed(j, row0 + j, e0);
+      const bool n1 = two && embed(j + 1, row0 + j + 1, e1);
+      float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+      if (n0) sums(e0, a1, a2);
+      if (n1) sums(e1, b1, b2);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {      // four interleaved shuffle trees
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+      }
+      if (n0) finish(j, row0 + j, e0, a1, a2);
+      if (n1) finish(j + 1, row0 + j + 1, e1, b1, b2);
+    }
   }
 }
 
@@ -304,46 +363,33 @@ struct PrologueBwdParams {
 
 struct BranchAcc { float dw[8], db[8], dg[8], dbe[8]; };
 
-__device__ __forceinline__ void branch_bwd(const BranchLane& L, float s, const float (&de)[8], BranchAcc& acc) {
-  const float rstd = branch_rstd(L, s);
-  float zh[8], dzh[8];
-  float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    zh[i] = fmaf(s, L.wc[i], L.bc[i]) * rstd;
-    const float pre = fmaf(zh[i], L.g[i], L.be[i]);
-    const float gm = pre > 0.f ? de[i] : 0.f;
-    acc.dbe[i] += gm;
-    acc.dg[i] += gm * zh[i];
-    dzh[i] = gm * L.g[i];
-    m1 += dzh[i];
-    m2 += dzh[i] * zh[i];
-  }
-  warp_sum2(m1, m2);
-  m1 *= (1.f / D); m2 *= (1.f / D);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float dz = rstd * (dzh[i] - m1 - zh[i] * m2);
-    acc.dw[i] += dz * s;
-    acc.db[i] += dz;
-  }
-}
-
 __device__ __forceinline__ void flush8(float* sm, const float (&v)[8], int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) atomicAdd(&sm[lane * 8 + i], v[i]);
 }
 
+// Backward, same row grouping as the forward: lane j prepares row j's scalars (inputs, both branch rstd's, feature id), the
+// row loop reads them by broadcast, the gradient row of the NEXT row is prefetched while the current one is reduced, the
+// sum / sum-of-squares of the input LayerNorm come from one pass (one shuffle tree instead of two), the two rank-1 branch
+// backward reductions share one tree, and the feature-embedding gradient goes to a WARP-PRIVATE [20,256] table in shared
+// memory (plain read-modify-write, each lane owns its 8 channels) instead of shared-memory atomics that eight warps
+// contended for on the five common feature ids. First version: 155-178 us at the bench shape (0.2 TB/s).
+struct BwdTok { float sv, rv, st, rt; };
+
 template <int KIND, int ST>
 __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdParams q) {
   const PrologueParams& p = q.f;
   extern __shared__ __align__(16) float sm[];
-  float* sW = sm;                 // [20*256] forward table
-  float* sG = sm + 20 * D;        // [20*256] feature-embedding gradient
-  float* sAcc = sG + 20 * D;      // [15*256]: val(4) tim(4) cls(1) bott(4) ln(2)
-  for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) { sW[i] = p.Wfeat[i]; sG[i] = 0.f; }
-  for (int i = threadIdx.x; i < 15 * D; i += blockDim.x) sAcc[i] = 0.f;
-  const int lane = threadIdx.x & 31;
+  float* sW = sm;                              // [20*256] forward table
+  float* sAcc = sm + 20 * D;                   // [16*256]: val(4) tim(4) cls(1) bott(4) ln(2) feat-const(1, KIND 1)
+  BwdTok* sTok = reinterpret_cast<BwdTok*>(sAcc + 16 * D);           // [8][32]
+  RowMeta* sMeta = reinterpret_cast<RowMeta*>(sTok + 8 * 32);        // [8][32]
+  float* sG = reinterpret_cast<float*>(sMeta + 8 * 32);              // KIND 0: [8 warps][20*256] feature-embedding gradient
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
+  for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) sAcc[i] = 0.f;
+  if (KIND == 0)
+    for (int i = threadIdx.x; i < 8 * 20 * D; i += blockDim.x) sG[i] = 0.f;
   BranchLane V, Tm;
   if (KIND == 0) branch_setup(p.val, lane, V);
   branch_setup(p.tim, lane, Tm);
@@ -358,71 +404,167 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
     a_cls[i] = a_lng[i] = a_lnb[i] = a_feat[i] = 0.f;
   }
   __syncthreads();
+  float* sGw = sG + (size_t)wid * 20 * D + lane * 8;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long rows = (long long)p.B * p.T;
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
-    const int b = (int)(row / p.T), t = (int)(row % p.T);
-    float g[8];
-    ld8<ST>(q.dX0, (size_t)row * D + lane * 8, g);
-    float e[8], sv = 0.f, st = 0.f;
-    int fid = 0;
-    if (!prologue_row_embed<KIND, ST>(p, V, Tm, sW, b, t, lane, e, sv, st, fid)) {
-      flush8(sAcc + (9 + t) * D, g, lane);  // bottleneck parameter rows
-      continue;
+  const long long n_grp = (rows + 31) / 32;
+  const uint32_t dkey = p.drop_thr16 ? dropout_key(effective_seed(p.seed, p.seed_dev), p.salt) : 0u;
+
+  for (long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_grp; grp += warps) {
+    const long long row0 = grp * 32;
+    {
+      const long long r = row0 + lane;
+      RowMeta m{-1, 0, 0, 0};
+      BwdTok tok{0.f, 0.f, 0.f, 0.f};
+      if (r < rows) {
+        const int b = (int)(r / p.T), t = (int)(r - (long long)b * p.T);
+        m.t = t;
+        if (t < 4) m.code = -1 - t;
+        else if (t == 4) m.code = -5;
+        else {
+          const int j = t - 5;
+          if (KIND == 0) {
+            const float* xr = p.x + ((size_t)b * p.n + j) * 3;
+            tok.st = __ldg(xr);
+            tok.sv = __ldg(xr + 1);
+            m.code = min(max(__float2int_rz(__ldg(xr + 2)), 0), 19) * D;
+            tok.rv = branch_rstd(V, tok.sv);
+          } else {
+            m.proj_row = b * p.n + j;
+            tok.st = __ldg(p.times + b * p.n_slots + j / p.rows_per_slot);
+            m.code = p.feat_id * D;
+          }
+          tok.rt = branch_rstd(Tm, tok.st);
+        }
+      }
+      __syncwarp();
+      sTok[wid * 32 + lane] = tok;
+      sMeta[wid * 32 + lane] = m;
+      __syncwarp();
     }
-    if (p.drop_thr16) {
-      const uint32_t base = (uint32_t)row * D + lane * 8;
-      dropout_apply_run<8>(g, dropout_key(effective_seed(p.seed, p.seed_dev), p.salt), base, p.drop_thr16, p.drop_scale);
+    const int cnt = (int)min(32LL, rows - row0);
+    float g[8], gn[8];
+    ld8<ST>(q.dX0, (size_t)row0 * D + lane * 8, g);
+    for (int j = 0; j < cnt; ++j) {
+      const long long row = row0 + j;
+      if (j + 1 < cnt) ld8<ST>(q.dX0, (size_t)(row + 1) * D + lane * 8, gn);     // prefetch the next gradient row
+      const RowMeta m = sMeta[wid * 32 + j];
+      if (m.code < 0 && m.code > -5) {
+        flush8(sAcc + (9 + (-m.code - 1)) * D, g, lane);      // bottleneck parameter rows (4 of T rows)
+      } else {
+        const BwdTok tk = sTok[wid * 32 + j];
+        float e[8];
+        if (m.code == -5) {
+          load8_f32(p.cls + lane * 8, e);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = 0.f;
+          if (KIND == 0) branch_add(V, tk.sv, tk.rv, e);
+          else ld8<ST>(p.proj, (size_t)m.proj_row * D + lane * 8, e);
+          branch_add(Tm, tk.st, tk.rt, e);
+          const float4 f0 = *reinterpret_cast<const float4*>(&sW[m.code + lane * 8]);
+          const float4 f1 = *reinterpret_cast<const float4*>(&sW[m.code + lane * 8 + 4]);
+          e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w;
+          e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
+        }
+        if (p.drop_thr16) dropout_apply_run<8>(g, dkey, (uint32_t)row * D + lane * 8, p.drop_thr16, p.drop_scale);
+        // input LayerNorm statistics, one pass
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1 += e[i]; s2 = fmaf(e[i], e[i], s2); }
+        warp_sum2(s1, s2);
+        const float mean = s1 * (1.f / D);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+        float de[8], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float yh = (e[i] - mean) * rstd;
+          a_lng[i] += g[i] * yh;
+          a_lnb[i] += g[i];
+          de[i] = g[i] * lg[i];   // d yhat
+          m1 += de[i];
+          m2 = fmaf(de[i], yh, m2);
+          e[i] = yh;
+        }
+        warp_sum2(m1, m2);
+        m1 *= (1.f / D); m2 *= (1.f / D);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) de[i] = rstd * (de[i] - m1 - e[i] * m2);
+        if (m.code == -5) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a_cls[i] += de[i];
+        } else {
+          if (KIND == 0) {
+            float* gw = sGw + m.code;          // warp-private table: no atomics
+            float4 u0 = *reinterpret_cast<float4*>(gw), u1 = *reinterpret_cast<float4*>(gw + 4);
+            u0.x += de[0]; u0.y += de[1]; u0.z += de[2]; u0.w += de[3];
+            u1.x += de[4]; u1.y += de[5]; u1.z += de[6]; u1.w += de[7];
+            *reinterpret_cast<float4*>(gw) = u0; *reinterpret_cast<float4*>(gw + 4) = u1;
+          } else {
+            st8<ST>(q.dproj, (size_t)m.proj_row * D + lane * 8, de);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a_feat[i] += de[i];
+          }
+          // both rank-1 LayerNorm branches: ReLU gate, LN-parameter gradients, then ONE shuffle tree for the four sums
+          float zv[8], dzv[8], zt[8], dzt[8];
+          float v1 = 0.f, v2 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) {
+              zv[i] = fmaf(tk.sv, V.wc[i], V.bc[i]) * tk.rv;
+              const float gm = fmaf(zv[i], V.g[i], V.be[i]) > 0.f ? de[i] : 0.f;
+              aV.dbe[i] += gm;
+              aV.dg[i] = fmaf(gm, zv[i], aV.dg[i]);
+              dzv[i] = gm * V.g[i];
+              v1 += dzv[i];
+              v2 = fmaf(dzv[i], zv[i], v2);
+            }
+            zt[i] = fmaf(tk.st, Tm.wc[i], Tm.bc[i]) * tk.rt;
+            const float gt = fmaf(zt[i], Tm.g[i], Tm.be[i]) > 0.f ? de[i] : 0.f;
+            aT.dbe[i] += gt;
+            aT.dg[i] = fmaf(gt, zt[i], aT.dg[i]);
+            dzt[i] = gt * Tm.g[i];
+            t1 += dzt[i];
+            t2 = fmaf(dzt[i], zt[i], t2);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            if (KIND == 0) {
+              v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+              v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+          }
+          v1 *= (1.f / D); v2 *= (1.f / D); t1 *= (1.f / D); t2 *= (1.f / D);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) {
+              const float dz = tk.rv * (dzv[i] - v1 - zv[i] * v2);
+              aV.dw[i] = fmaf(dz, tk.sv, aV.dw[i]);
+              aV.db[i] += dz;
+            }
+            const float dz = tk.rt * (dzt[i] - t1 - zt[i] * t2);
+            aT.dw[i] = fmaf(dz, tk.st, aT.dw[i]);
+            aT.db[i] += dz;
+          }
+        }
+      }
+      if (j + 1 < cnt) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = gn[i];
+      }
     }
-    float s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s1 += e[i];
-    const float mean = warp_sum(s1) * (1.f / D);
-    float s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { e[i] -= mean; s2 += e[i] * e[i]; }
-    const float rstd = rsqrtf(warp_sum(s2) * (1.f / D) + 1e-5f);
-    float de[8], m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float yh = e[i] * rstd;
-      a_lng[i] += g[i] * yh;
-      a_lnb[i] += g[i];
-      de[i] = g[i] * lg[i];   // d yhat
-      m1 += de[i];
-      m2 += de[i] * yh;
-      e[i] = yh;
-    }
-    warp_sum2(m1, m2);
-    m1 *= (1.f / D); m2 *= (1.f / D);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) de[i] = rstd * (de[i] - m1 - e[i] * m2);
-    if (t == 4) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a_cls[i] += de[i];
-      continue;
-    }
-    if (KIND == 0) {
-      branch_bwd(V, sv, de, aV);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sG[fid * D + lane * 8 + i], de[i]);
-    } else {
-      st8<ST>(q.dproj, ((size_t)b * p.n + (t - 5)) * D + lane * 8, de);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a_feat[i] += de[i];
-    }
-    branch_bwd(Tm, st, de, aT);
   }
   if (KIND == 0) {
     flush8(sAcc + 0 * D, aV.dw, lane); flush8(sAcc + 1 * D, aV.db, lane);
     flush8(sAcc + 2 * D, aV.dg, lane); flush8(sAcc + 3 * D, aV.dbe, lane);
-  } else {
-    flush8(sG + p.feat_id * D, a_feat, lane);
   }
   flush8(sAcc + 4 * D, aT.dw, lane); flush8(sAcc + 5 * D, aT.db, lane);
   flush8(sAcc + 6 * D, aT.dg, lane); flush8(sAcc + 7 * D, aT.dbe, lane);
   flush8(sAcc + 8 * D, a_cls, lane);
   flush8(sAcc + 13 * D, a_lng, lane); flush8(sAcc + 14 * D, a_lnb, lane);
+  if (KIND == 1) flush8(sAcc + 15 * D, a_feat, lane);
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
     if (KIND == 0) atomicAdd(&q.g_val[i], sAcc[i]);
@@ -435,19 +577,15 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
     atomicAdd(&q.g_ln[D + i], sAcc[14 * D + i]);
   }
   if (KIND == 0) {
-    for (int i = threadIdx.x; i < 20 * D; i += blockDim.x)
-      if (sG[i] != 0.f) atomicAdd(&q.g_feat[i], sG[i]);
+    for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += sG[(size_t)w * 20 * D + i];
+      if (v != 0.f) atomicAdd(&q.g_feat[i], v);
+    }
   } else {
-    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&q.g_feat[p.feat_id * D + i], sG[p.feat_id * D + i]);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&q.g_feat[p.feat_id * D + i], sAcc[15 * D + i]);
   }
-}
-
-int grid_for_rows(long long rows) {
-  long long blocks = (rows + 7) / 8;
-  const long long cap = (long long)tmp::num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
 }
 
 }  // namespace
@@ -504,7 +642,10 @@ static int prologue_fwd_impl(int stf, int kind, int B, int n, const float* x, co
   int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
                          ln_b, pe, drop_p, seed, salt, seed_dev, X0);
   if (rc) return rc;
-  const int grid = grid_for_rows((long long)B * p.T);
+  long long fblocks = ((long long)B * p.T + 255) / 256;      // one warp per 32-row group
+  const long long fcap = (long long)tmp::num_sms() * (kind == 0 ? 2 : 3);
+  if (fblocks > fcap) fblocks = fcap;
+  const int grid = (int)(fblocks < 1 ? 1 : fblocks);
   cudaStream_t s = (cudaStream_t)stream;
   if (stf == FMT_F32) {
     if (kind == 0) stream_prologue_fwd_kernel<0, FMT_F32><<<grid, 256, 0, s>>>(p);
@@ -553,17 +694,23 @@ static int prologue_bwd_impl(int stf, int kind, int B, int n, const float* x, co
   q.dX0 = dX0;
   q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
   q.dproj = dproj;
-  const int smem = (20 + 20 + 15) * D * 4;
+  // forward table + accumulators + per-warp row scalars (+ 8 warp-private feature-gradient tables for the vslt stream)
+  const int smem1 = (20 + 16) * D * 4 + 2 * 8 * 32 * 16;
+  const int smem0 = smem1 + 8 * 20 * D * 4;
+  const int smem = kind == 0 ? smem0 : smem1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<0, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0);
+    cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     attr_set = true;
   }
-  long long blocks = ((long long)B * q.f.T + 7) / 8;
-  if (blocks > tmp::num_sms()) blocks = tmp::num_sms();
+  // one warp per 32-row group; the vslt kernel holds 200 KB of shared memory (one block per SM), the img / txt one 45 KB
+  long long blocks = ((long long)B * q.f.T + 255) / 256;
+  const long long cap = (long long)tmp::num_sms() * (kind == 0 ? 1 : 3);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;
   if (stf == FMT_F32) {
     if (kind == 0) stream_prologue_bwd_kernel<0, FMT_F32><<<(int)blocks, 256, smem, s>>>(q);

@@ -151,9 +151,9 @@ def case_prologue():
     cls = torch.randn(256, device=dev); bott = torch.randn(4, 256, device=dev)
     lg = 1 + 0.1 * torch.randn(256, device=dev); lb = 0.1 * torch.randn(256, device=dev)
     pe = torch.randn(200, 256, device=dev)
-    for kind in (0, 1):
-        B, n = 5, (37 if kind == 0 else 147)
+    for kind, B, n, drop in ((0, 5, 37, 0.0), (1, 5, 147, 0.0), (0, 7, 300, 0.25), (1, 9, 147, 0.25)):
         T = n + 5
+        tag = f"{kind}" if drop == 0.0 else f"{kind}_drop"
         leaves = [t.clone().requires_grad_(True) for t in (*val4, *tim4, W, cls, bott, lg, lb)]
         v4, t4, Wl, cl, bo, lgl, lbl = leaves[0:4], leaves[4:8], leaves[8], leaves[9], leaves[10], leaves[11], leaves[12]
         if kind == 0:
@@ -168,19 +168,25 @@ def case_prologue():
             proj = torch.randn(B * n, 256, device=dev).half()
             projf = proj.float().requires_grad_(True)
             times = -torch.rand(B, 3, device=dev) * 24
-            n_slots = 3; feat = 18; use_pe = pe
+            n_slots = 3; feat = 18; use_pe = pe[: n + 1].contiguous()
             te = _branch_ref(times, *t4)  # [B,3,256]
             E = projf.view(B, 3, 49, 256) + te[:, :, None, :] + Wl[feat]
             E = E.reshape(B, n, 256)
         seq = torch.cat([cl.expand(B, 1, 256), E], 1)
         y = torch.nn.functional.layer_norm(seq, (256,), lgl, lbl, 1e-5)
         if use_pe is not None:
-            y = y + use_pe[: n + 1]
-        ref = torch.cat([bo.expand(B, 4, 256), y], 1)
+            y = y + use_pe
         X0 = torch.empty(B, T, 256, device=dev, dtype=ACT)
         ops.stream_prologue_fwd(kind, B, n, x, val4 if kind == 0 else None, proj, times, n_slots, feat, tim4, W, cls,
-                                bott, lg, lb, use_pe, 0.0, 0, 0, X0)
-        res[f"fwd{kind}"] = _err(X0, ref)
+                                bott, lg, lb, use_pe, drop, 11, 5, X0)
+        if drop > 0:
+            # the mask is a stateless hash: read it off the forward output, apply it to the reference, and require the
+            # backward (same seed / salt) to use the identical mask
+            keep = (X0[:, 4:] != 0).float()
+            res[f"keep_frac{tag}"] = {"rel_to_max": abs(keep.mean().item() - (1 - drop)), "finite": True}
+            y = y * keep / (1 - drop)
+        ref = torch.cat([bo.expand(B, 4, 256), y], 1)
+        res[f"fwd{tag}"] = _err(X0, ref)
         dX0 = torch.randn(B, T, 256, device=dev).to(GRD)
         ref.backward(dX0.float())
         g_val = torch.zeros(4, 256, device=dev); g_tim = torch.zeros(4, 256, device=dev)
@@ -188,17 +194,17 @@ def case_prologue():
         g_bott = torch.zeros(4, 256, device=dev); g_ln = torch.zeros(2, 256, device=dev)
         dproj = torch.empty(B * n, 256, device=dev, dtype=GRD) if kind == 1 else None
         ops.stream_prologue_bwd(kind, B, n, x, val4 if kind == 0 else None, proj, times, n_slots, feat, tim4, W, cls,
-                                bott, lg, lb, use_pe, 0.0, 0, 0, dX0, g_val if kind == 0 else None, g_tim, g_feat,
+                                bott, lg, lb, use_pe, drop, 11, 5, dX0, g_val if kind == 0 else None, g_tim, g_feat,
                                 g_cls, g_bott, g_ln, dproj)
         if kind == 0:
-            res["g_val"] = _err(g_val, torch.stack([l.grad for l in v4]))
+            res[f"g_val{tag}"] = _err(g_val, torch.stack([l.grad for l in v4]))
         else:
-            res["dproj"] = _err(dproj, projf.grad)
-        res[f"g_tim{kind}"] = _err(g_tim, torch.stack([l.grad for l in t4]))
-        res[f"g_feat{kind}"] = _err(g_feat, Wl.grad)
-        res[f"g_cls{kind}"] = _err(g_cls, cl.grad)
-        res[f"g_bott{kind}"] = _err(g_bott, bo.grad)
-        res[f"g_ln{kind}"] = _err(g_ln, torch.stack([lgl.grad, lbl.grad]))
+            res[f"dproj{tag}"] = _err(dproj, projf.grad)
+        res[f"g_tim{tag}"] = _err(g_tim, torch.stack([l.grad for l in t4]))
+        res[f"g_feat{tag}"] = _err(g_feat, Wl.grad)
+        res[f"g_cls{tag}"] = _err(g_cls, cl.grad)
+        res[f"g_bott{tag}"] = _err(g_bott, bo.grad)
+        res[f"g_ln{tag}"] = _err(g_ln, torch.stack([lgl.grad, lbl.grad]))
     res["ok"] = all(v["rel_to_max"] < 2e-2 for k, v in res.items() if isinstance(v, dict))
     return res
 
