@@ -172,7 +172,7 @@ def main():
         f"tokens={n_tok}")
 
     results = []
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if a.flush else None
+    flush_buf = torch.zeros(256 << 20, dtype=torch.uint8, device=dev) if a.flush else None
     for name, fn, flops, bytes_, shape in cases:
         fn()
         if not a.time:
@@ -184,7 +184,8 @@ def main():
         if a.flush:
             tot = 0.0
             for _ in range(a.iters):
-                flush_buf.fill_(1)                       # evict the 126 MB L2
+                flush_buf.view(torch.int32).sum()        # evict the 126 MB L2 with CLEAN lines (a write would leave 126 MB of
+                                                         # dirty lines whose write-back the kernel under test then pays for)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); fn(); e1.record()
                 torch.cuda.synchronize()
