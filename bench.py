@@ -452,19 +452,23 @@ def run_b200(a):
 
 
 def _finish(world, model):
-    """End of a multi-rank run. The NCCL communicator is referenced by the captured CUDA graphs of the train step, and
-    `destroy_process_group()` then blocks in ncclCommDestroy (measured on 2 x B200: the JSON line was printed and the
-    job never exited). All ranks meet at a barrier, drop the graphs, and leave without running the communicator's
-    destructor; the result line is already flushed."""
+    """End of a multi-rank run: drop the captured step graphs (they reference the NCCL communicator, and
+    `destroy_process_group()` blocks in ncclCommDestroy while they live), then tear the group down. A watchdog leaves the
+    process if the teardown still does not return -- the result line is already flushed."""
     if world <= 1:
         return
+    import threading
     import torch
     import torch.distributed as dist
     dist.barrier()
     torch.cuda.synchronize()
-    model.__dict__.pop("_graphed_steps", None)
     sys.stdout.flush()
     sys.stderr.flush()
+    threading.Timer(30.0, lambda: os._exit(0)).start()
+    sync = getattr(model, "grad_sync", None)
+    if sync is not None:
+        sync.close()
+    dist.destroy_process_group()
     os._exit(0)
 
 

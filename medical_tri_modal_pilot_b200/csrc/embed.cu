@@ -209,39 +209,19 @@ struct PrologueParams {
   void* X0;                    // [B, T, 256] fp16 (fp32 in the fp32 mode)
 };
 
-// Sum over the 32 lanes of 16 per-lane values a[0..15] (one per row of a 16-row half group): afterwards a[0] of lane L is
-// the full sum for row (L & 15). Recursive halving -- 8 + 4 + 2 + 1 + 1 = 16 shuffles for 16 rows instead of 5 per row.
-__device__ __forceinline__ void transpose_reduce16(float (&a)[16], int lane) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? a[i] : a[i + o];
-      const float keep = up ? a[i + o] : a[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
-}
-
 // Forward. A warp takes 32 consecutive rows of the [B*T, 256] output at a time, in the manner of umse_embed_fwd_kernel: lane j
 // turns row j's inputs (the (time, value, feature) triple, or the slot time of an img / txt row) into the two per-token
-// scalars of each rank-1 LayerNorm branch and parks them in the warp's shared-memory slot; everything after that runs on
-// broadcast reads and packed fp32 math (FFMA2). The row LayerNorm (layer_norms_in) needs a sum and a sum of squares over
-// the 256 channels of every row; a shuffle tree per row would put ten dependent shuffles into every row's chain (the first
-// version: 0.65 TB/s cold at the bench shape), so the kernel makes TWO passes over each 16-row half group: pass 1 evaluates
-// the rows and keeps only the per-lane partial sums, one transposed reduction turns them into (mean, rstd) per row, pass 2
-// re-evaluates the rows (cheap: ~40 packed instructions) and normalises, adds PE, applies dropout and stores. Neither pass
-// has a cross-lane operation inside its row loop, so the compiler overlaps the rows like in the plain embedding kernel.
+// scalars of each rank-1 LayerNorm branch and parks them in the warp's shared-memory slot; the row loop then runs on
+// broadcast reads and packed fp32 math (FFMA2), two rows at a time so that the two shuffle trees of the row LayerNorm (sum and
+// sum of squares, one pass) overlap. The first version walked one row per warp iteration with every load, both branch
+// evaluations and two dependent warp reductions in one serial chain: 0.65 TB/s cold at the bench shape, 0.97 TB/s at 512 k rows.
 struct RowMeta { int code; int proj_row; int t; int pad; };   // code: >= 0 feature-table offset (fid*D), -1..-4 bottleneck row, -5 CLS
 
 template <int KIND, int ST>
-__global__ void __launch_bounds__(256, 2) stream_prologue_fwd_kernel(PrologueParams p) {
+__global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_kernel(PrologueParams p) {
   __shared__ __align__(16) float sW[20 * D];
   __shared__ __align__(16) float4 sTok[8][32];
   __shared__ __align__(16) RowMeta sMeta[8][32];
-  __shared__ float2 sStat[8][32];
   for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   BranchFwd V, Tm;
@@ -257,16 +237,17 @@ __global__ void __launch_bounds__(256, 2) stream_prologue_fwd_kernel(ProloguePar
   const uint32_t dkey = p.drop_thr16 ? dropout_key(effective_seed(p.seed, p.seed_dev), p.salt) : 0u;
   const float* sWl = sW + lane * 8;
 
-  // e <- [CLS ; E] row `j` of the group (before the input LayerNorm); bottleneck rows give zeros here (handled in pass 2)
-  auto embed = [&](int j, float (&e)[8]) {
+  // e <- [CLS ; E] row `j` of the group (before the input LayerNorm); returns false for a bottleneck row (copied verbatim)
+  auto embed = [&](int j, long long row, float (&e)[8]) -> bool {
     const RowMeta m = sMeta[wid][j];
-    if (m.code < 0) {
-      if (m.code == -5) load8_f32(p.cls + lane * 8, e);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = 0.f;
-      }
-      return;
+    if (m.code < 0 && m.code > -5) {
+      load8_f32(p.bottlenecks + (-m.code - 1) * D + lane * 8, e);
+      st8<ST>(p.X0, (size_t)row * D + lane * 8, e);
+      return false;
+    }
+    if (m.code == -5) {
+      load8_f32(p.cls + lane * 8, e);
+      return true;
     }
     const float4 t4 = sTok[wid][j];
     const float4 f0 = *reinterpret_cast<const float4*>(sWl + m.code);
@@ -286,6 +267,28 @@ __global__ void __launch_bounds__(256, 2) stream_prologue_fwd_kernel(ProloguePar
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) upk2(acc[i], e[2 * i], e[2 * i + 1]);
+    return true;
+  };
+  // layer_norms_in (nn.LayerNorm, eps 1e-5) + PE + dropout + store, given the row's sum and sum of squares
+  auto finish = [&](int j, long long row, float (&e)[8], float s1, float s2) {
+    const float mean = s1 * (1.f / D);
+    const float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = fmaf((e[i] - mean) * rstd, lg[i], lb[i]);
+    if (p.pe) {
+      float pe[8];
+      load8_f32(p.pe + (size_t)(sMeta[wid][j].t - 4) * D + lane * 8, pe);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] += pe[i];
+    }
+    if (p.drop_thr16) dropout_apply_run<8>(y, dkey, (uint32_t)row * D + lane * 8, p.drop_thr16, p.drop_scale);
+    st8<ST>(p.X0, (size_t)row * D + lane * 8, y);
+  };
+  auto sums = [&](const float (&e)[8], float& s1, float& s2) {
+    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += e[i]; s2 = fmaf(e[i], e[i], s2); }
   };
 
   for (long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_grp; grp += warps) {
@@ -324,54 +327,23 @@ __global__ void __launch_bounds__(256, 2) stream_prologue_fwd_kernel(ProloguePar
       __syncwarp();
     }
     const int cnt = (int)min(32LL, rows - row0);
-#pragma unroll 1
-    for (int h = 0; h < 32 && h < cnt; h += 16) {
-      // ---- pass 1: per-lane partial sums of the 16 rows of this half group ----
-      float s1[16], s2[16];
+    for (int j = 0; j < cnt; j += 2) {
+      float e0[8], e1[8];
+      const bool two = j + 1 < cnt;
+      const bool n0 = embed(j, row0 + j, e0);
+      const bool n1 = two && embed(j + 1, row0 + j + 1, e1);
+      float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+      if (n0) sums(e0, a1, a2);
+      if (n1) sums(e1, b1, b2);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float e[8];
-        embed(h + j, e);           // rows past `cnt` carry code -1 (zeros)
-        float a = 0.f, b2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { a += e[i]; b2 = fmaf(e[i], e[i], b2); }
-        s1[j] = a; s2[j] = b2;
+      for (int o = 16; o > 0; o >>= 1) {      // four interleaved shuffle trees
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
       }
-      transpose_reduce16(s1, lane);
-      transpose_reduce16(s2, lane);
-      {
-        const float mean = s1[0] * (1.f / D);
-        const float rstd = rsqrtf(fmaxf(s2[0] * (1.f / D) - mean * mean, 0.f) + 1e-5f);
-        if (lane < 16) sStat[wid][h + lane] = make_float2(mean, rstd);
-      }
-      __syncwarp();
-      // ---- pass 2: re-evaluate, normalise (layer_norms_in, eps 1e-5), + PE, dropout, store ----
-      const int n2 = min(16, cnt - h);
-#pragma unroll 4
-      for (int j = 0; j < n2; ++j) {
-        const long long row = row0 + h + j;
-        const RowMeta m = sMeta[wid][h + j];
-        float e[8];
-        if (m.code < 0 && m.code != -5) {
-          load8_f32(p.bottlenecks + (-m.code - 1) * D + lane * 8, e);      // bottleneck rows are copied verbatim
-          st8<ST>(p.X0, (size_t)row * D + lane * 8, e);
-          continue;
-        }
-        embed(h + j, e);
-        const float2 ms = sStat[wid][h + j];
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = fmaf((e[i] - ms.x) * ms.y, lg[i], lb[i]);
-        if (p.pe) {
-          float pe[8];
-          load8_f32(p.pe + (size_t)(m.t - 4) * D + lane * 8, pe);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] += pe[i];
-        }
-        if (p.drop_thr16) dropout_apply_run<8>(y, dkey, (uint32_t)row * D + lane * 8, p.drop_thr16, p.drop_scale);
-        st8<ST>(p.X0, (size_t)row * D + lane * 8, y);
-      }
-      __syncwarp();
+      if (n0) finish(j, row0 + j, e0, a1, a2);
+      if (n1) finish(j + 1, row0 + j + 1, e1, b1, b2);
     }
   }
 }

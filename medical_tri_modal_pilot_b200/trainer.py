@@ -78,6 +78,24 @@ class GradSync:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         self.n_collectives += 1
 
+    def close(self):
+        """Detach from the model and drop every captured step graph that references the communicator. A process group
+        whose communicator is still referenced by a live CUDA graph cannot be torn down (`destroy_process_group()` blocked
+        in ncclCommDestroy in the first 2-GPU runs); call this first, then destroy the group."""
+        import gc
+        self.fp.comm_hook = None
+        cache = self.model.__dict__.pop("_graphed_steps", None)
+        if cache:
+            for gs in cache.values():
+                gs.graph = None
+                gs.loss = None
+            cache.clear()
+        if getattr(self.model, "grad_sync", None) is self:
+            object.__setattr__(self.model, "grad_sync", None)
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def finish(self):
         """Head bucket + join the communication stream. Call after loss.backward(), before optimizer.step()."""
         if self.world == 1:
