@@ -26,6 +26,8 @@
 // the fp32 accumulator with cp.reduce.async.bulk.tensor (no per-thread atomics). The key-padding mask is kv_len[b]
 // applied in-register, only in boundary tiles (P^T rows of masked keys are exactly 0, so dK/dV of pad rows are exactly
 // 0, as in the reference).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -92,7 +94,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
                 const int32_t* __restrict__ kv_len, int T, int n_jt, int H, int q_tiles_max,
                 int n_items, const float* __restrict__ lse2, const float* __restrict__ delta, int T_lse,
-                uint16_t* __restrict__ dQKV, float scale_log2) {
+                uint16_t* __restrict__ dQKV, float scale_log2, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   Bars* bars = (Bars*)(smem + kSmemBar);
@@ -212,9 +214,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // K_j / V_j of this item. Their buffers (V's doubles as dS^T pair 1) are dead once the last dQ of the previous
         // item has retired.
         if (it > 0) mbar_wait(&bars->kv_free, (it - 1) & 1);
-        mbar_expect_tx(&bars->kv_full, 2 * kTile);
-        tma_load_2d(smem + kSmemK, &tmQKV, &bars->kv_full, 256 + w.h * HD, w.row_base + w.k0);
-        tma_load_2d(smem + kSmemV, &tmQKV, &bars->kv_full, 512 + w.h * HD, w.row_base + w.k0);
+        if (!(dbg & 1) || it == 0) {   // dbg bit 0 (timing experiment only): keep the first item's K_j / V_j
+          mbar_expect_tx(&bars->kv_full, 2 * kTile);
+          tma_load_2d(smem + kSmemK, &tmQKV, &bars->kv_full, 256 + w.h * HD, w.row_base + w.k0);
+          tma_load_2d(smem + kSmemV, &tmQKV, &bars->kv_full, 512 + w.h * HD, w.row_base + w.k0);
+        }
         mbar_wait(&bars->kv_tmem, it & 1);
         mbar_wait(&bars->qdo_full[gq % kStages], (gq / kStages) & 1);
         tc_fence_after();
@@ -292,9 +296,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // K_j, V_j -> TMEM (A operands of S^T / dP^T): thread = key row = TMEM lane, 64 fp16 = 32 packed columns each.
         // One warp per lane quarter; the swizzled 16 B chunks of a row are read in logical order. (tm_K / tm_V are
         // free: this warp has consumed the last S^T/dP^T of the previous item.)
-        mbar_wait(&bars->kv_full, it & 1);
+        if (!(dbg & 1) || it == 0) mbar_wait(&bars->kv_full, it & 1);
 #pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
+        for (int which = 0; which < 2 && (!(dbg & 1) || it == 0); ++which) {
           const uint8_t* src = smem + (which == 0 ? kSmemK : kSmemV);
           uint32_t wv[32];
 #pragma unroll
@@ -319,6 +323,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->dq_empty);
+        if (dbg & 2) return;          // dbg bit 1 (timing experiment only): no write-out
         tma_store_wait_read0();   // previous reduce / store of this warp has finished reading the staging box (every lane
                                   // waits: bulk groups are per thread, lanes without any return at once)
         __syncwarp();
@@ -423,6 +428,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // 32 key rows of ONE of the two (colhalf 0: dK, 1: dV): a [32 x 128 B] box, staged in the warp's swizzled dQ
         // box and written with one TMA store. (Per-thread 16 B stores to 32 different rows per instruction -- 32
         // partial sectors each -- cost 1.8 us per item, 25 us of the 267 us kernel at T=1005.)
+        if (dbg & 2) { tc_fence_before(); gq += n_q; ++it; continue; }
         const int which = colhalf;
         const uint32_t src = which == 0 ? tm_DK : tm_DV;
         const float osc = which == 0 ? 1.f : 8.f;   // dV was accumulated from P^T / 8
@@ -575,16 +581,17 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
       return (int)e;
     }
   }
+  static const int dbg = getenv("TMP_B200_ATTN_BWD_DBG") ? atoi(getenv("TMP_B200_ATTN_BWD_DBG")) : 0;   // timing experiments
   const int n_jt = (T + BT - 1) / BT;
   const int n_items = n_jt * H * B;
   const int sms = tmp::num_sms();
   const int grid = n_items < sms ? n_items : sms;
   if (fused)
     attn_bwd_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, q_tiles_max, n_items,
-                                                              lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
+                                                              lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f, dbg);
   else
     attn_bwd_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(tmQKV, tmDO, tmDQ, tmDKV, kv_len, T, n_jt, H, q_tiles_max, n_items,
-                                                               lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f);
+                                                               lse2, delta, T_lse, (uint16_t*)dQKV, kLog2e / 8.0f, dbg);
   rc = tmp::check_launch("attn_bwd_kernel");
   if (rc || fused) return rc;
   const size_t rows = (size_t)B * T;
