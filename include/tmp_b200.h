@@ -91,12 +91,14 @@ int tmp_layernorm_bwd_attn(const void* dy, const void* x, const void* dres, cons
  * mask_out (optional, [M, N/32] uint32): bit c%32 of word (row, c/32) = (result before the residual > 0) -- the ReLU /
  * dropout pattern in one bit per element. A later call passes it back as `gate` with gate_fmt = 3 and ld_gate = N/32
  * (the FFN2 input gradient) instead of re-reading the 16-bit activation. gate_fmt / res_fmt 2 = fp32 tensors (fp32 mode).
+ * row_live (optional, uint8 per group of rows_per_group consecutive rows): output tiles whose rows all lie in dead groups
+ * are skipped (images without a consumer in the Swin feed).
  * A, B and out16 go through TMA: 16-byte aligned base addresses, leading dimensions multiples of 8 elements. */
 int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const void* B, int b_fmt, int ldb, int M, int N, int K,
                           float alpha, const float* bias, int relu, const void* gate, int gate_fmt, int ld_gate,
                           const void* residual, int res_fmt, int ld_res, float drop_p, uint32_t seed, uint32_t salt,
                           const uint32_t* seed_dev, void* out16, int out_fmt, float* out_f32, int ld_out,
-                          uint32_t* mask_out, void* stream);
+                          uint32_t* mask_out, const uint8_t* row_live, int rows_per_group, void* stream);
 /* dW[N,K] fp32 += dY[M,N]^T . X[M,K]  (weight gradient; N,K % 128 == 0; same format for dY and X).
  * dbias (optional, may be NULL): dbias[N] fp32 += column sums of dY (the bias gradient), computed from the dY tiles
  * the kernel stages in shared memory anyway -- replaces a separate tmp_colsum pass over dY.
@@ -151,21 +153,24 @@ int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n
  * shifted_window_attention :115-214, PatchMerging :34-46,75-86). Activations fp16 [tokens, Cp] (Cp = padded channel
  * stride, pad channels zero); LayerNorm parameters fp32; n_img images; H x W token map; C real channels. -------------- */
 /* img fp32 [n_img,224,224]; Wt [16,96] = conv weight transposed (pixel-major); out [n_img*56*56, Cp] */
+/* live (every tmp_swin_* call): optional uint8 [n_img]; 0 = the image's features have no consumer (empty slot, img_time == 10,
+ * tri_mbt_vsltcls.py:229-231, or an img-missing sample): its work is skipped. The last kernel of the encoder passes
+ * zero_dead = 1 so that dead images end up as zero rows (a masked key still meets 0 * V in the attention). */
 int tmp_swin_patch_embed_ln(const float* img, int n_img, const float* Wt, const float* bconv, const float* g,
-                            const float* b, void* out, int Cp, void* stream);
+                            const float* b, void* out, int Cp, const uint8_t* live, void* stream);
 /* out[window order] = LayerNorm(x[natural order]) after torch.roll(-shift) and window partition (7x7 windows) */
 int tmp_swin_ln_window(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp, int shift,
-                       void* out, void* stream);
+                       void* out, const uint8_t* live, int zero_dead, void* stream);
 /* qkv [tokens(window order), ld_qkv] = q|k|v (head h at h*32 inside each C-wide part); rel_bias fp32 [heads,49,49];
  * out [tokens(window order), ld_out] */
 int tmp_swin_window_attn(const void* qkv, int ld_qkv, const float* rel_bias, int n_img, int H, int W, int C, int heads,
-                         int shift, void* out, int ld_out, void* stream);
+                         int shift, void* out, int ld_out, const uint8_t* live, void* stream);
 /* x[natural] += y[window order] (window reverse + reverse shift); hn = LayerNorm(x) unless hn == NULL */
 int tmp_swin_unwindow_add_ln(const void* y, void* x, const float* g, const float* b, int n_img, int H, int W, int C,
-                             int Cp, int shift, void* hn, void* stream);
+                             int Cp, int shift, void* hn, const uint8_t* live, void* stream);
 /* out[(n,i,j), 4C] = LayerNorm(x0|x1|x2|x3) of the 2x2 neighbourhood (PatchMerging), out stride 4C */
 int tmp_swin_merge_ln(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp, void* out,
-                      void* stream);
+                      const uint8_t* live, void* stream);
 
 /* ---- fp32 ("precise") mode: north-star's FP32 parity mode of the same path (trainer.py:126 is the only place the
  * reference drops precision; called outside autocast the reference runs in fp32). Every activation / gradient tensor is

@@ -30,7 +30,7 @@ SIGNATURES = {
     "tmp_layernorm_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
     "tmp_layernorm_bwd_attn": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "tmp_gemm_bias_act_fwd": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _i, _vp, _i, _i, _f, _u32,
-                              _u32, _vp, _vp, _i, _vp, _i, _vp, _vp],
+                              _u32, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "tmp_gemm_wgrad": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
     "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
@@ -55,11 +55,11 @@ SIGNATURES = {
     "tmp_split_bf16x3": [_vp, _ll, _ll, _i, _i, _i, _vp, _vp],
     "tmp_attn_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
     "tmp_attn_bwd_f32": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
-    "tmp_swin_patch_embed_ln": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-    "tmp_swin_ln_window": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "tmp_swin_window_attn": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
-    "tmp_swin_unwindow_add_ln": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "tmp_swin_merge_ln": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "tmp_swin_patch_embed_ln": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    "tmp_swin_ln_window": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "tmp_swin_window_attn": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "tmp_swin_unwindow_add_ln": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "tmp_swin_merge_ln": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
 }
 _RESTYPES = {"tmp_last_error": C.c_char_p}
 

@@ -45,6 +45,8 @@ struct EpiParams {
   const uint32_t* drop_seed_dev;   // optional device word added to the seed (CUDA-graph replays), or null
   uint32_t* mask_out;     // optional [M, N/32] bit mask of (result > 0) -- the ReLU/dropout gate of the backward pass in 1 bit per
                           // element instead of re-reading the 16-bit activation (gate_fmt == FMT_MASK consumes it)
+  const uint8_t* row_live;   // optional: liveness per group of `rows_per_group` consecutive rows (an image of the Swin feed);
+  int rows_per_group;        // an m-tile whose rows all belong to dead groups is skipped by every role
   uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
   float* out_f32;         // [M, ld_out] fp32 (or null) -- direct stores
   int ld_out;
@@ -199,6 +201,14 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
   }
 }
 
+__device__ __forceinline__ bool tile_dead(const EpiParams& p, int m0) {
+  if (!p.row_live) return false;
+  const int g1 = (min(m0 + BM, p.M) - 1) / p.rows_per_group;
+  for (int g = m0 / p.rows_per_group; g <= g1; ++g)
+    if (__ldg(p.row_live + g)) return false;
+  return true;
+}
+
 template <int BN, bool WS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -268,6 +278,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int it = it_first; it < it_end; it += it_step) {
         const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
+        if (tile_dead(p, m0)) continue;
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * L::kStageBytes;
@@ -291,6 +302,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
       }
       for (int it = it_first; it < it_end; it += it_step) {
+        if (tile_dead(p, (WS ? it : it / n_blks) * BM)) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -333,6 +345,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t drop_key = p.drop_thr16 ? dropout_key(effective_seed(p.drop_seed, p.drop_seed_dev), p.drop_salt) : 0u;
     for (int it = it_first; it < it_end; it += it_step) {
       const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
+      if (tile_dead(p, m0)) continue;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
@@ -634,8 +647,10 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
                                      int K, float alpha, const float* bias, int relu, const void* gate, int gate_fmt,
                                      int ld_gate, const void* residual, int res_fmt, int ld_res, float drop_p,
                                      uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* out16, int out_fmt,
-                                     float* out_f32, int ld_out, uint32_t* mask_out, void* stream) {
+                                     float* out_f32, int ld_out, uint32_t* mask_out, const uint8_t* row_live,
+                                     int rows_per_group, void* stream) {
   void* out_bf16 = out16;
+  TMP_REQUIRE(!row_live || rows_per_group > 0, "gemm: row_live needs rows_per_group > 0");
   TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
   TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok32(gate_fmt) || gate_fmt == FMT_MASK) &&
                   (!residual || fmt_ok32(res_fmt)),
@@ -669,6 +684,7 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.drop_seed = seed; p.drop_salt = salt; p.drop_seed_dev = seed_dev;
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   p.mask_out = mask_out;
+  p.row_live = row_live; p.rows_per_group = rows_per_group;
   CUtensorMap tmOut;
   if (out_bf16) {
     // 16-bit output written by TMA: boxes of [32 rows x 32 cols], 64B swizzle; rows >= M are clipped

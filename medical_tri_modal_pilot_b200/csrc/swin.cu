@@ -77,6 +77,18 @@ __device__ __forceinline__ void group_layernorm(float (&v)[NI][8], int sub, cons
   }
 }
 
+// Dead-image skipping: `live` (uint8 per image, or null) marks the images whose features have a consumer --
+// empty slots (img_time == 10, tri_mbt_vsltcls.py:229-231) and the images of img-missing samples are masked keys of a
+// de-selected stream, so their encoder work is skipped. Images are independent in every kernel of the encoder; a warp skips
+// its tokens when every image they belong to is dead. Skipped rows keep stale (finite or not) data; the LAST kernel of the
+// encoder writes zeros for dead images (`zero_dead`), because a masked key still meets 0 * V in the attention's P.V product.
+__device__ __forceinline__ bool all_dead(const uint8_t* __restrict__ live, int first_img, int last_img) {
+  if (!live) return false;
+  for (int n = first_img; n <= last_img; ++n)
+    if (__ldg(live + n)) return false;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // patch embedding: img fp32 [N,224,224] -> tokens [N*56*56, Cp] fp16 = LN(conv4x4s4(img)).
 // 4 lanes per token: lane `sub` fetches row `sub` of the 4x4 patch (one float4), the group exchanges rows by shuffle,
@@ -85,7 +97,8 @@ __device__ __forceinline__ void group_layernorm(float (&v)[NI][8], int sub, cons
 __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __restrict__ img, int n_tok,
                                                              const float* __restrict__ Wt /*[16][96]*/,
                                                              const float* __restrict__ bconv, const float* __restrict__ g,
-                                                             const float* __restrict__ b, __half* __restrict__ out, int Cp) {
+                                                             const float* __restrict__ b, __half* __restrict__ out, int Cp,
+                                                             const uint8_t* __restrict__ live) {
   constexpr int LPT = 4, TPW = 8;
   __shared__ __align__(16) float sW[16 * 96];
   __shared__ __align__(16) float sBc[96], sG[96], sBe[96];
@@ -95,6 +108,7 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
   const int lane = threadIdx.x & 31, sub = lane & (LPT - 1), grp = lane / LPT;
   const int stride = gridDim.x * (blockDim.x >> 5) * TPW;
   for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; base < n_tok; base += stride) {
+    if (all_dead(live, base / 3136, min(base + TPW - 1, n_tok - 1) / 3136)) continue;
     const bool valid = base + grp < n_tok;
     const int tok = valid ? base + grp : n_tok - 1;
     const int n = tok / 3136, r = tok % 3136, ty = r / 56, tx = r % 56;
@@ -141,7 +155,8 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
 template <int C, int H>
 __global__ void __launch_bounds__(256) ln_window_kernel(const __half* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ b, int n_img, int Cp, int shift,
-                                                        __half* __restrict__ out) {
+                                                        __half* __restrict__ out, const uint8_t* __restrict__ live,
+                                                        int zero_dead) {
   constexpr int W = H, LPT = C / 24, TPW = 32 / LPT, PER = H * W, NWW = W / WS;
   __shared__ __align__(16) float sG[C], sB[C];
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sG[i] = g[i]; sB[i] = b[i]; }
@@ -153,6 +168,13 @@ __global__ void __launch_bounds__(256) ln_window_kernel(const __half* __restrict
   for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; base < n_tok; base += stride) {
     const bool valid = base + grp < n_tok;
     const int tok = valid ? base + grp : n_tok - 1;
+    if (all_dead(live, base / PER, min(base + TPW - 1, n_tok - 1) / PER)) {
+      if (zero_dead && valid) {
+        __half* dst = out + (size_t)tok * Cp;
+        for (int c = sub; c < (Cp >> 3); c += LPT) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
     const int n = tok / PER, rw = tok % PER;
     const int win = rw / WT, t = rw % WT;
     const int ys = (win / NWW) * WS + t / WS, xs = (win % NWW) * WS + t % WS;     // position in the shifted map
@@ -166,8 +188,10 @@ __global__ void __launch_bounds__(256) ln_window_kernel(const __half* __restrict
     group_layernorm<3, LPT>(v, sub, sG, sB);
     if (valid) {
       __half* dst = out + (size_t)tok * Cp;
+      const bool dead = zero_dead && live && !__ldg(live + n);     // a dead image sharing the warp with a live one
 #pragma unroll
-      for (int i = 0; i < 3; ++i) *reinterpret_cast<uint4*>(dst + (sub + LPT * i) * 8) = pack8(v[i]);
+      for (int i = 0; i < 3; ++i)
+        *reinterpret_cast<uint4*>(dst + (sub + LPT * i) * 8) = dead ? make_uint4(0, 0, 0, 0) : pack8(v[i]);
       for (int c = C / 8 + sub; c < (Cp >> 3); c += LPT) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
     }
   }
@@ -180,7 +204,8 @@ __global__ void __launch_bounds__(256) ln_window_kernel(const __half* __restrict
 template <int C, int H>
 __global__ void __launch_bounds__(256) unwindow_add_ln_kernel(const __half* __restrict__ y, __half* __restrict__ x,
                                                               const float* __restrict__ g, const float* __restrict__ b,
-                                                              int n_img, int Cp, int shift, __half* __restrict__ hn) {
+                                                              int n_img, int Cp, int shift, __half* __restrict__ hn,
+                                                              const uint8_t* __restrict__ live) {
   constexpr int W = H, LPT = C / 24, TPW = 32 / LPT, PER = H * W, NWW = W / WS, NWH = H / WS;
   __shared__ __align__(16) float sG[C], sB[C];
   if (hn)
@@ -190,6 +215,7 @@ __global__ void __launch_bounds__(256) unwindow_add_ln_kernel(const __half* __re
   const int n_tok = n_img * PER;
   const int stride = gridDim.x * (blockDim.x >> 5) * TPW;
   for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; base < n_tok; base += stride) {
+    if (all_dead(live, base / PER, min(base + TPW - 1, n_tok - 1) / PER)) continue;
     const bool valid = base + grp < n_tok;
     const int tok = valid ? base + grp : n_tok - 1;
     const int n = tok / PER, r = tok % PER, yy = r / W, xx = r % W;
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(256) unwindow_add_ln_kernel(const __half* __re
 template <int C, int H>
 __global__ void __launch_bounds__(256) merge_ln_kernel(const __half* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ b, int n_img, int Cp,
-                                                       __half* __restrict__ out) {
+                                                       __half* __restrict__ out, const uint8_t* __restrict__ live) {
   constexpr int W = H, H2 = H / 2, W2 = W / 2, C4 = 4 * C, LPT = C / 12, TPW = 32 / LPT, CCH = C / 8;
   __shared__ __align__(16) float sG[C4], sB[C4];
   for (int i = threadIdx.x; i < C4; i += blockDim.x) { sG[i] = g[i]; sB[i] = b[i]; }
@@ -245,6 +271,7 @@ __global__ void __launch_bounds__(256) merge_ln_kernel(const __half* __restrict_
   const int n_tok = n_img * H2 * W2;
   const int stride = gridDim.x * (blockDim.x >> 5) * TPW;
   for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; base < n_tok; base += stride) {
+    if (all_dead(live, base / (H2 * W2), min(base + TPW - 1, n_tok - 1) / (H2 * W2))) continue;
     const bool valid = base + grp < n_tok;
     const int tok = valid ? base + grp : n_tok - 1;
     const int n = tok / (H2 * W2), r = tok % (H2 * W2), i2 = r / W2, j2 = r % W2;
@@ -309,7 +336,7 @@ __device__ __forceinline__ float ex2f(float x) {
 
 __global__ void __launch_bounds__(kAttnWarps * 32, 2)
 window_attn_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __restrict__ rel_bias, int n_win_total, int H,
-                   int W, int C, int shift, __half* __restrict__ out, int ld_out) {
+                   int W, int C, int shift, __half* __restrict__ out, int ld_out, const uint8_t* __restrict__ live) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
   float* sBias = reinterpret_cast<float*>(attn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,7 +365,9 @@ window_attn_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __re
   const int qr = lane >> 2, qc = (lane & 3) * 2;
   const float qs2 = 0.17677669529663687f * kL2e;    // 32^-0.5 (swin_transformer.py:177) in the log2 domain
   const float mask2 = -100.f * kL2e;                // attn_mask fill value (swin_transformer.py:195)
+  const int win_per_img = (H / WS) * (W / WS);
   for (int win = blockIdx.x * kAttnWarps + warp; win < n_win_total; win += gridDim.x * kAttnWarps) {
+    if (live && !__ldg(live + win / win_per_img)) continue;       // dead image (see all_dead)
     const __half* base = qkv + (size_t)win * WT * ld_qkv + head * HDIM;
     for (int i = lane; i < WT * 4; i += 32) {
       const int r = i >> 2, c8 = (i & 3) * 8;
@@ -485,12 +514,13 @@ int stage_index(int H, int W, int C) {
 
 }  // namespace
 
+// `live` (every tmp_swin_* call): optional uint8 [n_img], 0 = the image's features have no consumer, skip its work
 extern "C" int tmp_swin_patch_embed_ln(const float* img, int n_img, const float* Wt, const float* bconv, const float* g,
-                                       const float* b, void* out, int Cp, void* stream) {
+                                       const float* b, void* out, int Cp, const uint8_t* live, void* stream) {
   TMP_REQUIRE(img && Wt && bconv && g && b && out && n_img > 0 && n_img <= 600000 && Cp >= 96 && Cp % 8 == 0,
               "swin_patch_embed_ln: bad argument");
   const int n_tok = n_img * 3136;
-  patch_embed_ln_kernel<<<token_grid(n_tok, 8), 256, 0, (cudaStream_t)stream>>>(img, n_tok, Wt, bconv, g, b, (__half*)out, Cp);
+  patch_embed_ln_kernel<<<token_grid(n_tok, 8), 256, 0, (cudaStream_t)stream>>>(img, n_tok, Wt, bconv, g, b, (__half*)out, Cp, live);
   return tmp::check_launch("patch_embed_ln_kernel");
 }
 
@@ -502,8 +532,9 @@ extern "C" int tmp_swin_patch_embed_ln(const float* img, int n_img, const float*
     default: { CALL(768, 7); break; }                  \
   }
 
+// zero_dead: dead images' output rows are written as zeros (the last kernel of the encoder) instead of being skipped
 extern "C" int tmp_swin_ln_window(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp,
-                                  int shift, void* out, void* stream) {
+                                  int shift, void* out, const uint8_t* live, int zero_dead, void* stream) {
   const int si = stage_index(H, W, C);
   TMP_REQUIRE(x && g && b && out && n_img > 0 && n_img <= 600000 && si >= 0 && Cp >= C && Cp % 8 == 0 && shift >= 0 &&
                   shift < WS, "swin_ln_window: bad argument (H=%d W=%d C=%d Cp=%d shift=%d; Swin-T stages only)", H, W, C,
@@ -511,34 +542,34 @@ extern "C" int tmp_swin_ln_window(const void* x, const float* g, const float* b,
   if (H <= WS) shift = 0;   // window covers the whole map: torchvision disables the shift (swin_transformer.py:141-145)
 #define CALL(C_, H_)                                                                                              \
   ln_window_kernel<C_, H_><<<token_grid((long long)n_img * H_ * H_, 32 / (C_ / 24)), 256, 0, (cudaStream_t)stream>>>( \
-      (const __half*)x, g, b, n_img, Cp, shift, (__half*)out)
+      (const __half*)x, g, b, n_img, Cp, shift, (__half*)out, live, zero_dead)
   SWIN_STAGE_DISPATCH(si, CALL)
 #undef CALL
   return tmp::check_launch("ln_window_kernel");
 }
 
 extern "C" int tmp_swin_unwindow_add_ln(const void* y, void* x, const float* g, const float* b, int n_img, int H, int W,
-                                        int C, int Cp, int shift, void* hn, void* stream) {
+                                        int C, int Cp, int shift, void* hn, const uint8_t* live, void* stream) {
   const int si = stage_index(H, W, C);
   TMP_REQUIRE(y && x && n_img > 0 && n_img <= 600000 && si >= 0 && Cp >= C && Cp % 8 == 0 && shift >= 0 && shift < WS &&
                   (!hn || (g && b)), "swin_unwindow_add_ln: bad argument");
   if (H <= WS) shift = 0;
 #define CALL(C_, H_)                                                                                                    \
   unwindow_add_ln_kernel<C_, H_><<<token_grid((long long)n_img * H_ * H_, 32 / (C_ / 24)), 256, 0, (cudaStream_t)stream>>>( \
-      (const __half*)y, (__half*)x, g, b, n_img, Cp, shift, (__half*)hn)
+      (const __half*)y, (__half*)x, g, b, n_img, Cp, shift, (__half*)hn, live)
   SWIN_STAGE_DISPATCH(si, CALL)
 #undef CALL
   return tmp::check_launch("unwindow_add_ln_kernel");
 }
 
 extern "C" int tmp_swin_merge_ln(const void* x, const float* g, const float* b, int n_img, int H, int W, int C, int Cp,
-                                 void* out, void* stream) {
+                                 void* out, const uint8_t* live, void* stream) {
   const int si = stage_index(H, W, C);
   TMP_REQUIRE(x && g && b && out && n_img > 0 && n_img <= 600000 && si >= 0 && si < 3 && Cp >= C && Cp % 8 == 0,
               "swin_merge_ln: bad argument");
 #define CALL(C_, H_)                                                                                                       \
   merge_ln_kernel<C_, H_><<<token_grid((long long)n_img * (H_ / 2) * (H_ / 2), 32 / (C_ / 12)), 256, 0, (cudaStream_t)stream>>>( \
-      (const __half*)x, g, b, n_img, Cp, (__half*)out)
+      (const __half*)x, g, b, n_img, Cp, (__half*)out, live)
   switch (si) {
     case 0: { CALL(96, 56); break; }
     case 1: { CALL(192, 28); break; }
@@ -549,7 +580,7 @@ extern "C" int tmp_swin_merge_ln(const void* x, const float* g, const float* b, 
 }
 
 extern "C" int tmp_swin_window_attn(const void* qkv, int ld_qkv, const float* rel_bias, int n_img, int H, int W, int C,
-                                    int heads, int shift, void* out, int ld_out, void* stream) {
+                                    int heads, int shift, void* out, int ld_out, const uint8_t* live, void* stream) {
   TMP_REQUIRE(qkv && rel_bias && out && n_img > 0 && H % WS == 0 && W % WS == 0 && heads > 0 && heads <= 65535 &&
                   C == heads * HDIM && ld_qkv >= 3 * C && ld_qkv % 8 == 0 && ld_out >= C && ld_out % 8 == 0 && shift >= 0 &&
                   shift < WS, "swin_window_attn: bad argument");
@@ -571,6 +602,6 @@ extern "C" int tmp_swin_window_attn(const void* qkv, int ld_qkv, const float* re
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)heads);
   window_attn_kernel<<<grid, kAttnWarps * 32, kAttnSmem, (cudaStream_t)stream>>>(
-      (const __half*)qkv, ld_qkv, rel_bias, (int)n_win, H, W, C, H > WS ? shift : 0, (__half*)out, ld_out);
+      (const __half*)qkv, ld_qkv, rel_bias, (int)n_win, H, W, C, H > WS ? shift : 0, (__half*)out, ld_out, live);
   return tmp::check_launch("window_attn_kernel");
 }

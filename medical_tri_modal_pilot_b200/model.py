@@ -158,6 +158,7 @@ class TRI_MBT_VSLTCLS(nn.Module):
         self.fc_list = nn.Sequential(nn.Linear(2 * D, D), nn.BatchNorm1d(D), self.activations["relu"], nn.Linear(D, 1))
         self._fused = FusedPath(self)
         self.native_swin = True      # frozen image encoder through swin_feed.SwinFeed (False: stock torchvision forward)
+        self.swin_skip_dead = True   # skip the encoder work of images that no key of the img stream can see
         self.img_autocast = True     # run the frozen Swin in bf16 (its output feeds an fp16 tensor-core GEMM anyway)
         # precision mode: "fp16" (tensor-core plan, the reference's autocast dtype) or "fp32" (north-star FP32 parity mode:
         # fp32 storage, bf16x3-split tensor-core GEMMs, fp32 attention; runtime.FusedPath.precision). Not a reference flag:
@@ -207,10 +208,25 @@ class TRI_MBT_VSLTCLS(nn.Module):
         m = (missing.to(torch.long) != 0).to(torch.long)
         return 2 + m if self.input_types == "vslt_txt" else 1 + 2 * m
 
-    def encode_images(self, img, missing=None, ready=None):
+    def live_images(self, img_time, missing):
+        """uint8 [B*n_img]: which images have a consumer. With --multiimages 1 the img stream's key length is 49 * #(img_time
+        != 10) (tri_mbt_vsltcls.py:229-232), i.e. the FIRST count_b slots of a sample are visible, whatever their position
+        in time; the rest are masked keys. Samples whose `missing` code de-selects the img stream (2, 3) have no live image.
+        With --multiimages 0 the stream is unmasked (:144,:234): only the missing code decides."""
+        B = missing.shape[0]
+        present = ~((missing == 2) | (missing == 3))
+        if self.multiimages == 1:
+            cnt = (img_time.reshape(B, -1) != 10).sum(1, keepdim=True)
+            live = (torch.arange(img_time.numel() // B, device=missing.device)[None, :] < cnt) & present[:, None]
+        else:
+            live = present[:, None]
+        return live.reshape(-1).to(torch.uint8).contiguous()
+
+    def encode_images(self, img, missing=None, ready=None, img_time=None):
         """Frozen image encoder (reference tri_mbt_vsltcls.py:205-209: reshape(-1,1,224,224), torch.no_grad).
         Returns [B*n_img, 49, 768] fp16 (the A operand of the 768->256 projection GEMM). `ready`: optional per-chunk CUDA
-        events of a staged upload (swin_feed.SwinFeed.__call__)."""
+        events of a staged upload (swin_feed.SwinFeed.__call__). With `missing` and `img_time` given (the fused path does),
+        images without a consumer are skipped and come out as zero rows (`live_images`; exact: SURVEY Appendix A)."""
         f32 = self._fused.precision == "fp32"
 
         def wait_all():
@@ -224,7 +240,10 @@ class TRI_MBT_VSLTCLS(nn.Module):
             img = img.reshape(-1, 1, 224, 224)
         with torch.no_grad():
             if self.native_swin:
-                return self._swin_feed()(img, ready=ready)     # sm_100a kernels (swin_feed.py), fp16 [N,49,768]
+                live = None
+                if self.swin_skip_dead and missing is not None and img_time is not None:
+                    live = self.live_images(img_time, missing)
+                return self._swin_feed()(img, ready=ready, live=live)     # sm_100a kernels (swin_feed.py), fp16 [N,49,768]
             wait_all()
             if self.img_autocast:
                 f = self._img_encoder_bf16()(img.to(torch.bfloat16))

@@ -134,9 +134,10 @@ def layernorm_bwd_attn(dy, x, dres, gamma, dx, dgamma, dbeta, attn_O, T, delta, 
 
 
 def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residual=None, alpha=1.0, drop_p=0.0, seed=0,
-         salt=0, M=None, seed_dev=None, mask_out=None):
+         salt=0, M=None, seed_dev=None, mask_out=None, row_live=None, rows_per_group=0):
     """out[M,N] = residual + dropout(gate>0 ? relu?(alpha*A@Bw^T + bias) : 0). A [M,K], Bw [N,K]: fp16 or bf16.
     mask_out (int32 [M, N/32]): receives the (result > 0) bit pattern; an int32 `gate` is read as such a bit mask.
+    row_live (uint8 per group of rows_per_group rows): output tiles that only cover dead groups are skipped.
     fp32 mode (A and Bw fp32): both operands are split into bf16x3 along K and the same tcgen05 kernel accumulates the six
     partial products in fp32; `out` is then an fp32 tensor, gate / residual are fp32."""
     if _f32(A):
@@ -158,7 +159,7 @@ def gemm(A, Bw, out=None, out_f32=None, bias=None, relu=False, gate=None, residu
                                             gate_fmt, gate.shape[-1] if gate is not None else 0, ptr(residual),
                                             _fmt(residual), residual.shape[-1] if residual is not None else 0,
                                             float(drop_p), seed, salt, ptr(seed_dev), ptr(out), _fmt(out), ptr(out_f32),
-                                            ld_out, ptr(mask_out), stream_ptr()),
+                                            ld_out, ptr(mask_out), ptr(row_live), int(rows_per_group), stream_ptr()),
           "tmp_gemm_bias_act_fwd")
 
 
@@ -246,28 +247,29 @@ def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev
 
 
 # ---- image-encoder feed (csrc/swin.cu) -------------------------------------------------------------------------
-def swin_patch_embed_ln(img, Wt, bconv, g, b, out, Cp):
+# `live`: optional uint8 [n_img] device tensor, 0 = skip the image (its features have no consumer)
+def swin_patch_embed_ln(img, Wt, bconv, g, b, out, Cp, live=None):
     n_img = img.numel() // (224 * 224)
     _cuda_contig(img, torch.float32, "img")
     check(_lib.load().tmp_swin_patch_embed_ln(ptr(img), n_img, ptr(Wt), ptr(bconv), ptr(g), ptr(b), ptr(out), Cp,
-                                              stream_ptr()), "tmp_swin_patch_embed_ln")
+                                              ptr(live), stream_ptr()), "tmp_swin_patch_embed_ln")
 
 
-def swin_ln_window(x, g, b, n_img, H, C, Cp, shift, out):
-    check(_lib.load().tmp_swin_ln_window(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, shift, ptr(out), stream_ptr()),
-          "tmp_swin_ln_window")
+def swin_ln_window(x, g, b, n_img, H, C, Cp, shift, out, live=None, zero_dead=False):
+    check(_lib.load().tmp_swin_ln_window(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, shift, ptr(out), ptr(live),
+                                         int(zero_dead), stream_ptr()), "tmp_swin_ln_window")
 
 
-def swin_window_attn(qkv, rel_bias, n_img, H, C, heads, shift, out):
+def swin_window_attn(qkv, rel_bias, n_img, H, C, heads, shift, out, live=None):
     check(_lib.load().tmp_swin_window_attn(ptr(qkv), qkv.shape[-1], ptr(rel_bias), n_img, H, H, C, heads, shift, ptr(out),
-                                           out.shape[-1], stream_ptr()), "tmp_swin_window_attn")
+                                           out.shape[-1], ptr(live), stream_ptr()), "tmp_swin_window_attn")
 
 
-def swin_unwindow_add_ln(y, x, g, b, n_img, H, C, Cp, shift, hn):
+def swin_unwindow_add_ln(y, x, g, b, n_img, H, C, Cp, shift, hn, live=None):
     check(_lib.load().tmp_swin_unwindow_add_ln(ptr(y), ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, shift, ptr(hn),
-                                               stream_ptr()), "tmp_swin_unwindow_add_ln")
+                                               ptr(live), stream_ptr()), "tmp_swin_unwindow_add_ln")
 
 
-def swin_merge_ln(x, g, b, n_img, H, C, Cp, out):
-    check(_lib.load().tmp_swin_merge_ln(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, ptr(out), stream_ptr()),
+def swin_merge_ln(x, g, b, n_img, H, C, Cp, out, live=None):
+    check(_lib.load().tmp_swin_merge_ln(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, ptr(out), ptr(live), stream_ptr()),
           "tmp_swin_merge_ln")

@@ -327,7 +327,8 @@ class FusedPath:
         # encoder runs at the head of the img lane.
         self._fork()
         with self._lane(1):
-            img_feats = m.encode_images(img, ready=ready.get("img"))
+            img_feats = m.encode_images(img, missing=ctx["missing"] if self.skip_missing else None, ready=ready.get("img"),
+                                        img_time=ctx["img_time"])
             ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(adt).contiguous()
             ops.gemm(ctx["img16"], Wop("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[1]["X"][0], **self._prologue_args(1, ctx))

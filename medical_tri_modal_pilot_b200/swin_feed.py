@@ -120,10 +120,12 @@ class SwinFeed:
         return k if (k > 1 and n_img >= 32 * k and n_img % k == 0) else 1
 
     @torch.no_grad()
-    def __call__(self, img, ready=None):
+    def __call__(self, img, ready=None, live=None):
         """img fp32 [N,1,224,224] (or [N,224,224]) in [0,1] -> features fp16 [N,49,768] = norm(features(img)).
         ready: optional list of CUDA events, one per chunk (`n_chunks(N)` of them): chunk c is not touched before
-        ready[c] has fired (its pixels are still being uploaded)."""
+        ready[c] has fired (its pixels are still being uploaded).
+        live: optional uint8 [N] device tensor; images with 0 are skipped by every kernel (their features have no
+        consumer) and come out as zero rows."""
         n_img = img.numel() // (224 * 224)
         if img.dtype != torch.float32 or not img.is_contiguous():
             if ready is not None:                       # a cast reads every pixel: all chunks must have landed
@@ -139,30 +141,34 @@ class SwinFeed:
         for c in range(k):
             if ready is not None:
                 torch.cuda.current_stream().wait_event(ready[c] if len(ready) == k else ready[-1])
-            self._stages(img[c * nc:(c + 1) * nc], nc, ws, 0, 2, ws[2]["x"][c * rows3:(c + 1) * rows3])
-        self._stages(None, n_img, ws, 2, 4, None)
-        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, self.out)
+            lv = None if live is None else live[c * nc:(c + 1) * nc]
+            self._stages(img[c * nc:(c + 1) * nc], nc, ws, 0, 2, ws[2]["x"][c * rows3:(c + 1) * rows3], lv)
+        self._stages(None, n_img, ws, 2, 4, None, live)
+        ops.swin_ln_window(ws[3]["x"], self.norm["g"], self.norm["b"], n_img, 7, 768, 768, 0, self.out, live=live,
+                           zero_dead=True)
         return self.out.view(n_img, 49, 768)
 
-    def _stages(self, img, n_img, ws, s0, s1, x_next):
+    def _stages(self, img, n_img, ws, s0, s1, x_next, live=None):
         """Stages [s0, s1) on n_img images. Stage 0 starts from the pixels; the merged output of stage s1-1 goes to `x_next`
         (a slice of the next stage's input) when s1 < 4."""
         if s0 == 0:
             e = self.embed
-            ops.swin_patch_embed_ln(img, e["Wt"], e["b"], e["g"], e["be"], ws[0]["x"], STAGES[0][4])
+            ops.swin_patch_embed_ln(img, e["Wt"], e["b"], e["g"], e["be"], ws[0]["x"], STAGES[0][4], live=live)
         for si in range(s0, s1):
             C, heads, H, depth, Cp = STAGES[si]
             w = ws[si]
+            rl = dict(row_live=live, rows_per_group=H * H) if live is not None else {}      # token rows are image-major
             for b in self.blocks[si]:
                 sh = b["shift"]
-                ops.swin_ln_window(w["x"], b["n1g"], b["n1b"], n_img, H, C, Cp, sh, w["xw"])
-                ops.gemm(w["xw"], b["wqkv"], out=w["qkv"], bias=b["bqkv"])
-                ops.swin_window_attn(w["qkv"], b["rel"], n_img, H, C, heads, sh, w["ao"])
-                ops.gemm(w["ao"], b["wproj"], out=w["y"], bias=b["bproj"])
-                ops.swin_unwindow_add_ln(w["y"], w["x"], b["n2g"], b["n2b"], n_img, H, C, Cp, sh, w["hn"])
-                ops.gemm(w["hn"], b["wfc1"], out=w["a"], bias=b["bfc1"], relu=2)
-                ops.gemm(w["a"], b["wfc2"], out=w["x"], bias=b["bfc2"], residual=w["x"])
+                ops.swin_ln_window(w["x"], b["n1g"], b["n1b"], n_img, H, C, Cp, sh, w["xw"], live=live)
+                ops.gemm(w["xw"], b["wqkv"], out=w["qkv"], bias=b["bqkv"], **rl)
+                ops.swin_window_attn(w["qkv"], b["rel"], n_img, H, C, heads, sh, w["ao"], live=live)
+                ops.gemm(w["ao"], b["wproj"], out=w["y"], bias=b["bproj"], **rl)
+                ops.swin_unwindow_add_ln(w["y"], w["x"], b["n2g"], b["n2b"], n_img, H, C, Cp, sh, w["hn"], live=live)
+                ops.gemm(w["hn"], b["wfc1"], out=w["a"], bias=b["bfc1"], relu=2, **rl)
+                ops.gemm(w["a"], b["wfc2"], out=w["x"], bias=b["bfc2"], residual=w["x"], **rl)
             if si < 3:
                 m = self.merges[si]
-                ops.swin_merge_ln(w["x"], m["g"], m["b"], n_img, H, C, Cp, w["mg"])
-                ops.gemm(w["mg"], m["w"], out=(x_next if si == s1 - 1 and x_next is not None else ws[si + 1]["x"]))
+                ops.swin_merge_ln(w["x"], m["g"], m["b"], n_img, H, C, Cp, w["mg"], live=live)
+                rm = dict(row_live=live, rows_per_group=(H // 2) * (H // 2)) if live is not None else {}
+                ops.gemm(w["mg"], m["w"], out=(x_next if si == s1 - 1 and x_next is not None else ws[si + 1]["x"]), **rm)

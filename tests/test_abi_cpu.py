@@ -38,7 +38,7 @@ def test_argument_errors_are_reported_not_crashed():
     """Argument validation runs before any CUDA call, so it can be exercised on the CPU box."""
     lib = _lib.load()
     rc = lib.tmp_gemm_bias_act_fwd(None, 0, 0, None, 0, 0, 1, 1, 1, 1.0, None, 0, None, 0, 0, None, 0, 0, 0.0, 0, 0, None,
-                                   None, 0, None, 0, None, None)
+                                   None, 0, None, 0, None, None, 0, None)
     assert rc < 0 and "null operand" in _lib.last_error()
     rc = lib.tmp_mma_attn_fwd(1, None, 1, 1, 3, 1, 8, 1, 128, 1, None)
     assert rc < 0 and "H==4" in _lib.last_error()

@@ -147,3 +147,56 @@ def test_model_uses_native_feed_and_matches_stock_path():
     r = model.encode_images(img, None).float()
     mx, rm = _err(a, r)
     assert a.shape == (6, 49, 768) and mx < 2e-2 and rm < 1e-2, (mx, rm)
+
+
+@pytest.mark.parametrize("n_img", [5, 96])
+def test_swin_feed_skips_dead_images(n_img):
+    """`live` mask: live images give the same features as the unmasked run, dead images come out as
+    zero rows whatever their workspace held before (NaN-poisoned by the conftest fixture). n_img = 96 takes the 3-chunk
+    path of the high-resolution stages."""
+    from medical_tri_modal_pilot_b200.swin_feed import SwinFeed
+    m = _randomised_swin()
+    feed = SwinFeed(m)
+    img = torch.rand(n_img, 1, 224, 224, device="cuda")
+    full = feed(img).clone()
+    g = torch.Generator().manual_seed(3)
+    live = (torch.rand(n_img, generator=g) < 0.4).to(torch.uint8)
+    live[0], live[-1] = 1, 0
+    for ws in feed.ws:                      # poison every workspace the dead images would have written
+        for t in ws.values():
+            if torch.is_tensor(t) and t is not ws.get("ao"):
+                t.fill_(float("nan"))
+    got = feed(img, live=live.cuda())
+    lv = live.bool()
+    assert torch.isfinite(got.float()).all()
+    assert (got[~lv] == 0).all()
+    assert torch.equal(got[lv], full[lv])
+
+
+def test_model_logits_unchanged_by_dead_image_skipping():
+    """Whole model on pixels with mixed missing codes and partly filled image slots: skipping the dead images' encoder work
+    changes no logit (their keys are masked / their stream is de-selected)."""
+    from builder.models import get_model
+    from medical_tri_modal_pilot_b200 import synth
+    from medical_tri_modal_pilot_b200.config import make_args
+    B, L = 8, 60
+    args = make_args(transformer_num_layers=2, multiimages=1, mbt_only_vslt=1, input_types="vslt_img_txt", imgtxt_time=1,
+                     dropout=0.0, batch_size=B, img_pretrain="No")
+    args.device = torch.device("cuda")
+    torch.manual_seed(0)
+    model = get_model(args)(args).cuda().train()
+    hb = synth.make_batch(B, L, n_img=3, seed=21, missing_mode="mixed", with_pixels=True, feats=False)
+    b = {k: v.cuda() for k, v in hb.items()}
+
+    def run():
+        with torch.no_grad():
+            out, _, _ = model(b["x"], None, None, None, None, b["age"], b["gen"], b["input_lengths"], b["txts"], b["txt_lengths"],
+                              b["img"], b["missing"], None, b["img_time"], b["txt_time"], "train", None, None)
+        return out
+    live = model.live_images(b["img_time"].float(), b["missing"])
+    assert 0 < int(live.sum()) < live.numel()
+    model.swin_skip_dead = True
+    a = run()
+    model.swin_skip_dead = False
+    r = run()
+    assert torch.equal(a, r)
