@@ -111,6 +111,21 @@ def main():
             add(f"wgradb_{nm}_T{T}", lambda dY=dY, A=A, dW=dW, cs=cs: ops.gemm_wgrad(dY, A, dW, dbias=cs), 2.0 * M * N * K,
                 None, f"M={M} N={N} K={K} (+ fused bias gradient)")
             add(f"colsum_{nm}_T{T}", lambda dY=dY, cs=cs: ops.colsum(dY, cs), None, M * N * 2.0, f"M={M} N={N}")
+        # dgrads of the same block: FFN2 dgrad is gated by the 1-bit ReLU/dropout mask FFN1 wrote in the forward pass
+        gy = torch.randn(M, 256, device=dev).half()
+        w2t = (torch.randn(1024, 256, device=dev) / 16).half()
+        am = torch.randint(-2 ** 31, 2 ** 31 - 1, (M, 32), device=dev, dtype=torch.int32)
+        ga = torch.empty(M, 1024, device=dev, dtype=torch.float16)
+        add(f"dgrad_ffn2_gated_T{T}", lambda gy=gy, w2t=w2t, ga=ga, am=am: ops.gemm(gy, w2t, out=ga, gate=am, alpha=1.0 / 0.9),
+            2.0 * M * 1024 * 256, None, f"M={M} N=1024 K=256, 1-bit gate")
+        w1t = (torch.randn(256, 1024, device=dev) / 32).half()
+        ghn = torch.empty(M, 256, device=dev, dtype=torch.float16)
+        add(f"dgrad_ffn1_T{T}", lambda ga=ga, w1t=w1t, ghn=ghn: ops.gemm(ga, w1t, out=ghn), 2.0 * M * 1024 * 256, None,
+            f"M={M} N=256 K=1024")
+        gqkv = torch.randn(M, 768, device=dev).half()
+        wqt = (torch.randn(256, 768, device=dev) / 28).half()
+        add(f"dgrad_qkv_T{T}", lambda gqkv=gqkv, wqt=wqt, ghn=ghn: ops.gemm(gqkv, wqt, out=ghn), 2.0 * M * 768 * 256, None,
+            f"M={M} N=256 K=768")
         x = torch.randn(M, 256, device=dev).half()
         y = torch.empty_like(x)
         g = torch.ones(256, device=dev); b = torch.zeros(256, device=dev)
