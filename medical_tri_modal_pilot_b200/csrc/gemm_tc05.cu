@@ -623,8 +623,11 @@ int launch_wgrad(const CUtensorMap& tmY, const CUtensorMap& tmX, const CUtensorM
     }
     attr_set = true;
   }
+  // one CTA per SM (197 KB of shared memory): tiles * splits must not exceed the SM count, or the few CTAs of a second
+  // wave double the kernel time (8 tiles x 19 splits = 152 CTAs on 148 SMs ran as two waves)
   const int tiles = (N / 128) * (K / BNW);
-  int splits = (tmp::num_sms() + tiles - 1) / tiles;
+  int splits = tmp::num_sms() / tiles;
+  if (splits < 1) splits = 1;
   int rows_per_split = (M + splits - 1) / splits;
   rows_per_split = ((rows_per_split + BK - 1) / BK) * BK;
   if (rows_per_split < BK) rows_per_split = BK;
@@ -666,6 +669,8 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   const int m_blks = (M + BM - 1) / BM;
   int BN = 256;
   if (N % 256 != 0 || m_blks * (N / 256) < sms) BN = 128;
+  static const int bn_force = getenv("TMP_B200_GEMM_BN") ? atoi(getenv("TMP_B200_GEMM_BN")) : 0;   // A/B timing only
+  if (bn_force == 128 || (bn_force == 256 && N % 256 == 0)) BN = bn_force;
   CUtensorMap tmA, tmB;
   int rc = tmp::encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
   if (rc) return rc;
