@@ -59,22 +59,23 @@ struct EpiParams {
 template <int BN, bool WS>
 struct SmemLayout {
   static constexpr int kWsMaxK = (BN == 256) ? 256 : 512;
-  static constexpr int kStages = WS ? 4 : ((BN == 256) ? 3 : 4);
+  static constexpr int kStages = WS ? 4 : ((BN == 256) ? 4 : 5);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;                          // one 64-wide K slice of B
   static constexpr int kBResBytes = WS ? BN * kWsMaxK * 2 : 0;         // resident B (WS): K/64 slices
   static constexpr int kRingOffset = kBResBytes;
   static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
   static constexpr int kOutOffset = kRingOffset + kStages * kStageBytes;
-  static constexpr int kOutBufs = WS ? 1 : 2;                          // per epilogue warp: [32 rows x 64 B] boxes
+  static constexpr int kOutBufs = 1;                                   // per epilogue warp: [32 rows x 64 B] boxes
   static constexpr int kOutBoxBytes = 2048;
   static constexpr int kOutBytes = kEpiWarps * kOutBufs * kOutBoxBytes;
   static constexpr int kBiasOffset = kOutOffset + kOutBytes;
-  static constexpr int kBiasFloats = WS ? BN : kBiasSmemFloats;
+  static constexpr int kBiasFloats = WS ? BN : (BN == 256 ? 256 : kBiasSmemFloats);
   static constexpr int kBarOffset = kBiasOffset + kBiasFloats * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
 static_assert(SmemLayout<256, true>::kTotal <= 232448 && SmemLayout<128, true>::kTotal <= 232448, "WS smem budget");
+static_assert(SmemLayout<256, false>::kTotal <= 232448 && SmemLayout<128, false>::kTotal <= 232448, "smem budget");
 
 // erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 output rounding):
 // erf(z) = 1 - q, q = (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x| / sqrt 2. With that,
@@ -237,7 +238,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int it_step = WS ? (int)gridDim.x / n_blks : (int)gridDim.x;
   const int it_end = WS ? m_blks : m_blks * n_blks;
   const int n_fixed = WS ? ((int)blockIdx.x % n_blks) * BN : 0;
-  const bool bias_in_smem = p.bias && (WS || p.N <= kBiasSmemFloats);
+  const bool bias_in_smem = p.bias && (WS || p.N <= L::kBiasFloats);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
