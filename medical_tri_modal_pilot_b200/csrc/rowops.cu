@@ -117,7 +117,7 @@ struct LnAttnArgs {
 };
 
 template <int ST, bool ATTN>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                             const void* __restrict__ dres,
                                                             const float* __restrict__ gamma, long long rows,
                                                             void* __restrict__ dx, void* __restrict__ dx_drop,
@@ -136,22 +136,29 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   // Software-pipelined over rows: the loads of the NEXT row (x, dy, dres, O: up to 64 B per lane) are issued before the
   // current row is reduced and stored, so every warp keeps two rows of loads in flight. One row at a time left the kernel
-  // latency-bound at 2.5 TB/s (54 us for 64 320 rows, profiles/r2b_step_breakdown.txt).
+  // latency-bound at 2.5 TB/s (54 us for 64 320 rows, profiles/r2b_step_breakdown.txt). The row in flight is held in its
+  // storage form (Raw8: 4 registers per tensor instead of 8) and the launch bounds ask for 3 resident blocks (80
+  // registers, 48 B of spills): 24 instead of 16 warps per SM took the cold-L2 time from 46 to 34 us (57 -> 44 us with the
+  // attention extras, 4.5 TB/s); 4 blocks (64 registers) spill too much and are slower again.
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  float c[8], gy[8], a[8], o[8];
-  auto fetch = [&](long long r, float (&c_)[8], float (&gy_)[8], float (&a_)[8], float (&o_)[8]) {
+  Raw8<ST> rc, rgy, ra, ro;   // the row in flight, in storage form (4 registers per 16-bit tensor)
+  auto fetch = [&](long long r) {
     const size_t at = (size_t)r * D + lane * 8;
-    ld8<ST>(x, at, c_);
-    ld8<ST>(dy, at, gy_);
-    if (dres) ld8<ST>(dres, at, a_);
-    if (ATTN) ld8<ST>(at_.O, at, o_);
+    rc.load(x, at);
+    rgy.load(dy, at);
+    if (dres) ra.load(dres, at);
+    if (ATTN) ro.load(at_.O, at);
   };
-  if (row < rows) fetch(row, c, gy, a, o);
+  if (row < rows) fetch(row);
   for (; row < rows; row += warps) {
     const size_t at = (size_t)row * D + lane * 8;
-    float cn[8], gyn[8], an[8], on[8];
+    float c[8], gy[8], a[8], o[8];
+    rc.get(c);
+    rgy.get(gy);
+    if (dres) ra.get(a);
+    if (ATTN) ro.get(o);
     const long long nxt = row + warps;
-    if (nxt < rows) fetch(nxt, cn, gyn, an, on);
+    if (nxt < rows) fetch(nxt);
     float r, sd;
     ln_stats(c, r, sd);
     float gbar = 0.f, gc = 0.f;
@@ -192,10 +199,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       const uint32_t base = (uint32_t)row * D + lane * 8;
       dropout_apply_run<8>(out, dropout_key(effective_seed(seed, seed_dev), salt), base, drop_thr16, drop_scale);
       st8<ST>(dx_drop, at, out);
-    }
-    if (nxt < rows) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { c[i] = cn[i]; gy[i] = gyn[i]; a[i] = an[i]; o[i] = on[i]; }
     }
   }
 #pragma unroll
@@ -457,7 +460,7 @@ static int layernorm_bwd_impl(int st, const void* dy, const void* x, const void*
   TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: dropout p out of range");
   if (rows == 0) return TMP_OK;
   long long blocks = (rows + 7) / 8;
-  if (blocks > 4LL * tmp::num_sms()) blocks = 4LL * tmp::num_sms();
+  if (blocks > 3LL * tmp::num_sms()) blocks = 3LL * tmp::num_sms();   // 3 resident blocks per SM (launch bounds): one wave   // 3 resident blocks per SM (launch bounds): one wave
   const uint32_t thr = drop_p > 0.f ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const LnAttnArgs none{nullptr, nullptr, nullptr, 1, 1};
@@ -479,7 +482,7 @@ extern "C" int tmp_layernorm_bwd_attn(const void* dy, const void* x, const void*
   TMP_REQUIRE(T > 0 && T_lse >= T && rows % T == 0, "layernorm_bwd_attn: rows must be B*T and T_lse >= T");
   if (rows == 0) return TMP_OK;
   long long blocks = (rows + 7) / 8;
-  if (blocks > 4LL * tmp::num_sms()) blocks = 4LL * tmp::num_sms();
+  if (blocks > 3LL * tmp::num_sms()) blocks = 3LL * tmp::num_sms();   // 3 resident blocks per SM (launch bounds): one wave
   const LnAttnArgs a{attn_O, delta, dQKV, T, T_lse};
   layernorm_bwd_kernel<ACT, true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, dres, gamma, rows, dx, nullptr, 0u, 1.f,
                                                                                 0u, 0u, nullptr, dgamma, dbeta, a);

@@ -70,4 +70,35 @@ __device__ __forceinline__ void st8(void* __restrict__ base, size_t elem, const 
   else store8<ST == tc05::FMT_F32 ? tc05::FMT_F16 : ST>(static_cast<h16*>(base) + elem, v);
 }
 
+// The same 8 elements kept in their storage form (4 registers for a 16-bit tensor): what a software-pipelined loop holds for
+// the NEXT row while the current one is processed.
+template <int ST>
+struct Raw8 {
+  uint4 u;
+  __device__ __forceinline__ void load(const void* __restrict__ base, size_t elem) {
+    u = *reinterpret_cast<const uint4*>(static_cast<const h16*>(base) + elem);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = tc05::unpack2<ST>(w[t]);
+      v[2 * t] = f.x;
+      v[2 * t + 1] = f.y;
+    }
+  }
+};
+template <>
+struct Raw8<tc05::FMT_F32> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const void* __restrict__ base, size_t elem) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem);
+    a = p[0];
+    b = p[1];
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 }  // namespace rw
