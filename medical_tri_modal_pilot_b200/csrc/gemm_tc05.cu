@@ -50,7 +50,31 @@ struct EpiParams {
   uint16_t* out;          // [M, ld_out] 16-bit in out_fmt (or null) -- written through tmOut (TMA store)
   float* out_f32;         // [M, ld_out] fp32 (or null) -- direct stores
   int ld_out;
+  int mode;               // >= 0: compile-time specialised epilogue (bit set of EPI_*), -1: the generic run-time one
 };
+
+// Epilogue features that exist as compile-time specialisations. The generic epilogue tests every feature at run time in
+// ~1 600 SASS instructions of branchy code; with 16 epilogue warps a bias-only [128 x 256] tile took ~3 500 cycles of
+// epilogue against 2 048 cycles of MMA, i.e. the QKV GEMM was epilogue-bound (43 us; 34 us with a straight-line epilogue).
+enum : int {
+  EPI_BIAS = 1,        // + bias (staged in shared memory, already multiplied by bias_scale)
+  EPI_RELU = 2,
+  EPI_GELU = 4,
+  EPI_GATEMASK = 8,    // multiply by the 1-bit gate written by an earlier mask_out
+  EPI_DROPFOLD = 16,   // dropout with 1/(1-p) folded into alpha / bias: zeroing only
+  EPI_MASKOUT = 32,    // write the (result > 0) bit mask
+  EPI_RES16 = 64,      // + fp16 residual
+  EPI_ALPHA = 128,     // accumulator scale != 1
+};
+// the hot call sites of the training step and the image-encoder feed (everything else runs the generic epilogue)
+#define TMP_EPI_MODES(X)                                                                                              \
+  X(0)                                                        /* dgrads: plain */                                     \
+  X(EPI_BIAS)                                                 /* QKV, 768->256 projections, Swin qkv / proj / fc2 */   \
+  X(EPI_BIAS | EPI_RELU | EPI_DROPFOLD | EPI_MASKOUT | EPI_ALPHA)   /* FFN1 forward */                                \
+  X(EPI_BIAS | EPI_DROPFOLD | EPI_RES16 | EPI_ALPHA)          /* FFN2 forward */                                      \
+  X(EPI_GATEMASK | EPI_ALPHA)                                 /* FFN2 input gradient */                                \
+  X(EPI_BIAS | EPI_GELU)                                      /* Swin fc1 */
+
 
 // WS ("weight-stationary") variant: for K <= kWsMaxK the whole B operand of an n-block ([BN x K], <= 128 KB) is loaded ONCE per
 // CTA and stays in shared memory while the CTA walks over m-tiles of that n-block; the TMA ring then carries A tiles only.
@@ -202,12 +226,184 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const EpiParams& p
   }
 }
 
+// Compile-time specialised form (MODE >= 0: only the features in the bit set, 16-bit fp16 output, bias in shared memory,
+// fp16 residual); MODE < 0 = the generic function above.
+template <int MODE>
+__device__ __forceinline__ void epilogue_math_t(float (&v)[32], const EpiParams& p, const float* sbias, int row, bool row_ok,
+                                                int col0, uint32_t drop_key) {
+  if constexpr (MODE < 0) {
+    epilogue_math(v, p, sbias, row, row_ok, col0, drop_key);
+  } else {
+    if constexpr ((MODE & EPI_BIAS) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + j);   // smem broadcast
+        if constexpr ((MODE & EPI_ALPHA) != 0) {
+          v[j] = fmaf(v[j], p.alpha, b.x); v[j + 1] = fmaf(v[j + 1], p.alpha, b.y);
+          v[j + 2] = fmaf(v[j + 2], p.alpha, b.z); v[j + 3] = fmaf(v[j + 3], p.alpha, b.w);
+        } else {
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+    } else if constexpr ((MODE & EPI_ALPHA) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    }
+    if constexpr ((MODE & EPI_RELU) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if constexpr ((MODE & EPI_GELU) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gelu_erf_pair(v[j], v[j + 1]);
+    }
+    if constexpr ((MODE & EPI_GATEMASK) != 0) {
+      if (row_ok) {
+        const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(p.gate) + (size_t)row * p.ld_gate + (col0 >> 5));
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (!((m >> j) & 1u)) v[j] = 0.f;
+      }
+    }
+    if constexpr ((MODE & EPI_DROPFOLD) != 0) {
+      const uint32_t idx0 = (uint32_t)row * (uint32_t)p.N + (uint32_t)col0;
+      dropout_zero_run<32>(v, drop_key, idx0, p.drop_thr16);
+    }
+    if constexpr ((MODE & EPI_MASKOUT) != 0) {
+      if (row_ok) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+        p.mask_out[(size_t)row * (p.N >> 5) + (col0 >> 5)] = m;
+      }
+    }
+    if constexpr ((MODE & EPI_RES16) != 0) {
+      if (row_ok) {
+        const uint4* g = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ld_res + col0);
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = __ldg(g + q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 rv = unpack2<FMT_F16>(w[t]);
+            v[q * 8 + t * 2] += rv.x;
+            v[q * 8 + t * 2 + 1] += rv.y;
+          }
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ bool tile_dead(const EpiParams& p, int m0) {
   if (!p.row_live) return false;
   const int g1 = (min(m0 + BM, p.M) - 1) / p.rows_per_group;
   for (int g = m0 / p.rows_per_group; g <= g1; ++g)
     if (__ldg(p.row_live + g)) return false;
   return true;
+}
+
+struct EpiCtx {
+  uint8_t* out_stage;           // staging boxes of all epilogue warps
+  uint64_t* tfull_bar;          // [2] accumulator complete
+  uint64_t* tempty_bar;         // [2] accumulator drained
+  const float* sb_ptr;          // bias in shared memory, indexed by the global column (or null)
+  uint32_t tmem_base;
+  int it_first, it_end, it_step, n_blks, n_fixed, warp, lane;
+};
+
+// The epilogue role (warps 2..17) of gemm_tn_kernel, templated on the epilogue MODE (see TMP_EPI_MODES).
+// 16 warps = 4 per scheduler: the fused epilogue is a dependent chain per warp (tcgen05.ld -> bias/activation/dropout
+// -> pack -> smem -> TMA store) and ran at 43-48 % issue utilisation with 2 warps per scheduler (profiles/r1g).
+// warp -> (TMEM lane quarter it may access, column quarter of the tile). Each thread owns one output row and BN/4
+// columns in 32-column chunks; 16-bit results are staged as [32 rows x 32 cols] boxes (64 B rows inside the 128B
+// swizzle pattern: two rows per 128 B line) and written with TMA stores (coalesced, asynchronous, M-tail clipped by
+// the tensor map). Lane 0 issues the stores; every lane executes the bulk-group waits (groups are per thread, lanes
+// without any return at once).
+template <int BN, bool WS, int MODE>
+__device__ __forceinline__ void epilogue_role(const EpiCtx& cx, const EpiParams& p, const CUtensorMap& tmOut) {
+  using L = SmemLayout<BN, WS>;
+  constexpr bool kGeneric = MODE < 0;
+  const int warp = cx.warp, lane = cx.lane;
+  const int e = warp - 2;
+  const int quarter = warp & 3;
+  const int cg = e >> 2;
+  constexpr int kChunks = BN / 128;   // 32-column chunks per warp
+  uint8_t* stage_buf = cx.out_stage + e * (L::kOutBufs * L::kOutBoxBytes);
+  int sbuf = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const bool has_drop = kGeneric ? p.drop_thr16 != 0 : (MODE & EPI_DROPFOLD) != 0;
+  const uint32_t drop_key = has_drop ? dropout_key(effective_seed(p.drop_seed, p.drop_seed_dev), p.drop_salt) : 0u;
+  for (int it = cx.it_first; it < cx.it_end; it += cx.it_step) {
+    const int m0 = (WS ? it : it / cx.n_blks) * BM, n0 = WS ? cx.n_fixed : (it % cx.n_blks) * BN;
+    if (tile_dead(p, m0)) continue;
+    mbar_wait(&cx.tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int colw = n0 + cg * (BN / 4);
+    const uint32_t taddr = tmem_addr(cx.tmem_base, quarter * 32, acc * BN + cg * (BN / 4));
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (c == kChunks - 1) {
+        // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.tempty_bar[acc]);
+      }
+      const int col0 = colw + c * 32;
+      epilogue_math_t<MODE>(v, p, cx.sb_ptr, row, row_ok, col0, drop_key);
+      if (kGeneric && p.out_f32 && row_ok) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+      if (!kGeneric || p.out) {
+        uint8_t* sbox = stage_buf + sbuf * L::kOutBoxBytes;
+        // the TMA store that last used this buffer must have finished reading it
+        // (every lane executes the wait: bulk groups are per thread, lanes without any return at once -- no reliance on
+        // elect.sync picking the same lane that committed the store)
+        if (L::kOutBufs == 2) tma_store_wait_read1();
+        else tma_store_wait_read0();
+        __syncwarp();
+        uint4 u[4];
+        if (!kGeneric || p.out_fmt == FMT_F16) {   // uniform branch: one pack per pair
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            u[q] = make_uint4(pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                              pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            u[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                              pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        }
+        // 64B-swizzled box, dense 64 B rows: 16 B chunk q of row `lane` at lane*64 + ((q ^ ((lane >> 1) & 3)) << 4)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sbox + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u[q];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {   // fixed lane: its bulk groups gate the reuse of this warp's staging boxes
+          tma_store_2d(&tmOut, sbox, col0, m0 + quarter * 32);
+          tma_store_commit();
+        }
+        if (L::kOutBufs == 2) sbuf ^= 1;
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  tma_store_wait_read0();
 }
 
 template <int BN, bool WS>
@@ -327,89 +523,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // 16 warps = 4 per scheduler: the fused epilogue is a dependent chain per warp (tcgen05.ld -> bias/activation/dropout
-    // -> pack -> smem -> TMA store) and ran at 43-48 % issue utilisation with 2 warps per scheduler (profiles/r1g).
-    // warp -> (TMEM lane quarter it may access, column quarter of the tile). Each thread owns one output row and BN/4
-    // columns in 32-column chunks; 16-bit results are staged as [32 rows x 32 cols] boxes (64 B rows inside the 128B
-    // swizzle pattern: two rows per 128 B line) and written with TMA stores (coalesced, asynchronous, M-tail clipped by
-    // the tensor map), double-buffered per warp (single-buffered in the WS variant: smem holds B). Lane 0 issues the
-    // stores; every lane executes the bulk-group waits (groups are per thread, lanes without any return at once).
-    const int e = warp - 2;
-    const int quarter = warp & 3;
-    const int cg = e >> 2;
-    constexpr int kChunks = BN / 128;   // 32-column chunks per warp
-    uint8_t* stage_buf = smem + L::kOutOffset + e * (L::kOutBufs * L::kOutBoxBytes);
-    const float* sb_ptr = bias_in_smem ? sbias - n_fixed : nullptr;
-    int sbuf = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t drop_key = p.drop_thr16 ? dropout_key(effective_seed(p.drop_seed, p.drop_seed_dev), p.drop_salt) : 0u;
-    for (int it = it_first; it < it_end; it += it_step) {
-      const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
-      if (tile_dead(p, m0)) continue;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int colw = n0 + cg * (BN / 4);
-      const uint32_t taddr = tmem_addr(tmem_base, quarter * 32, acc * BN + cg * (BN / 4));
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (c == kChunks - 1) {
-          // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        const int col0 = colw + c * 32;
-        epilogue_math(v, p, sb_ptr, row, row_ok, col0, drop_key);
-        if (p.out_f32 && row_ok) {
-          float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + col0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-        }
-        if (p.out) {
-          uint8_t* sbox = stage_buf + sbuf * L::kOutBoxBytes;
-          // the TMA store that last used this buffer must have finished reading it
-          // (every lane executes the wait: bulk groups are per thread, lanes without any return at once -- no reliance on
-          // elect.sync picking the same lane that committed the store)
-          if (L::kOutBufs == 2) tma_store_wait_read1();
-          else tma_store_wait_read0();
-          __syncwarp();
-          uint4 u[4];
-          if (p.out_fmt == FMT_F16) {   // uniform branch: one pack per pair (the ternary form computed both formats)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              u[q] = make_uint4(pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              u[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-          }
-          // 64B-swizzled box, dense 64 B rows: 16 B chunk q of row `lane` at lane*64 + ((q ^ ((lane >> 1) & 3)) << 4)
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(sbox + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u[q];
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {   // fixed lane: its bulk groups gate the reuse of this warp's staging boxes
-            tma_store_2d(&tmOut, sbox, col0, m0 + quarter * 32);
-            tma_store_commit();
-          }
-          if (L::kOutBufs == 2) sbuf ^= 1;
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    const EpiCtx cx{smem + L::kOutOffset, tfull_bar, tempty_bar, bias_in_smem ? sbias - n_fixed : nullptr, tmem_base,
+                    it_first, it_end, it_step, n_blks, n_fixed, warp, lane};
+    switch (p.mode) {
+#define X(M) case (M): epilogue_role<BN, WS, (M)>(cx, p, tmOut); break;
+      TMP_EPI_MODES(X)
+#undef X
+      default: epilogue_role<BN, WS, -1>(cx, p, tmOut); break;
     }
-    tma_store_wait_read0();
   }
 
   tc_fence_before();
@@ -691,6 +812,35 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
   p.mask_out = mask_out;
   p.row_live = row_live; p.rows_per_group = rows_per_group;
+  // compile-time specialised epilogue when the call is one of the hot combinations (TMP_EPI_MODES), else the generic one
+  p.mode = -1;
+  static const bool epi_generic = getenv("TMP_B200_GEMM_GENERIC_EPILOGUE") != nullptr;   // A/B timing
+  int mode_cand = -1;
+  if (!epi_generic && out_bf16 && !out_f32 && out_fmt == FMT_F16 && (!gate || gate_fmt == FMT_MASK) &&
+      (!residual || res_fmt == FMT_F16) && (drop_p == 0.f || p.drop_fold) && relu >= 0 && relu <= 2) {
+    int m = 0;
+    if (bias) m |= EPI_BIAS;
+    if (relu == 1) m |= EPI_RELU;
+    if (relu == 2) m |= EPI_GELU;
+    if (gate) m |= EPI_GATEMASK;
+    if (p.drop_fold) m |= EPI_DROPFOLD;
+    if (mask_out) m |= EPI_MASKOUT;
+    if (residual) m |= EPI_RES16;
+    if (p.alpha != 1.f) m |= EPI_ALPHA;
+    switch (m) {
+#define X(M) case (M):
+      TMP_EPI_MODES(X)
+#undef X
+        mode_cand = m;
+        break;
+      default: break;
+    }
+  }
+  // the specialised bias path reads the bias from shared memory: only where the kernel variant stages it
+  auto with_mode = [&](bool ws, int bn) -> const EpiParams& {
+    p.mode = (!bias || ws || N <= (bn == 256 ? 256 : kBiasSmemFloats)) ? mode_cand : -1;
+    return p;
+  };
   CUtensorMap tmOut;
   if (out_bf16) {
     // 16-bit output written by TMA: boxes of [32 rows x 32 cols], 64B swizzle; rows >= M are clipped
@@ -706,12 +856,12 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   const int ws_max_k = BN == 256 ? SmemLayout<256, true>::kWsMaxK : SmemLayout<128, true>::kWsMaxK;
   if (!ws_off && K <= ws_max_k && n_blks <= sms && tiles >= 2 * sms) {
     const int grid = (sms / n_blks) * n_blks;
-    if (BN == 256) return launch_tn<256, true>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
-    return launch_tn<128, true>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+    if (BN == 256) return launch_tn<256, true>(tmA, tmB, tmOut, with_mode(true, 256), grid, (cudaStream_t)stream);
+    return launch_tn<128, true>(tmA, tmB, tmOut, with_mode(true, 128), grid, (cudaStream_t)stream);
   }
   const int grid = tiles < sms ? tiles : sms;
-  if (BN == 256) return launch_tn<256, false>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
-  return launch_tn<128, false>(tmA, tmB, tmOut, p, grid, (cudaStream_t)stream);
+  if (BN == 256) return launch_tn<256, false>(tmA, tmB, tmOut, with_mode(false, 256), grid, (cudaStream_t)stream);
+  return launch_tn<128, false>(tmA, tmB, tmOut, with_mode(false, 128), grid, (cudaStream_t)stream);
 }
 
 extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, int M, int N, int K,

@@ -280,6 +280,21 @@ def case_gemm():
             gate = torch.randn(M, N, device=dev).to(ACT)
             ops.gemm(A, Bw, out=out, gate=gate, alpha=0.5)
             res[f"{tag}_gate_{M}x{N}x{K}"] = _err(out, 0.5 * ref * (gate.float() > 0))
+            if tag != "fwd":
+                continue
+            # the compile-time specialised epilogues (gemm_tc05.cu TMP_EPI_MODES) that the cases above do not reach:
+            # bias only; bias + GELU; bias + folded dropout + fp16 residual (checked against the GENERIC epilogue, which an
+            # additional fp32 output selects: same dropout pattern, same values)
+            ops.gemm(A, Bw, out=out, bias=bias)
+            res[f"spec_bias_{M}x{N}x{K}"] = _err(out, ref + bias)
+            ops.gemm(A, Bw, out=out, bias=bias, relu=2)
+            res[f"spec_bias_gelu_{M}x{N}x{K}"] = _err(out, torch.nn.functional.gelu(ref + bias))
+            o_s = torch.empty(M, N, device=dev, dtype=do); o_g = torch.empty_like(o_s)
+            ops.gemm(A, Bw, out=o_s, bias=bias, residual=resid, drop_p=0.1, seed=11, salt=3)
+            ops.gemm(A, Bw, out=o_g, out_f32=of, bias=bias, residual=resid, drop_p=0.1, seed=11, salt=3)
+            res[f"spec_bias_drop_res_{M}x{N}x{K}"] = _err(o_s, o_g.float())
+            kept = (of - resid.float()) != 0
+            res[f"spec_bias_drop_res_vs_math_{M}x{N}x{K}"] = _err(o_s[kept], ((ref + bias) / 0.9 + resid.float())[kept])
     M, N, K = 2048, 1024, 256
     A = torch.randn(M, K, device=dev).half(); Bw = (torch.randn(N, K, device=dev) / 16).half()
     o0 = torch.empty(M, N, device=dev, dtype=ACT); o1 = torch.empty_like(o0); o2 = torch.empty_like(o0)
