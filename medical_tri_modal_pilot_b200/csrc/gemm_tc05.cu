@@ -418,8 +418,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint64_t* bres_bar = tempty_bar + 2;         // WS: resident B landed
-  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
+  uint64_t* bres_bar = tempty_bar + 2;         // WS: [8] K slice kb of the resident B landed
+  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 8);
+  static_assert((2 * kStages + 4 + 8) * 8 + 4 <= 256, "barrier block");
   float* sbias = (float*)(smem + L::kBiasOffset);
   uint8_t* ring = smem + L::kRingOffset;
 
@@ -448,7 +449,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
-    mbar_init(bres_bar, 1);
+    for (int s = 0; s < 8; ++s) mbar_init(&bres_bar[s], 1);
     fence_barrier_init();
   }
   if (bias_in_smem) {
@@ -467,16 +468,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      if (WS) {
-        mbar_expect_tx(bres_bar, (uint32_t)(k_blks * L::kBBytes));
-        for (int kb = 0; kb < k_blks; ++kb) tma_load_2d(smem + kb * L::kBBytes, &tmB, bres_bar, kb * BK, n_fixed);
-      }
+      // WS: the K slices of the resident B are requested one by one, interleaved with the A stages of the first tile, each
+      // on its own barrier: the first MMAs start after 1/k_blks of B instead of all of it (128 KB per CTA at kernel start)
+      bool b_pending = WS;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = it_first; it < it_end; it += it_step) {
         const int m0 = (WS ? it : it / n_blks) * BM, n0 = WS ? n_fixed : (it % n_blks) * BN;
         if (tile_dead(p, m0)) continue;
         for (int kb = 0; kb < k_blks; ++kb) {
+          if (b_pending) {
+            mbar_expect_tx(&bres_bar[kb], (uint32_t)L::kBBytes);
+            tma_load_2d(smem + kb * L::kBBytes, &tmB, &bres_bar[kb], kb * BK, n_fixed);
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * L::kStageBytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -484,6 +488,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!WS) tma_load_2d(sa + L::kABytes, &tmB, &full_bar[stage], kb * BK, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        b_pending = false;
       }
     }
   } else if (warp == 1) {
@@ -494,16 +499,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (WS) {
-        mbar_wait(bres_bar, 0);
-        tc_fence_after();
-      }
+      bool b_pending = WS;
       for (int it = it_first; it < it_end; it += it_step) {
         if (tile_dead(p, (WS ? it : it / n_blks) * BM)) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
+          if (b_pending) mbar_wait(&bres_bar[kb], 0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * L::kStageBytes);
@@ -519,6 +522,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        b_pending = false;
       }
     }
   } else {
