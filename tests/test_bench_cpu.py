@@ -13,9 +13,11 @@ def test_profiled_traffic_reads_the_committed_ncu_summary():
     """roofline.traffic = dram read + write bytes of one attn_bwd_kernel launch from profiles/*_ncu_full.csv."""
     t, src = bench.profiled_traffic("attn_bwd_kernel")
     assert src is not None and src.endswith("_ncu_full.csv")
-    # algorithmic bytes at B=64, T=1005: Q,K,V,dO,O read once + dQ,dK,dV written = 64320 rows * (768+256+256+768) * 2 B
-    algorithmic = 64320 * (768 + 256 + 256 + 768) * 2
-    assert algorithmic <= t <= 1.25 * algorithmic, (t, algorithmic)
+    # algorithmic bytes at B=64, T=1005 in the fused protocol (delta and the zeroed dQ columns come from the LayerNorm
+    # backward): Q,K,V,dO read once + dQ,dK,dV written = 64320 rows * (768 + 256 + 768) * 2 B; the profiled launch may sit a
+    # few % below (lines still in L2) or above (lse / delta, partial sectors)
+    algorithmic = 64320 * (768 + 256 + 768) * 2
+    assert 0.9 * algorithmic <= t <= 1.25 * algorithmic, (t, algorithmic)
     assert bench.profiled_traffic("no_such_kernel") == (None, None)
 
 
