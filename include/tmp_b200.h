@@ -143,10 +143,15 @@ int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* 
  * flat fp32 parameter / gradient buffers of the fused path: w,g,m,v fp32 [n], n % 4 == 0; step >= 1. ---------- */
 int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, void* stream);
-/* same update with the learning rate and the step count read from DEVICE words (lr_dev: fp32, step_dev: int32 >= 1;
- * bias corrections are evaluated in the kernel) -- the form a captured CUDA graph replays. */
+/* same update with the learning rate and the step count read from DEVICE words -- the form a captured CUDA graph replays.
+ * lr_dev: fp32. step_dev: int32[3] = {optimizer calls so far (>= 1, incremented by the caller before this call), calls
+ * skipped, last call whose gradient was non-finite}: when step_dev[2] == step_dev[0] the call leaves w, m, v untouched and
+ * increments step_dev[1]; bias corrections use step_dev[0] - step_dev[1] (evaluated in the kernel). */
 int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1,
-                       float beta2, float eps, float weight_decay, const int32_t* step_dev, void* stream);
+                       float beta2, float eps, float weight_decay, int32_t* step_dev, void* stream);
+/* state[2] <- state[0] if any of g[0..n) (fp32, n % 4 == 0) is inf or NaN: the overflow guard of the 16-bit plan (gradients
+ * pass through fp16 scratch with a static scale). Call it on the fully reduced gradient, before tmp_adamw_step_dev. */
+int tmp_grad_nonfinite(const float* g, long long n, int32_t* state, void* stream);
 
 /* ---- image-encoder feed: the glue of the frozen Swin-T forward around the tcgen05 GEMMs
  * (reference builder/models/src/swin_transformer.py: patch embedding :541-551, SwinTransformerBlock.forward :447-450,

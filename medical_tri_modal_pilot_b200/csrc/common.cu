@@ -90,4 +90,4 @@ int num_sms() {
 }  // namespace tmp
 
 extern "C" const char* tmp_last_error(void) { return tmp::g_err; }
-extern "C" int tmp_abi_version(void) { return 3; }   // 3: q_rows of the attention calls, fused attn_bwd protocol, fp32 mode
+extern "C" int tmp_abi_version(void) { return 4; }   // 4: tmp_grad_nonfinite, three-word step_dev of tmp_adamw_step_dev (3: q_rows, fused attn_bwd protocol, fp32 mode)

@@ -374,12 +374,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ w, cons
                                                     float lr, float b1, float b2, float eps, float wd,
                                                     float inv_bc1, float inv_sqrt_bc2,
                                                     const float* __restrict__ lr_dev,
-                                                    const int32_t* __restrict__ step_dev) {
+                                                    int32_t* __restrict__ step_dev) {
   if (DEV) {
     // learning rate / step count live in device memory (CUDA-graph replays): bias corrections per thread, in double
-    // like the host path (pow of a handful of values, once per thread)
+    // like the host path (pow of a handful of values, once per thread).
+    // step_dev = {calls, skipped, last call with a non-finite gradient}: a call flagged by grad_nonfinite_kernel leaves
+    // w, m, v untouched and does not count as an optimizer step (what torch.cuda.amp.GradScaler does on the host).
+    const int calls = step_dev[0], skipped = step_dev[1], bad = step_dev[2];
+    if (bad == calls) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) step_dev[1] = skipped + 1;   // nobody else reads it in a skipped call
+      return;
+    }
     lr = __ldg(lr_dev);
-    const double t = (double)__ldg(step_dev);
+    const double t = (double)(calls - skipped);
     inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, t)));
     inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
   }
@@ -399,6 +406,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ w, cons
     }
     w[i] = W; m[i] = M; v[i] = V;
   }
+}
+
+// state[2] <- state[0] (= the optimizer call in progress) when any of g[0..n) is inf / NaN. Runs on the fully reduced
+// gradient (after the data-parallel all-reduce: every rank takes the same decision).
+__global__ void __launch_bounds__(256) grad_nonfinite_kernel(const float4* __restrict__ g, long long n4,
+                                                             int32_t* __restrict__ state) {
+  bool bad = false;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 u = *reinterpret_cast<const uint4*>(g + i);
+    bad |= ((u.x & 0x7f800000u) == 0x7f800000u) | ((u.y & 0x7f800000u) == 0x7f800000u) |
+           ((u.z & 0x7f800000u) == 0x7f800000u) | ((u.w & 0x7f800000u) == 0x7f800000u);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicMax(&state[2], state[0]);
 }
 
 int rows_grid(long long rows) {
@@ -615,8 +636,15 @@ extern "C" int tmp_adamw_step(float* w, const float* g, float* m, float* v, long
   return tmp::check_launch("adamw_kernel");
 }
 
+extern "C" int tmp_grad_nonfinite(const float* g, long long n, int32_t* state, void* stream) {
+  TMP_REQUIRE(g && state && n >= 0 && n % 4 == 0, "grad_nonfinite: bad argument");
+  if (n == 0) return TMP_OK;
+  grad_nonfinite_kernel<<<adamw_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, state);
+  return tmp::check_launch("grad_nonfinite_kernel");
+}
+
 extern "C" int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev,
-                                  float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
+                                  float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev,
                                   void* stream) {
   TMP_REQUIRE(w && g && m && v && lr_dev && step_dev && n >= 0 && n % 4 == 0, "adamw_step_dev: bad argument");
   if (n == 0) return TMP_OK;

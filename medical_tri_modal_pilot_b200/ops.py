@@ -236,11 +236,23 @@ def adamw_step(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
                                      float(eps), float(weight_decay), int(step), stream_ptr()), "tmp_adamw_step")
 
 
+def grad_nonfinite(g, state):
+    """state[2] <- state[0] when g (fp32, numel % 4 == 0) holds an inf / NaN (see adamw_step_dev)."""
+    _cuda_contig(g, torch.float32, "g")
+    _cuda_contig(state, torch.int32, "state")
+    if state.numel() < 3:
+        raise ValueError("grad_nonfinite: state must hold 3 int32 words")
+    check(_lib.load().tmp_grad_nonfinite(ptr(g), g.numel(), ptr(state), stream_ptr()), "tmp_grad_nonfinite")
+
+
 def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev):
-    """Same update with lr (fp32 [1]) and the step count (int32 [1]) read from device memory: CUDA-graph replayable."""
+    """Same update with lr (fp32 [1]) and the step words (int32 [3]: calls, skipped, last call with a non-finite
+    gradient -- a flagged call is skipped and not counted) read from device memory: CUDA-graph replayable."""
     for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v"), (lr_dev, "lr_dev")):
         _cuda_contig(t, torch.float32, nm)
     _cuda_contig(step_dev, torch.int32, "step_dev")
+    if step_dev.numel() < 3:
+        raise ValueError("adamw_step_dev: step_dev must hold 3 int32 words (calls, skipped, last bad call)")
     check(_lib.load().tmp_adamw_step_dev(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(lr_dev), float(beta1),
                                          float(beta2), float(eps), float(weight_decay), ptr(step_dev), stream_ptr()),
           "tmp_adamw_step_dev")

@@ -26,7 +26,11 @@ class FlatAdamW(torch.optim.Optimizer):
         # The step count and the learning rate live in device memory (`t_dev`, `lr_dev`): the whole optimizer step is
         # a fixed sequence of launches with no per-step host scalars, i.e. replayable inside a captured CUDA graph
         # (trainer.GraphedStep). The few head parameters use torch.optim.AdamW in its capturable form.
-        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        # t_dev = {step() calls, calls skipped, last call whose gradient was non-finite}. Gradients of the 16-bit plan pass
+        # through fp16 scratch with a static scale (runtime.GRAD_SCALE): an overflow there would otherwise poison w, m and
+        # v for good. Every step checks the (all-reduced) flat gradient on the device; a flagged call changes nothing and
+        # does not count (the semantics of torch.cuda.amp.GradScaler, without the host round trip).
+        self.t_dev = torch.zeros(4, dtype=torch.int32, device=dev)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
         self._rest_opt = torch.optim.AdamW(self.rest, lr=torch.tensor(float(lr), device=dev), betas=betas, eps=eps,
@@ -49,14 +53,20 @@ class FlatAdamW(torch.optim.Optimizer):
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
         self.t += 1
-        self.t_dev.add_(1)
+        self.t_dev[:1].add_(1)
         fp = self.fp
         if fp.grads_fresh:
+            ops.grad_nonfinite(fp.flat_g[: self.n_live], self.t_dev)
             ops.adamw_step_dev(fp.flat_w[: self.n_live], fp.flat_g[: self.n_live], self.m, self.v, self.lr_dev,
                                g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.t_dev)
             fp.grads_fresh = False
         self._rest_opt.step()
         return None
+
+    def steps_taken(self):
+        """(optimizer steps applied, calls skipped because of a non-finite gradient) -- reads the device words (a sync)."""
+        calls, skipped = (int(v) for v in self.t_dev[:2].tolist())
+        return calls - skipped, skipped
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=True)
@@ -66,7 +76,7 @@ class FlatAdamW(torch.optim.Optimizer):
         """torch.optim.Optimizer.state_dict() plus the flat moments, the step count and the head optimizer's state (the
         base class only knows `self.state`, which this optimizer does not use)."""
         sd = super().state_dict()
-        sd["flat"] = {"m": self.m.detach().clone(), "v": self.v.detach().clone(), "t": int(self.t),
+        sd["flat"] = {"m": self.m.detach().clone(), "v": self.v.detach().clone(), "t": self.steps_taken()[0],
                       "n_live": int(self.n_live), "rest": self._rest_opt.state_dict()}
         return sd
 
@@ -82,7 +92,8 @@ class FlatAdamW(torch.optim.Optimizer):
             self.m.copy_(flat["m"])
             self.v.copy_(flat["v"])
             self.t = int(flat["t"])
-            self.t_dev.fill_(self.t)
+            self.t_dev.zero_()
+            self.t_dev[:1].fill_(self.t)
         self._rest_opt.load_state_dict(flat["rest"])
         lr = float(self.param_groups[0]["lr"])
         self.lr_dev.fill_(lr)

@@ -146,7 +146,7 @@ def test_flat_adamw_state_dict_round_trip():
     m_b.load_state_dict(ck["model"])
     o_b = FlatAdamW(m_b, lr=1e-3, weight_decay=1e-2, eps=1e-3)
     o_b.load_state_dict(ck["optimizer"])
-    assert o_b.t == 3 and int(o_b.t_dev.item()) == 3 and o_b.m.abs().sum().item() > 0
+    assert o_b.t == 3 and o_b.steps_taken() == (3, 0) and o_b.m.abs().sum().item() > 0
     la, lb = steps(m_a, o_a, 2), steps(m_b, o_b, 2)
     for a, b in zip(la, lb):
         assert abs(a - b) < max(1e-3, 0.03 * a), (la, lb)
@@ -215,13 +215,78 @@ def test_adamw_dev_equals_host_scalars():
     w1 = torch.randn(n, device="cuda"); w2 = w1.clone()
     m1, v1, m2, v2 = (torch.zeros(n, device="cuda") for _ in range(4))
     lr_dev = torch.zeros(1, device="cuda")
-    t_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    t_dev = torch.zeros(4, dtype=torch.int32, device="cuda")
     for t, lr in ((1, 3e-3), (2, 1e-3), (3, 2e-3)):
         g = torch.randn(n, device="cuda")
         ops.adamw_step(w1, g, m1, v1, lr, 0.9, 0.999, 1e-8, 1e-2, t)
-        lr_dev.fill_(lr); t_dev.fill_(t)
+        lr_dev.fill_(lr); t_dev.zero_(); t_dev[:1].fill_(t)
         ops.adamw_step_dev(w2, g, m2, v2, lr_dev, 0.9, 0.999, 1e-8, 1e-2, t_dev)
     assert (w1 - w2).abs().max().item() < 1e-6
+
+
+def test_nonfinite_gradient_skips_the_optimizer_step():
+    """Overflow guard of the 16-bit plan (gradients pass through fp16 scratch with a static scale): a call whose flat
+    gradient holds an inf / NaN leaves w, m, v untouched and is not counted; the next clean call continues with the bias
+    corrections of the steps actually taken. All on the device (graph-replayable): {calls, skipped, last bad call}."""
+    from medical_tri_modal_pilot_b200 import ops
+    torch.manual_seed(2)
+    n = 1 << 16
+    w = torch.randn(n, device="cuda"); w_ref = w.clone()
+    m, v, m_ref, v_ref = (torch.zeros(n, device="cuda") for _ in range(4))
+    lr_dev = torch.full((1,), 1e-3, device="cuda")
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
+    taken = 0
+    for call, poison in enumerate((None, float("inf"), None, float("nan"), float("-inf"), None), start=1):
+        g = torch.randn(n, device="cuda")
+        if poison is not None:
+            g[12345] = poison
+        state[:1].add_(1)
+        ops.grad_nonfinite(g, state)
+        before = (w.clone(), m.clone(), v.clone())
+        ops.adamw_step_dev(w, g, m, v, lr_dev, 0.9, 0.999, 1e-8, 1e-2, state)
+        if poison is None:
+            taken += 1
+            ops.adamw_step(w_ref, g, m_ref, v_ref, 1e-3, 0.9, 0.999, 1e-8, 1e-2, taken)
+        else:
+            assert torch.equal(w, before[0]) and torch.equal(m, before[1]) and torch.equal(v, before[2])
+        assert state[:2].tolist() == [call, call - taken]
+    assert taken == 3 and (w - w_ref).abs().max().item() < 1e-6 and torch.isfinite(w).all()
+
+
+def test_flat_adamw_survives_an_overflowing_backward():
+    """End to end: a step whose fused-path gradient overflowed (injected inf in flat_g) changes no fused-path weight and
+    FlatAdamW reports it; training continues on the next batch."""
+    from builder.models import get_model
+    from medical_tri_modal_pilot_b200 import synth, trainer
+    from medical_tri_modal_pilot_b200.config import make_args
+    from medical_tri_modal_pilot_b200.optim import FlatAdamW
+    dev = torch.device("cuda", 0)
+    args = make_args(transformer_num_layers=2, multiimages=1, mbt_only_vslt=1, input_types="vslt_img_txt", imgtxt_time=1,
+                     dropout=0.1, batch_size=8, img_pretrain="No", TIE_len=40)
+    args.device = dev
+    torch.manual_seed(0)
+    model = get_model(args)(args).to(dev).train()
+    opt = FlatAdamW(model, lr=1e-3, weight_decay=1e-6)
+    crit = torch.nn.BCEWithLogitsLoss()
+    host = synth.make_batch(8, 40, n_img=3, seed=5, full_length=False, missing_mode="mixed", with_pixels=True, feats=False)
+    miss = host["missing"]
+    missing3 = torch.stack([torch.zeros_like(miss), (miss >= 2).long(), (miss % 2).long()], 1).float()
+    r = {k: v.to(dev) for k, v in host.items()}
+    b = trainer.prepare_batch(args, dev, r["x"], torch.stack([r["gen"], r["age"]], 1), r["input_lengths"], r["y"], r["img"],
+                              r["txts"], r["txt_lengths"], (r["img_time"], r["txt_time"]), missing3.to(dev))
+    fp = model._fused
+    trainer.train_step(args, model, opt, crit, b, None, 0, None)
+    assert opt.steps_taken() == (1, 0)
+    w0 = fp.flat_w.clone()
+    # second step by hand: forward / backward, then poison one gradient element before the optimizer runs
+    opt.zero_grad()
+    _, loss = trainer.forward_loss(args, model, crit, b, "train")
+    loss.backward()
+    fp.flat_g[7] = float("inf")
+    opt.step()
+    assert opt.steps_taken() == (1, 1) and torch.equal(fp.flat_w, w0)
+    trainer.train_step(args, model, opt, crit, b, None, 2, None)
+    assert opt.steps_taken() == (2, 1) and not torch.equal(fp.flat_w, w0) and torch.isfinite(fp.flat_w).all()
 
 
 def test_staged_upload_feeds_every_replay_with_the_new_batch():
