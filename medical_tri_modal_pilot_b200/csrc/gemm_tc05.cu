@@ -101,30 +101,31 @@ struct SmemLayout {
 static_assert(SmemLayout<256, true>::kTotal <= 232448 && SmemLayout<128, true>::kTotal <= 232448, "WS smem budget");
 static_assert(SmemLayout<256, false>::kTotal <= 232448 && SmemLayout<128, false>::kTotal <= 232448, "smem budget");
 
-// erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 output rounding):
-// erf(z) = 1 - q, q = (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x| / sqrt 2. With that,
+// erf GELU with erf from Abramowitz-Stegun 7.1.28 (|abs error| <= 3e-7, far below the fp16 output rounding):
+//   1 - erf(z) = q = 1 / (1 + a1 z + ... + a6 z^6)^16,   z = |x| / sqrt 2   (z >= 0)
 //   gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = relu(x) - (|x| / 2) q          (both signs of x, no select)
-// evaluated for a PAIR of elements on the packed fp32 pipe (FFMA2 / FMUL2): 11 packed + 4 MUFU + 4 scalar instructions
-// per pair (9.5 per element) instead of ~15 scalar ones (erff() is ~45): the FC1 epilogue of the image encoder touches
-// 1.1 G elements per step and is issue-bound on this function.
+// evaluated for a PAIR of elements on the packed fp32 pipe (FFMA2 / FMUL2). ONE MUFU per element (the reciprocal; the 16th
+// power is four packed squarings): the FC1 epilogue of the image encoder touches 1.1 G elements per step and with the
+// rcp + ex2 form of 7.1.26 (two MUFU per element) a [128 x 256] tile cost 4 096 cycles of the 16/clk/SM MUFU pipe against
+// 3 072 cycles of MMA at K = 384 -- the GELU GEMMs were MUFU-bound (MMA warp waiting 54 % of its loop for accumulators).
 __device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1) {
   const f32x2_t z = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_pack(0.70710678118654752f, 0.70710678118654752f));
+  f32x2_t poly = f2_fma(z, f2_pack(0.0000430638f, 0.0000430638f), f2_pack(0.0002765672f, 0.0002765672f));
+  poly = f2_fma(poly, z, f2_pack(0.0001520143f, 0.0001520143f));
+  poly = f2_fma(poly, z, f2_pack(0.0092705272f, 0.0092705272f));
+  poly = f2_fma(poly, z, f2_pack(0.0422820123f, 0.0422820123f));
+  poly = f2_fma(poly, z, f2_pack(0.0705230784f, 0.0705230784f));
+  poly = f2_fma(poly, z, f2_pack(1.f, 1.f));
   float u0, u1;
-  f2_unpack(f2_fma(f2_pack(0.3275911f, 0.3275911f), z, f2_pack(1.f, 1.f)), u0, u1);
-  float t0, t1;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
-  const f32x2_t t = f2_pack(t0, t1);
-  f32x2_t poly = f2_fma(t, f2_pack(1.061405429f, 1.061405429f), f2_pack(-1.453152027f, -1.453152027f));
-  poly = f2_fma(poly, t, f2_pack(1.421413741f, 1.421413741f));
-  poly = f2_fma(poly, t, f2_pack(-0.284496736f, -0.284496736f));
-  poly = f2_fma(poly, t, f2_pack(0.254829592f, 0.254829592f));
-  float a0, a1;
-  f2_unpack(f2_mul(f2_mul(z, z), f2_pack(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
-  float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  const f32x2_t q = f2_mul(f2_mul(poly, t), f2_pack(e0, e1));                      // 1 - erf(|z|)  in (0, 1]
+  f2_unpack(poly, u0, u1);
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(u0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(u1));
+  f32x2_t q = f2_pack(r0, r1);
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);                                                                // 1 - erf(|z|)  in (0, 1]
   const f32x2_t wn = f2_mul(z, f2_pack(-0.70710678118654752f, -0.70710678118654752f));   // -|x| / 2
   f2_unpack(f2_fma(wn, q, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
 }
@@ -306,10 +307,16 @@ __device__ __forceinline__ bool tile_dead(const EpiParams& p, int m0) {
   return true;
 }
 
+// fp32 accumulator buffers in TMEM: all 512 columns, i.e. 2 at BN = 256 and 4 at BN = 128. With 2 buffers the MMA warp of
+// the GELU GEMMs waited 54 % of its loop for the epilogue to release one (clock64 trace): the accumulator round trip
+// MMA -> epilogue -> MMA, not the epilogue's issue rate, set the tile period.
+template <int BN>
+constexpr int kAccBufs = 512 / BN;
+
 struct EpiCtx {
   uint8_t* out_stage;           // staging boxes of all epilogue warps
-  uint64_t* tfull_bar;          // [2] accumulator complete
-  uint64_t* tempty_bar;         // [2] accumulator drained
+  uint64_t* tfull_bar;          // [kAcc] accumulator complete
+  uint64_t* tempty_bar;         // [kAcc] accumulator drained
   const float* sb_ptr;          // bias in shared memory, indexed by the global column (or null)
   uint32_t tmem_base;
   int it_first, it_end, it_step, n_blks, n_fixed, warp, lane;
@@ -401,7 +408,7 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& cx, const EpiParams&
         if (L::kOutBufs == 2) sbuf ^= 1;
       }
     }
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if (++acc == kAccBufs<BN>) { acc = 0; acc_phase ^= 1; }
   }
   tma_store_wait_read0();
 }
@@ -416,11 +423,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint64_t* bres_bar = tempty_bar + 2;         // WS: [8] K slice kb of the resident B landed
+  constexpr int kAcc = kAccBufs<BN>;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [kAcc]
+  uint64_t* tempty_bar = tfull_bar + kAcc;     // [kAcc]
+  uint64_t* bres_bar = tempty_bar + kAcc;      // WS: [8] K slice kb of the resident B landed
   uint32_t* tmem_slot = (uint32_t*)(bres_bar + 8);
-  static_assert((2 * kStages + 4 + 8) * 8 + 4 <= 256, "barrier block");
+  static_assert((2 * kStages + 2 * kAcc + 8) * 8 + 4 <= 256, "barrier block");
   float* sbias = (float*)(smem + L::kBiasOffset);
   uint8_t* ring = smem + L::kRingOffset;
 
@@ -445,7 +453,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAcc; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
@@ -459,7 +467,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i] * p.bias_scale;
     }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, kAcc * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -521,7 +529,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         b_pending = false;
       }
     }
@@ -542,7 +550,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, kAcc * BN);
   }
 }
 
