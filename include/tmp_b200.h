@@ -127,8 +127,13 @@ int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, con
  * (fp16) ---------------------------------------------------------------------------------------------------- */
 int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
                            void* stream);
+/* backward: dYd_m (each optional, all ignored when drop_p == 0) additionally receive rows 0..3 of dY_m after dropout with
+ * the mask of (seed [+ *seed_dev], salt_m, element index in the stream's [B*T_m,256] matrix) -- the rows this call changes in
+ * a tensor whose dropped copy tmp_layernorm_bwd(dx_drop) has already written. */
 int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
-                           const long long* missing, int B, void* stream);
+                           const long long* missing, int B, void* dYd_v, void* dYd_i, void* dYd_t, float drop_p,
+                           uint32_t seed, const uint32_t* seed_dev, uint32_t salt_v, uint32_t salt_i, uint32_t salt_t,
+                           void* stream);
 
 /* ---- helpers ---------------------------------------------------------------------------------------------- */
 int tmp_dropout_apply(const void* in, void* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
@@ -192,7 +197,9 @@ int tmp_layernorm_bwd_f32(const float* dy, const float* x, const float* dres, co
 int tmp_bottleneck_mix_fwd_f32(float* Yv, float* Yi, float* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,
                                void* stream);
 int tmp_bottleneck_mix_bwd_f32(float* dYv, float* dYi, float* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
-                               const long long* missing, int B, void* stream);
+                               const long long* missing, int B, float* dYd_v, float* dYd_i, float* dYd_t, float drop_p,
+                               uint32_t seed, const uint32_t* seed_dev, uint32_t salt_v, uint32_t salt_i, uint32_t salt_t,
+                               void* stream);
 int tmp_dropout_apply_f32(const float* in, float* out, long long n, float drop_p, uint32_t seed, uint32_t salt,
                           const uint32_t* seed_dev, void* stream);
 int tmp_colsum_f32(const float* dY, int ld, long long M, int N, float* out, void* stream);

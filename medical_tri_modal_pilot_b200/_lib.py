@@ -36,7 +36,7 @@ SIGNATURES = {
     "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
     "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "tmp_bottleneck_mix_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
-    "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _u32, _vp, _u32, _u32, _u32, _vp],
     "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
@@ -46,7 +46,8 @@ SIGNATURES = {
     "tmp_layernorm_fwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
     "tmp_layernorm_bwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
     "tmp_bottleneck_mix_fwd_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
-    "tmp_bottleneck_mix_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "tmp_bottleneck_mix_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _u32, _vp, _u32, _u32, _u32,
+                                   _vp],
     "tmp_dropout_apply_f32": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
     "tmp_colsum_f32": [_vp, _i, _ll, _i, _vp, _vp],
     "tmp_stream_prologue_fwd_f32": [_i, _i, _i, _vp, _pp, _vp, _vp, _i, _i, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _u32,

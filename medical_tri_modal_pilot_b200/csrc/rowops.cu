@@ -255,10 +255,20 @@ __global__ void bottleneck_mix_fwd_kernel(void* __restrict__ Yv, void* __restric
 }
 
 // gradient: g = sum over present dY_m rows; dY_m rows <- w_m * g.  A null pointer = stream absent in the upper layer.
+// dYd_m (optional): the same rows after the NEXT layer-down's output dropout (mask of (seed, salt_m, element index in the
+// stream's [B*T_m, 256] matrix)): the LayerNorm backward that produced dY_m already wrote dropout(dY_m) for every row, and
+// this kernel is the only thing that changes rows afterwards.
+struct MixDrop {
+  void* dYd[3];
+  uint32_t salt[3];
+  uint32_t thr16, seed;
+  float scale;
+  const uint32_t* seed_dev;
+};
 template <int ST>
 __global__ void bottleneck_mix_bwd_kernel(void* __restrict__ dYv, void* __restrict__ dYi, void* __restrict__ dYt,
                                           int Tv, int Ti, int Tt, int upper_has_it,
-                                          const long long* __restrict__ missing, int B) {
+                                          const long long* __restrict__ missing, int B, MixDrop md) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * 4) return;
@@ -278,15 +288,19 @@ __global__ void bottleneck_mix_bwd_kernel(void* __restrict__ dYv, void* __restri
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += a[i];
   }
+  void* const dst[3] = {dYv, dYi, dYt};
+  const size_t pos[3] = {pv, pi, pt};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[0];
-  st8<ST>(dYv, pv, o);
+  for (int m = 0; m < 3; ++m) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[1];
-  st8<ST>(dYi, pi, o);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = g[i] * w[2];
-  st8<ST>(dYt, pt, o);
+    for (int i = 0; i < 8; ++i) o[i] = g[i] * w[m];
+    st8<ST>(dst[m], pos[m], o);
+    if (md.dYd[m]) {
+      dropout_apply_run<8>(o, dropout_key(effective_seed(md.seed, md.seed_dev), md.salt[m]), (uint32_t)pos[m], md.thr16,
+                           md.scale);
+      st8<ST>(md.dYd[m], pos[m], o);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -541,23 +555,41 @@ extern "C" int tmp_bottleneck_mix_fwd_f32(float* Yv, float* Yi, float* Yt, int T
 }
 
 static int mix_bwd_impl(int st, void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
-                        const long long* missing, int B, void* stream) {
+                        const long long* missing, int B, void* dYd_v, void* dYd_i, void* dYd_t, float drop_p, uint32_t seed,
+                        const uint32_t* seed_dev, uint32_t salt_v, uint32_t salt_i, uint32_t salt_t, void* stream) {
   TMP_REQUIRE(dYv && dYi && dYt && missing && B > 0, "bottleneck_mix_bwd: bad argument");
+  TMP_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "bottleneck_mix_bwd: dropout p out of range");
+  TMP_REQUIRE((long long)B * (Tv > Ti ? (Tv > Tt ? Tv : Tt) : (Ti > Tt ? Ti : Tt)) * D < (1ll << 32),
+              "bottleneck_mix_bwd: element index exceeds 32 bits");
+  MixDrop md;
+  const bool drop = drop_p > 0.f;
+  md.dYd[0] = drop ? dYd_v : nullptr; md.dYd[1] = drop ? dYd_i : nullptr; md.dYd[2] = drop ? dYd_t : nullptr;
+  md.salt[0] = salt_v; md.salt[1] = salt_i; md.salt[2] = salt_t;
+  md.thr16 = drop ? (uint32_t)(drop_p * 65536.f + 0.5f) : 0; md.seed = seed;
+  md.scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  md.seed_dev = seed_dev;
   if (st == FMT_F32)
     bottleneck_mix_bwd_kernel<FMT_F32><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dYv, dYi, dYt, Tv, Ti, Tt,
-                                                                                        upper_has_img_txt, missing, B);
+                                                                                        upper_has_img_txt, missing, B, md);
   else
     bottleneck_mix_bwd_kernel<GRD><<<(B * 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dYv, dYi, dYt, Tv, Ti, Tt,
-                                                                                    upper_has_img_txt, missing, B);
+                                                                                    upper_has_img_txt, missing, B, md);
   return tmp::check_launch("bottleneck_mix_bwd_kernel");
 }
 extern "C" int tmp_bottleneck_mix_bwd(void* dYv, void* dYi, void* dYt, int Tv, int Ti, int Tt, int upper_has_img_txt,
-                                      const long long* missing, int B, void* stream) {
-  return mix_bwd_impl(GRD, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, stream);
+                                      const long long* missing, int B, void* dYd_v, void* dYd_i, void* dYd_t,
+                                      float drop_p, uint32_t seed, const uint32_t* seed_dev, uint32_t salt_v,
+                                      uint32_t salt_i, uint32_t salt_t, void* stream) {
+  return mix_bwd_impl(GRD, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, dYd_v, dYd_i, dYd_t, drop_p, seed,
+                      seed_dev, salt_v, salt_i, salt_t, stream);
 }
 extern "C" int tmp_bottleneck_mix_bwd_f32(float* dYv, float* dYi, float* dYt, int Tv, int Ti, int Tt,
-                                          int upper_has_img_txt, const long long* missing, int B, void* stream) {
-  return mix_bwd_impl(FMT_F32, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, stream);
+                                          int upper_has_img_txt, const long long* missing, int B, float* dYd_v,
+                                          float* dYd_i, float* dYd_t, float drop_p, uint32_t seed,
+                                          const uint32_t* seed_dev, uint32_t salt_v, uint32_t salt_i, uint32_t salt_t,
+                                          void* stream) {
+  return mix_bwd_impl(FMT_F32, dYv, dYi, dYt, Tv, Ti, Tt, upper_has_img_txt, missing, B, dYd_v, dYd_i, dYd_t, drop_p, seed,
+                      seed_dev, salt_v, salt_i, salt_t, stream);
 }
 
 // out[N] += column sums of dY [M, N]. The 16-bit path gets its bias gradients from the weight-gradient kernel

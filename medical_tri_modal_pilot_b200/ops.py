@@ -211,11 +211,18 @@ def bottleneck_mix_fwd(Yv, Yi, Yt, missing):
                                              ptr(missing), B, stream_ptr()), "tmp_bottleneck_mix_fwd")
 
 
-def bottleneck_mix_bwd(dYv, dYi, dYt, upper_has_img_txt, missing):
+def bottleneck_mix_bwd(dYv, dYi, dYt, upper_has_img_txt, missing, dropped=(None, None, None), drop_p=0.0, seed=0,
+                       salts=(0, 0, 0), seed_dev=None):
+    """dropped[m] (optional, same shape as dY_m): receives rows 0..3 of dY_m after dropout(drop_p, seed, salts[m]) -- see
+    include/tmp_b200.h."""
     B = dYv.shape[0]
     fn = _lib.load().tmp_bottleneck_mix_bwd_f32 if _f32(dYv) else _lib.load().tmp_bottleneck_mix_bwd
+    for d, y in zip(dropped, (dYv, dYi, dYt)):
+        if d is not None and (d.shape != y.shape or d.dtype != y.dtype or not d.is_contiguous()):
+            raise ValueError("bottleneck_mix_bwd: a dropped output must match its gradient tensor")
     check(fn(ptr(dYv), ptr(dYi), ptr(dYt), dYv.shape[1], dYi.shape[1], dYt.shape[1],
-                                             int(upper_has_img_txt), ptr(missing), B, stream_ptr()),
+             int(upper_has_img_txt), ptr(missing), B, ptr(dropped[0]), ptr(dropped[1]), ptr(dropped[2]), float(drop_p),
+             seed, ptr(seed_dev), int(salts[0]), int(salts[1]), int(salts[2]), stream_ptr()),
           "tmp_bottleneck_mix_bwd")
 
 

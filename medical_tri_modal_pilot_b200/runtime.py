@@ -56,6 +56,7 @@ class FusedPath:
         self._ctx_token = 0
         self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
         self.skip_missing = True
+        self.fuse_grad_dropout = os.environ.get("TMP_B200_FUSE_GRAD_DROPOUT", "1") != "0"   # A/B switch
         self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
         self.debug_trace = None   # dict -> backward() records per-layer input gradients (debugging aid)
         # img / txt modality streams on side CUDA streams (TMP_B200_SINGLE_STREAM=1 serialises them: debugging aid)
@@ -457,7 +458,15 @@ class FusedPath:
                      st["g_qkv"], q_rows=5)
         ops.gemm(st["g_qkv"], self.wT[(l, 0, "qkv")], out=st["g_xn"])
         ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
-        ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
+        # LN1 (+ residual); the same pass writes dropout(dX[l]) for the layer below (its FFN2 output dropout mask): g_yd is
+        # free by now, its readers (FFN2 dgrad / wgrad of this layer) ran earlier on this stream
+        if p > 0 and l > 0 and self.fuse_grad_dropout:
+            ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b,
+                              dx_drop=st["g_yd"].view(M, D), drop_p=p, seed=seed, salt=((l - 1) * 3) * 4 + 2,
+                              seed_dev=ctx["seed_dev"])
+            ctx["gyd_layer"][0] = l - 1
+        else:
+            ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
         st["g_y"], st["g_x"] = st["g_x"], st["g_y"]
 
     # ------------------------------------------------------------------------------------------------------------
@@ -482,6 +491,7 @@ class FusedPath:
         self.flat_g.zero_()
         gscale = 1.0 if ctx["f32"] else self.grad_scale      # fp32 gradients need no scale
         ctx["gscale"] = gscale
+        ctx["gyd_layer"] = {}      # stream -> layer whose dropped input gradient (g_yd) is already in place
         cls_last = m.vsltonly == 1 and self.cls_only and not ctx["f32"]
         for s in range(3):
             if s == 0 and cls_last:
@@ -508,8 +518,14 @@ class FusedPath:
             # after _layer_bwd, g_y of each processed stream holds dX[l] (gradient wrt the layer input)
             if l > 0:
                 upper_has_it = 0 if last else 1
+                # rows 0..3 change here: streams whose dropped gradient copy was written by this layer's LayerNorm backward
+                # get those rows refreshed in the same launch
+                fused = [ctx["gyd_layer"].get(s) == l - 1 for s in range(3)]
                 ops.bottleneck_mix_bwd(self.ws[0]["g_y"], self.ws[1]["g_y"], self.ws[2]["g_y"], upper_has_it,
-                                       ctx["missing"])
+                                       ctx["missing"],
+                                       dropped=tuple(self.ws[s]["g_yd"] if fused[s] else None for s in range(3)),
+                                       drop_p=p if any(fused) else 0.0, seed=seed,
+                                       salts=tuple(((l - 1) * 3 + s) * 4 + 2 for s in range(3)), seed_dev=ctx["seed_dev"])
             self._range_done(*self.grad_range_of_layer(l))
         # prologue + projections
         F = "fusion_transformer"
@@ -556,7 +572,10 @@ class FusedPath:
             wT = {k: self.wT[(l, s, k)] for k in ("w2", "w1", "qkv")}
         gy = st["g_y"].view(M, D)
         if p > 0:
-            ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2, seed_dev=ctx["seed_dev"])
+            # dropout(gy) with the mask of this layer's FFN2 output dropout: already written by the LayerNorm backward of
+            # the layer above (dx_drop) + the bottleneck exchange (rows 0..3) when that layer ran through _layer_bwd
+            if ctx["gyd_layer"].get(s) != l:
+                ops.dropout_apply(gy, st["g_yd"].view(M, D), p, seed, (l * 3 + s) * 4 + 2, seed_dev=ctx["seed_dev"])
             gyd = st["g_yd"].view(M, D)
         else:
             gyd = gy
@@ -581,7 +600,13 @@ class FusedPath:
         ops.gemm(st["g_qkv"], wT["qkv"], out=st["g_xn"])
         ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
         # LN1 (+ residual)
-        ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
+        if p > 0 and l > 0 and self.fuse_grad_dropout:     # + dropout(dX[l]) for the layer below, see _layer_bwd_cls
+            ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b,
+                              dx_drop=st["g_yd"].view(M, D), drop_p=p, seed=seed, salt=((l - 1) * 3 + s) * 4 + 2,
+                              seed_dev=ctx["seed_dev"])
+            ctx["gyd_layer"][s] = l - 1
+        else:
+            ops.layernorm_bwd(st["g_xn"], st["X"][l].view(M, D), st["g_h"], w.ln1_g, st["g_x"].view(M, D), g.ln1_g, g.ln1_b)
         st["g_y"], st["g_x"] = st["g_x"], st["g_y"]
 
     def live_end(self):

@@ -278,3 +278,37 @@ def test_eval_mode_and_state_dict_roundtrip():
     sd2 = model.state_dict()
     for k, v in sd.items():
         assert torch.equal(sd2[k].cpu(), v), k
+
+
+@pytest.mark.parametrize("name,nl_multi", [("tri_nl3_multi_B16_L150", None), ("tri_nl6_multi_B16_L260", None)])
+def test_fused_gradient_dropout_equals_the_separate_pass(name, nl_multi):
+    """With dropout on, the gradient entering a layer's FFN2 is dropout(dX) under that layer's output mask. The LayerNorm
+    backward of the layer above writes that copy in the same pass (dx_drop) and the bottleneck exchange refreshes rows 0..3
+    of it; the older form ran one `dropout_apply` kernel per layer and stream. Two backward passes from the SAME forward
+    (same masks), one per form: the parameter gradients must agree to fp16 rounding of one intermediate tensor."""
+    fx = load_fixture(name)
+    sd, batch, cfg = fixture_inputs(fx)
+    sd = fp16_representable(sd)
+    B = batch["x"].shape[0]
+    model = build_model(cfg, sd, B, dropout=0.1)
+    model.train()
+    b = {k: v.to("cuda") for k, v in batch.items()}
+    fp = model._fused
+    cls = fp(b["x"], b["input_lengths"], b["txts"], b["txt_lengths"], model.encode_images(b["img_feats"], None),
+             b["img_time"], b["txt_time"], b["missing"])
+    gen = torch.Generator().manual_seed(4321)
+    R = (torch.randn(B, 256, generator=gen) * 0.02).cuda()
+    grads = {}
+    for fused in (True, False):
+        fp.fuse_grad_dropout = fused
+        model.zero_grad(set_to_none=True)
+        fp.backward(R.contiguous())
+        torch.cuda.synchronize()
+        grads[fused] = fp.flat_g[: fp.live_end()].clone()
+    fp.fuse_grad_dropout = True
+    a, c = grads[True].double(), grads[False].double()
+    assert torch.isfinite(a).all() and a.abs().sum() > 0
+    cos = (a @ c / (a.norm() * c.norm())).item()
+    rel = ((a - c).norm() / c.norm()).item()
+    print(f"[fused grad dropout {name}] cosine {cos:.8f} rel diff {rel:.2e}")
+    assert cos > 0.99999 and rel < 3e-3

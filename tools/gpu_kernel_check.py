@@ -235,6 +235,20 @@ def case_mix_colsum():
     ops.bottleneck_mix_bwd(*dYc, 0, missing)
     res["mix_bwd_vonly"] = max(_err(dYc[m][:, :4], dY[0][:, :4].float() * w[:, m, None, None])["rel_to_max"]
                                for m in range(3))
+    # dropped copies of rows 0..3: must equal dropout_apply of the mixed tensor (same mask: seed, per-stream salt, element
+    # index in the stream's [B*T, 256] matrix); rows >= 4 of the dropped tensors are not touched
+    dYc = [d.clone() for d in dY]
+    drp = [torch.full_like(d, 7.0) for d in dY]
+    salts = (10, 14, 18)
+    ops.bottleneck_mix_bwd(*dYc, 1, missing, dropped=tuple(drp), drop_p=0.1, seed=77, salts=salts)
+    ok = True
+    for m in range(3):
+        full = torch.empty_like(dYc[m])
+        ops.dropout_apply(dYc[m], full, 0.1, 77, salts[m])
+        a_, f_ = drp[m][:, :4].float(), full[:, :4].float()      # the kernel drops the fp32 value, dropout_apply the rounded one
+        ok = ok and torch.equal(a_ == 0, f_ == 0) and bool(((a_ - f_).abs() <= 2e-3 * f_.abs() + 1e-6).all()) \
+            and bool((drp[m][:, 4:] == 7.0).all())
+    res["mix_bwd_dropped_rows"] = ok
     for N in (256, 768, 1024):
         M = 4097
         dy = torch.randn(M, N, device=dev).to(GRD)
@@ -245,7 +259,7 @@ def case_mix_colsum():
     a = torch.ones(1 << 20, device=dev).to(GRD); o1 = torch.empty_like(a); o2 = torch.empty_like(a)
     ops.dropout_apply(a, o1, 0.1, 11, 5); ops.dropout_apply(a, o2, 0.1, 11, 5)
     res["drop_keep"] = (o1 != 0).float().mean().item(); res["drop_det"] = bool(torch.equal(o1, o2))
-    res["ok"] = res["mix_fwd"] < 1e-2 and res["mix_bwd"] < 1e-2 and res["mix_bwd_vonly"] < 1e-2 and \
+    res["ok"] = res["mix_bwd_dropped_rows"] and res["mix_fwd"] < 1e-2 and res["mix_bwd"] < 1e-2 and res["mix_bwd_vonly"] < 1e-2 and \
         res["mix_rest_untouched"] and all(res[f"colsum{N}"] < 1e-3 for N in (256, 768, 1024)) and \
         abs(res["drop_keep"] - 0.9) < 5e-3 and res["drop_det"]
     return res
