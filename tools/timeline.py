@@ -120,9 +120,45 @@ def main():
         "n_gaps": len(gaps), "gaps_over_5us": sum(1 for g in gaps if g[0] > 5), "gap_sum_over_5us_ms": sum(g[0] for g in gaps if g[0] > 5) / 1e3,
         "top_kernels": sorted(([k, round(v[0] / 1e3, 3), v[1]] for k, v in by_name.items()), key=lambda x: -x[1])[:40],
     }
+    # low-occupancy stretches: time during which only "small" kernels (grid < 64 blocks) are running -- the serial head /
+    # tail of the step (classifier head, loss, optimizer glue), where most SMs idle although the GPU counts as busy
+    def small(e):
+        g = e["args"].get("grid", [1 << 20])
+        return (g[0] * (g[1] if len(g) > 1 else 1) * (g[2] if len(g) > 2 else 1)) < 64
+    pts2 = []
+    for e in ks:
+        pts2.append((e["ts"], 1, small(e)))
+        pts2.append((e["ts"] + e["dur"], -1, small(e)))
+    pts2.sort(key=lambda x: (x[0], x[1]))
+    big = sm = 0
+    last = pts2[0][0]
+    small_only = 0.0
+    runs = []
+    run_start = None
+    for t, d_, is_small in pts2:
+        if big == 0 and sm > 0:
+            small_only += t - last
+            if run_start is None:
+                run_start = last
+        elif run_start is not None:
+            runs.append((last - run_start, (run_start - t0) / 1e3))
+            run_start = None
+        if is_small:
+            sm += d_
+        else:
+            big += d_
+        last = t
+    runs.sort(reverse=True)
+    out["small_kernels_only_ms"] = small_only / 1e3
+    out["small_only_runs"] = [{"us": r[0], "at_ms": r[1]} for r in runs[:12]]
+    seq = []
+    for e in ks:
+        if small(e):
+            seq.append([round((e["ts"] - t0) / 1e3, 3), round(e["dur"], 1), e["name"].replace("(anonymous namespace)::", "")[:80]])
+    out["small_kernel_sequence"] = seq
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
-    print(json.dumps({k: v for k, v in out.items() if k not in ("top_gaps_us", "top_kernels")}))
+    print(json.dumps({k: v for k, v in out.items() if k not in ("top_gaps_us", "top_kernels", "small_kernel_sequence")}))
     for g in out["top_gaps_us"][:15]:
         print(f"gap {g['gap']:7.1f} us at {g['at_ms']:7.3f} ms  after {g['after']}  before {g['before']}")
     for k in out["top_kernels"][:30]:
