@@ -207,6 +207,7 @@ struct PrologueParams {
   uint32_t drop_thr16; float drop_scale; uint32_t seed, salt;
   const uint32_t* seed_dev;    // optional device word added to `seed` (per-step counter of a captured CUDA graph)
   void* X0;                    // [B, T, 256] fp16 (fp32 in the fp32 mode)
+  int rows_per_group;          // forward: rows a warp takes at a time (32; 8 for short streams, see prologue_fwd_impl)
 };
 
 // Forward. A warp takes 32 consecutive rows of the [B*T, 256] output at a time, in the manner of umse_embed_fwd_kernel: lane j
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_ke
   __syncthreads();
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long rows = (long long)p.B * p.T;
-  const long long n_grp = (rows + 31) / 32;
+  const int rpg = p.rows_per_group;
+  const long long n_grp = (rows + rpg - 1) / rpg;
   const uint32_t dkey = p.drop_thr16 ? dropout_key(effective_seed(p.seed, p.seed_dev), p.salt) : 0u;
   const float* sWl = sW + lane * 8;
 
@@ -292,12 +294,12 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_ke
   };
 
   for (long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_grp; grp += warps) {
-    const long long row0 = grp * 32;
-    {   // lane j prepares row row0 + j
+    const long long row0 = grp * rpg;
+    {   // lane j < rows_per_group prepares row row0 + j
       const long long r = row0 + lane;
       RowMeta m{-1, 0, 0, 0};
       float4 tok = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows) {
+      if (lane < rpg && r < rows) {
         const int b = (int)(r / p.T), t = (int)(r - (long long)b * p.T);
         m.t = t;
         if (t < 4) m.code = -1 - t;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_ke
       sMeta[wid][lane] = m;
       __syncwarp();
     }
-    const int cnt = (int)min(32LL, rows - row0);
+    const int cnt = (int)min((long long)rpg, rows - row0);
     for (int j = 0; j < cnt; j += 2) {
       float e0[8], e1[8];
       const bool two = j + 1 < cnt;
@@ -642,7 +644,12 @@ static int prologue_fwd_impl(int stf, int kind, int B, int n, const float* x, co
   int rc = fill_prologue(p, kind, B, n, x, val4, proj, times, n_slots, feat_id, tim4, Wfeat, cls, bottlenecks, ln_g,
                          ln_b, pe, drop_p, seed, salt, seed_dev, X0);
   if (rc) return rc;
-  long long fblocks = ((long long)B * p.T + 255) / 256;      // one warp per 32-row group
+  // one warp per group of rows. A warp walks its group two rows at a time, i.e. a chain of rows_per_group / 2 dependent
+  // load -> LayerNorm -> store steps: with 32-row groups the 9 728-row image stream ran on 38 blocks for 32 us -- on the
+  // critical path between the image encoder and the first exchange -- whatever the grid. Short streams take 8-row groups.
+  const long long rows_total = (long long)B * p.T;
+  p.rows_per_group = rows_total >= 32LL * 8 * tmp::num_sms() ? 32 : 8;
+  long long fblocks = ((rows_total + p.rows_per_group - 1) / p.rows_per_group + 7) / 8;
   const long long fcap = (long long)tmp::num_sms() * (kind == 0 ? 2 : 3);
   if (fblocks > fcap) fblocks = fcap;
   const int grid = (int)(fblocks < 1 ? 1 : fblocks);
