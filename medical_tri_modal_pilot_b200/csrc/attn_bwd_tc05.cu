@@ -57,7 +57,10 @@ constexpr int kSmemDO = kSmemQ + kStages * kTile;
 constexpr int kSmemDQ = kSmemDO + kStages * kTile;        // per flush warp: [32 rows x 32 fp32], 128B swizzle
 constexpr int kSmemStat = kSmemDQ + kFlushWarps * 4096;
 constexpr int kSmemBar = kSmemStat + kStages * kStatBytes;
-constexpr int kSmemTotal = kSmemBar + 256 + 1024;
+constexpr int kMaxSortB = 256;                               // samples ordered by length inside the kernel up to this B
+constexpr int kSmemOrder = kSmemBar + 256;                   // uint16 order[kMaxSortB]
+constexpr int kSmemTotal = kSmemOrder + 2 * kMaxSortB + 1024;
+static_assert(kSmemTotal <= 232448, "attention backward: shared memory");
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -136,14 +139,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_V = tmem_base + 480;    // V_j likewise
   // P^T / dS^T (packed fp16) alias the S^T / dP^T columns: K-step k (16 queries) of half hh at column hh*64 + 16*k
 
+  // Item order for ragged kv_len (static stride over items, so the ORDER decides the balance):
+  //  * samples are taken longest first (rank computed here, once per CTA, B <= kMaxSortB): a CTA's items i, i + grid, ...
+  //    then sample every cost level (stratified) instead of a random subset of samples;
+  //  * the key tile of an item is skewed by its (sample, head) index: with jt = item % n_jt and a stride of 148 = 4 mod 8 a
+  //    CTA only ever saw two key-tile indices -- the CTAs stuck with jt = 3 / 7 got the tiles that are dead for short
+  //    samples, the others all the live ones. The n_jt items of one (sample, head) stay adjacent (they share Q / dO in L2).
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem + kSmemOrder);
+  const int n_b = n_items / (n_jt * H);
+  const bool sorted = kv_len != nullptr && n_b <= kMaxSortB;
+  if (sorted) {
+    for (int b = threadIdx.x; b < n_b; b += blockDim.x) {
+      const int lb = __ldg(kv_len + b);
+      int rank = 0;
+      for (int o = 0; o < n_b; ++o) {
+        const int lo = __ldg(kv_len + o);
+        rank += (lo > lb) || (lo == lb && o < b);
+      }
+      order[rank] = (uint16_t)b;
+    }
+    __syncthreads();
+  }
   // item -> (jt, h, b); live length of the sample
   struct Item { int jt, h, b, k0, len, n_q, row_base; };
   auto decode = [&](int item) {
     Item w;
-    w.jt = item % n_jt;
     const int t = item / n_jt;
+    w.jt = (item - t * n_jt + t) % n_jt;
     w.h = t % H;
-    w.b = t / H;
+    w.b = sorted ? (int)order[t / H] : t / H;
     w.k0 = w.jt * BT;
     w.len = kv_len ? min(__ldg(kv_len + w.b), T) : T;
     w.n_q = min((w.len + BT - 1) / BT, q_tiles_max);   // live query tiles (rows >= len are padding: dO == 0; rows past
