@@ -341,7 +341,7 @@ def run_b200(a):
     model = get_model(args)(args).to(dev)
     model.train()
     if world > 1:
-        GradSync(model)
+        GradSync(model, overlap=os.environ.get("TMP_B200_DDP_NO_OVERLAP") is None)     # env: A/B of the comm-stream overlap
     if a.optimizer == "fused":
         optimizer = FlatAdamW(model, lr=1e-4, weight_decay=1e-6)
     else:

@@ -55,6 +55,7 @@ class FusedPath:
         self._ws_cache = {}       # (B, L, n_img) -> workspace dict (small LRU; captured graphs pin theirs, see pin())
         self._ctx_token = 0
         self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
+        self.grad_post_scale = 1.0   # extra factor folded into the un-scaling pass (GradSync: 1 / world_size)
         self.skip_missing = True
         self.fuse_grad_dropout = os.environ.get("TMP_B200_FUSE_GRAD_DROPOUT", "1") != "0"   # A/B switch
         self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
@@ -555,8 +556,9 @@ class FusedPath:
     def _range_done(self, a, b):
         """flat_g[a:b] is complete: remove the fp16 gradient scale and hand the range to the data-parallel hook
         (trainer.GradSync launches its all-reduce on the communication stream while the backward continues)."""
-        if self.ctx["gscale"] != 1.0:
-            self.flat_g[a:b].mul_(1.0 / self.ctx["gscale"])
+        f = self.grad_post_scale / self.ctx["gscale"]
+        if f != 1.0:
+            self.flat_g[a:b].mul_(f)        # one pass: fp16 gradient scale out, data-parallel averaging in
         if self.comm_hook is not None:
             self.comm_hook(a, b)
 

@@ -46,6 +46,7 @@ class GradSync:
         self._head_flat = None
         self.n_collectives = 0
         self.fp.comm_hook = self._on_range_ready
+        self.fp.grad_post_scale = 1.0 / self.world      # averaging rides on the un-scaling pass of every range
         object.__setattr__(model, "grad_sync", self)      # found by train_step; not a submodule / state_dict entry
         if broadcast_from is not None:
             self.broadcast_parameters(broadcast_from)
@@ -60,12 +61,11 @@ class GradSync:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src, group=self.group)
 
-    # called by FusedPath.backward on the compute stream once flat_g[a:b] is final (already unscaled)
+    # called by FusedPath.backward on the compute stream once flat_g[a:b] is final (unscaled and pre-divided by world_size)
     def _on_range_ready(self, a: int, b: int):
         g = self.fp.flat_g[a:b]
         if self.world == 1:
             return
-        g.mul_(1.0 / self.world)
         if g.is_cuda and self.overlap:
             if self.comm_stream is None:
                 self.comm_stream = torch.cuda.Stream(device=g.device)
@@ -84,6 +84,7 @@ class GradSync:
         in ncclCommDestroy in the first 2-GPU runs); call this first, then destroy the group."""
         import gc
         self.fp.comm_hook = None
+        self.fp.grad_post_scale = 1.0
         cache = self.model.__dict__.pop("_graphed_steps", None)
         if cache:
             for gs in cache.values():

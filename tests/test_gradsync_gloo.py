@@ -49,7 +49,9 @@ def _worker(rank, world, port, q):
         # backward simulation: ranges become final in reverse layer order
         fp = model._fused
         fp.flat_g.copy_(torch.arange(64, dtype=torch.float32) * (rank + 1))
+        assert fp.grad_post_scale == 1.0 / world      # the averaging factor rides on FusedPath's un-scaling pass
         for a, b in ((32, 64), (16, 32), (0, 16)):
+            fp.flat_g[a:b].mul_(fp.grad_post_scale)    # what FusedPath._range_done does before handing the range over
             fp.comm_hook(a, b)
         for k, p in enumerate(sync.head_params):
             p.grad = torch.full_like(p, float((rank + 1) * (k + 1)))
