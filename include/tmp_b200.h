@@ -123,6 +123,12 @@ int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, int T, int H
 int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, int ld, const int32_t* kv_len, int B, int T, int H,
                      const float* lse2, int T_lse, float* delta, float* dQ_acc, void* dQKV, int q_rows, void* stream);
 
+/* Single-query form of the attention backward: the gradient enters through ONE query row `q_row` per sample (the CLS row of
+ * the last fused layer under --mbt-only-vslt 1, mbt_encoder.py:757-763). dO_row / O_row [B,256] fp16 = that row of dO / of the
+ * forward output for every sample; every element of dQKV [B*T,768] is written (zeros where nothing flows). */
+int tmp_attn_bwd_single_query(const void* qkv, const void* dO_row, const void* O_row, const int32_t* kv_len, int B, int T,
+                              int H, int q_row, const float* lse2, int T_lse, void* dQKV, void* stream);
+
 /* ---- a7: bottleneck exchange (mbt_encoder.py:764-776), in place on rows 0..3 of Y_m[B,T_m,256]
  * (fp16) ---------------------------------------------------------------------------------------------------- */
 int tmp_bottleneck_mix_fwd(void* Yv, void* Yi, void* Yt, int Tv, int Ti, int Tt, const long long* missing, int B,

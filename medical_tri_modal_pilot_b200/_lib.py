@@ -34,6 +34,7 @@ SIGNATURES = {
     "tmp_gemm_wgrad": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "tmp_colsum": [_vp, _i, _ll, _i, _vp, _vp],
     "tmp_mma_attn_fwd": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
+    "tmp_attn_bwd_single_query": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "tmp_mma_attn_bwd": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "tmp_bottleneck_mix_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "tmp_bottleneck_mix_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _u32, _vp, _u32, _u32, _u32, _vp],

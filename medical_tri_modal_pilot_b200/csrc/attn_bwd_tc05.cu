@@ -511,6 +511,112 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Single-query attention backward. In the last fused layer under --mbt-only-vslt 1 only the CLS row of the vslt stream has a
+// consumer, so dO is zero everywhere but in ONE query row per sample. The tile kernel above spends 75 us on that (2 048
+// items of one query tile each: all item overhead) plus three memsets; the job is ~165 MB of traffic:
+//   p_k = exp2((q . k_k) * scale_log2 - lse2[b,h,q_row])   for k < len
+//   dV_k = p_k dO        dS_k = p_k (dO . v_k - delta)      dK_k = dS_k q / 8      dQ[q_row] = sum_k dS_k k_k / 8
+// every other dQ row and the dK / dV rows of masked keys are zero. One CTA per (sample, head), one thread per key (stride
+// 128), fp32 math on the CUDA cores, no atomics. dO_row / O_row: [B, 256] fp16 (the CLS rows only), gradients scaled like
+// everywhere else on the 16-bit path.
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_single_query_kernel(const uint16_t* __restrict__ qkv,
+                                                                    const uint16_t* __restrict__ dO_row,
+                                                                    const uint16_t* __restrict__ O_row,
+                                                                    const int32_t* __restrict__ kv_len, int T, int H,
+                                                                    int q_row, const float* __restrict__ lse2, int T_lse,
+                                                                    uint16_t* __restrict__ dQKV, float scale_log2) {
+  __shared__ float sq[HD], sdo[HD], sprod[HD];
+  __shared__ float sred[4][HD];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int len = kv_len ? min(__ldg(kv_len + b), T) : T;
+  const size_t row_base = (size_t)b * T;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool live = q_row < len;
+  if (t < HD) {
+    const float qv = __half2float(__ushort_as_half(qkv[(row_base + q_row) * 768 + h * HD + t]));
+    const float dv = __half2float(__ushort_as_half(dO_row[(size_t)b * 256 + h * HD + t]));
+    const float ov = __half2float(__ushort_as_half(O_row[(size_t)b * 256 + h * HD + t]));
+    sq[t] = qv;
+    sdo[t] = dv;
+    sprod[t] = dv * ov;
+  }
+  __syncthreads();
+  float delta = 0.f;
+#pragma unroll
+  for (int d = 0; d < HD; ++d) delta += sprod[d];     // 64 broadcast reads: same order in every thread
+  const float lse = lse2[((size_t)b * H + h) * T_lse + q_row];
+  float dq[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) dq[d] = 0.f;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int k = t; k < T; k += 128) {
+    uint16_t* out_row = dQKV + (row_base + k) * 768 + h * HD;
+    uint4* dq_out = reinterpret_cast<uint4*>(out_row);
+    uint4* dk_out = reinterpret_cast<uint4*>(out_row + 256);
+    uint4* dv_out = reinterpret_cast<uint4*>(out_row + 512);
+    if (k != q_row) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dq_out[i] = zero4;
+    }
+    if (!live || k >= len) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dk_out[i] = zero4; dv_out[i] = zero4; }
+      continue;
+    }
+    const uint4* kp = reinterpret_cast<const uint4*>(qkv + (row_base + k) * 768 + 256 + h * HD);
+    const uint4* vp = reinterpret_cast<const uint4*>(qkv + (row_base + k) * 768 + 512 + h * HD);
+    uint4 kr[8], vr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { kr[i] = __ldg(kp + i); vr[i] = __ldg(vp + i); }
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t kw[4] = {kr[i].x, kr[i].y, kr[i].z, kr[i].w};
+      const uint32_t vw[4] = {vr[i].x, vr[i].y, vr[i].z, vr[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 kf = unpack2<FMT_F16>(kw[j]), vf = unpack2<FMT_F16>(vw[j]);
+        const int d = i * 8 + j * 2;
+        s = fmaf(sq[d], kf.x, s); s = fmaf(sq[d + 1], kf.y, s);
+        dp = fmaf(sdo[d], vf.x, dp); dp = fmaf(sdo[d + 1], vf.y, dp);
+      }
+    }
+    const float p = ex2_approx(fmaf(s, scale_log2, -lse));
+    const float ds = p * (dp - delta) * 0.125f;      // d/d(q.k) incl. the 1/sqrt(64) of the score
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t kw[4] = {kr[i].x, kr[i].y, kr[i].z, kr[i].w};
+      uint32_t ok[4], ov[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 kf = unpack2<FMT_F16>(kw[j]);
+        const int d = i * 8 + j * 2;
+        dq[d] = fmaf(ds, kf.x, dq[d]);
+        dq[d + 1] = fmaf(ds, kf.y, dq[d + 1]);
+        ok[j] = pack_f16x2(ds * sq[d], ds * sq[d + 1]);
+        ov[j] = pack_f16x2(p * sdo[d], p * sdo[d + 1]);
+      }
+      dk_out[i] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+      dv_out[i] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    }
+  }
+  // dQ[q_row] = sum over the keys of all threads
+#pragma unroll
+  for (int d = 0; d < HD; ++d) {
+    float v = dq[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[warp][d] = v;
+  }
+  __syncthreads();
+  if (t < HD) {
+    const float v = live ? (sred[0][t] + sred[1][t]) + (sred[2][t] + sred[3][t]) : 0.f;
+    dQKV[(row_base + q_row) * 768 + h * HD + t] = __half_as_ushort(__float2half_rn(v));
+  }
+}
+
 // delta[b,h,q] = sum_d dO[b,q,h*64+d] * O[b,q,h*64+d]   (one warp per row; rows past T_lse padding are zeroed)
 __global__ void attn_bwd_delta_kernel(const uint16_t* __restrict__ O, const uint16_t* __restrict__ dO, int ld, int B, int T,
                                       int H, float* __restrict__ delta, int T_lse) {
@@ -621,4 +727,17 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
   const size_t rows = (size_t)B * T;
   attn_bwd_dq_convert_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(dQ_acc, (uint16_t*)dQKV, rows);
   return tmp::check_launch("attn_bwd_dq_convert_kernel");
+}
+
+// Single-query form (see attn_bwd_single_query_kernel): dO_row / O_row [B,256] fp16 hold the one query row `q_row` of every
+// sample that carries a gradient; writes ALL of dQKV [B*T,768] (zeros where nothing flows).
+extern "C" int tmp_attn_bwd_single_query(const void* qkv, const void* dO_row, const void* O_row, const int32_t* kv_len, int B,
+                                         int T, int H, int q_row, const float* lse2, int T_lse, void* dQKV, void* stream) {
+  TMP_REQUIRE(qkv && dO_row && O_row && lse2 && dQKV, "attn_bwd_single_query: null operand");
+  TMP_REQUIRE(B > 0 && T > 0 && H == 4 && q_row >= 0 && q_row < T && T_lse >= T,
+              "attn_bwd_single_query: need B>0, T>0, H==4, 0 <= q_row < T <= T_lse");
+  attn_bwd_single_query_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)qkv, (const uint16_t*)dO_row, (const uint16_t*)O_row, kv_len, T, H, q_row, lse2, T_lse,
+      (uint16_t*)dQKV, kLog2e / 8.0f);
+  return tmp::check_launch("attn_bwd_single_query_kernel");
 }

@@ -194,6 +194,16 @@ def attn_fwd(qkv, kv_len, B, T, O, lse2, q_rows=None):
                                        T if q_rows is None else q_rows, stream_ptr()), "tmp_mma_attn_fwd")
 
 
+def attn_bwd_single_query(qkv, dO_row, O_row, kv_len, B, T, q_row, lse2, dQKV):
+    """Attention backward when only query row `q_row` of every sample carries a gradient (dO_row / O_row: [B,256] fp16).
+    Writes all of dQKV [B*T,768]."""
+    for t_, nm in ((qkv, "qkv"), (dO_row, "dO_row"), (O_row, "O_row"), (dQKV, "dQKV")):
+        _cuda_contig(t_, torch.float16, nm)
+    check(_lib.load().tmp_attn_bwd_single_query(ptr(qkv), ptr(dO_row), ptr(O_row), ptr(kv_len), B, T, H, int(q_row),
+                                                ptr(lse2), lse2.shape[-1], ptr(dQKV), stream_ptr()),
+          "tmp_attn_bwd_single_query")
+
+
 def attn_bwd(qkv, O, dO, kv_len, B, T, lse2, delta, dQ_acc, dQKV, q_rows=None):
     if _f32(qkv):
         return check(_lib.load().tmp_attn_bwd_f32(ptr(qkv), ptr(O), ptr(dO), O.shape[-1], ptr(kv_len), B, T, H, ptr(lse2),

@@ -58,6 +58,7 @@ class FusedPath:
         self.grad_post_scale = 1.0   # extra factor folded into the un-scaling pass (GradSync: 1 / world_size)
         self.skip_missing = True
         self.fuse_grad_dropout = os.environ.get("TMP_B200_FUSE_GRAD_DROPOUT", "1") != "0"   # A/B switch
+        self.cls_attn_bwd_fast = os.environ.get("TMP_B200_CLS_ATTN_BWD_GENERIC") is None    # A/B switch
         self.grads_fresh = False  # set by backward(), cleared by optim.FlatAdamW.step()
         self.debug_trace = None   # dict -> backward() records per-layer input gradients (debugging aid)
         # img / txt modality streams on side CUDA streams (TMP_B200_SINGLE_STREAM=1 serialises them: debugging aid)
@@ -452,11 +453,16 @@ class FusedPath:
         # the attention's dO / delta / dQ are zero everywhere but in the CLS rows
         st["g_h"].zero_()
         st["g_h"].view(B, T, D)[:, 4, :] = st["c_gh"]
-        st["delta"].zero_()
-        st["delta"][:, :, 4] = (st["c_gh"].float().view(B, 4, 64) * st["c_o"].float().view(B, 4, 64)).sum(-1)
-        st["g_qkv"][:, :D].zero_()
-        ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][0], B, T, st["lse"][l], st["delta"], None,
-                     st["g_qkv"], q_rows=5)
+        if self.cls_attn_bwd_fast:
+            # one query row per sample: the single-query kernel (delta, zero rows and all of dQ|dK|dV in one pass)
+            ops.attn_bwd_single_query(st["qkv"][l], st["c_gh"], st["c_o"], ctx["kv_len"][0], B, T, 4, st["lse"][l],
+                                      st["g_qkv"])
+        else:
+            st["delta"].zero_()
+            st["delta"][:, :, 4] = (st["c_gh"].float().view(B, 4, 64) * st["c_o"].float().view(B, 4, 64)).sum(-1)
+            st["g_qkv"][:, :D].zero_()
+            ops.attn_bwd(st["qkv"][l], st["O"][l], st["g_h"], ctx["kv_len"][0], B, T, st["lse"][l], st["delta"], None,
+                         st["g_qkv"], q_rows=5)
         ops.gemm(st["g_qkv"], self.wT[(l, 0, "qkv")], out=st["g_xn"])
         ops.gemm_wgrad(st["g_qkv"], st["xn"][l], g.wqkv, dbias=g.bqkv)
         # LN1 (+ residual); the same pass writes dropout(dX[l]) for the layer below (its FFN2 output dropout mask): g_yd is

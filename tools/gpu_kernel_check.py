@@ -541,6 +541,22 @@ def case_attn_bwd():
         res[f"fused_dK_B{B}_T{T}"] = _err(dQKV2[:, 256:512], g[:, 256:512])
         res[f"fused_dV_B{B}_T{T}"] = _err(dQKV2[:, 512:], g[:, 512:])
         res[f"fused_zero_B{B}_T{T}"] = {"rel_to_max": 0.0 if zero_ok else 1.0, "finite": True}
+        # single-query form (CLS-only last layer): dO is zero except in ONE query row per sample; compare with autograd of the
+        # reference attention under that dO (query row 4 is live in every sample with kv_len > 4; de-selected samples and
+        # samples shorter than the row get all-zero gradients)
+        q_row = 4 if T > 4 else 0
+        dO1 = torch.zeros(B, T, 256, device=dev)
+        row = torch.randn(B, 256, device=dev).to(GRD)
+        dO1[:, q_row, :] = row.float() * (kv > q_row)[:, None]
+        qf1 = qkv.float().requires_grad_(True)
+        _attn_ref(qf1, kv, B, T).backward(dO1)
+        g1 = qf1.grad.view(B * T, 768)
+        dQKV3 = torch.full((B * T, 768), 3.0, device=dev, dtype=GRD)
+        ops.attn_bwd_single_query(qkv, row.contiguous(), O.view(B, T, 256)[:, q_row, :].contiguous(), kv, B, T, q_row, lse,
+                                  dQKV3)
+        res[f"single_dQ_B{B}_T{T}"] = _err(dQKV3[:, :256], g1[:, :256])
+        res[f"single_dK_B{B}_T{T}"] = _err(dQKV3[:, 256:512], g1[:, 256:512])
+        res[f"single_dV_B{B}_T{T}"] = _err(dQKV3[:, 512:], g1[:, 512:])
     res["ok"] = all(v["rel_to_max"] < 5e-3 and v["finite"] for v in res.values() if isinstance(v, dict))
     return res
 
