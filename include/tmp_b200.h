@@ -157,9 +157,10 @@ int tmp_adamw_step(float* w, const float* g, float* m, float* v, long long n, fl
 /* same update with the learning rate and the step count read from DEVICE words -- the form a captured CUDA graph replays.
  * lr_dev: fp32. step_dev: int32[3] = {optimizer calls so far (>= 1, incremented by the caller before this call), calls
  * skipped, last call whose gradient was non-finite}: when step_dev[2] == step_dev[0] the call leaves w, m, v untouched and
- * increments step_dev[1]; bias corrections use step_dev[0] - step_dev[1] (evaluated in the kernel). */
+ * increments step_dev[1] (only if count_skip != 0: a second launch of the same step over another buffer passes 0); bias
+ * corrections use step_dev[0] - step_dev[1] (evaluated in the kernel). */
 int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1,
-                       float beta2, float eps, float weight_decay, int32_t* step_dev, void* stream);
+                       float beta2, float eps, float weight_decay, int32_t* step_dev, int count_skip, void* stream);
 /* state[2] <- state[0] if any of g[0..n) (fp32, n % 4 == 0) is inf or NaN: the overflow guard of the 16-bit plan (gradients
  * pass through fp16 scratch with a static scale). Call it on the fully reduced gradient, before tmp_adamw_step_dev. */
 int tmp_grad_nonfinite(const float* g, long long n, int32_t* state, void* stream);

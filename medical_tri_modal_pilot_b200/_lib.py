@@ -41,7 +41,7 @@ SIGNATURES = {
     "tmp_dropout_apply": [_vp, _vp, _ll, _f, _u32, _u32, _vp, _vp],
     "tmp_cast_weights": [_vp, _i, _i, _i, _vp],
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
-    "tmp_adamw_step_dev": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _vp],
+    "tmp_adamw_step_dev": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _i, _vp],
     "tmp_grad_nonfinite": [_vp, _ll, _vp, _vp],
     # fp32 ("precise") mode: same operators on fp32-stored tensors, bf16x3 operand split, CUDA-core fp32 attention
     "tmp_layernorm_fwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],

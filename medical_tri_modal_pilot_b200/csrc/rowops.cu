@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ w, cons
                                                     float lr, float b1, float b2, float eps, float wd,
                                                     float inv_bc1, float inv_sqrt_bc2,
                                                     const float* __restrict__ lr_dev,
-                                                    int32_t* __restrict__ step_dev) {
+                                                    int32_t* __restrict__ step_dev, int count_skip) {
   if (DEV) {
     // learning rate / step count live in device memory (CUDA-graph replays): bias corrections per thread, in double
     // like the host path (pow of a handful of values, once per thread).
@@ -396,7 +396,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ w, cons
     // w, m, v untouched and does not count as an optimizer step (what torch.cuda.amp.GradScaler does on the host).
     const int calls = step_dev[0], skipped = step_dev[1], bad = step_dev[2];
     if (bad == calls) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) step_dev[1] = skipped + 1;   // nobody else reads it in a skipped call
+      // nobody else reads it in a skipped call; count_skip == 0: a second launch of the same optimizer step (the head
+      // parameters' flat buffer) that shares the words but must not count the skip twice
+      if (count_skip && blockIdx.x == 0 && threadIdx.x == 0) step_dev[1] = skipped + 1;
       return;
     }
     lr = __ldg(lr_dev);
@@ -664,7 +666,7 @@ extern "C" int tmp_adamw_step(float* w, const float* g, float* m, float* v, long
   const long long n4 = n / 4;
   adamw_kernel<false><<<adamw_grid(n4), 256, 0, (cudaStream_t)stream>>>(
       (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
-      (float)(1.0 / sqrt(bc2)), nullptr, nullptr);
+      (float)(1.0 / sqrt(bc2)), nullptr, nullptr, 0);
   return tmp::check_launch("adamw_kernel");
 }
 
@@ -677,12 +679,12 @@ extern "C" int tmp_grad_nonfinite(const float* g, long long n, int32_t* state, v
 
 extern "C" int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n, const float* lr_dev,
                                   float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev,
-                                  void* stream) {
+                                  int count_skip, void* stream) {
   TMP_REQUIRE(w && g && m && v && lr_dev && step_dev && n >= 0 && n % 4 == 0, "adamw_step_dev: bad argument");
   if (n == 0) return TMP_OK;
   const long long n4 = n / 4;
   adamw_kernel<true><<<adamw_grid(n4), 256, 0, (cudaStream_t)stream>>>(
       (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, lr_dev,
-      step_dev);
+      step_dev, count_skip);
   return tmp::check_launch("adamw_kernel");
 }

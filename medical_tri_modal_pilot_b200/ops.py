@@ -262,7 +262,7 @@ def grad_nonfinite(g, state):
     check(_lib.load().tmp_grad_nonfinite(ptr(g), g.numel(), ptr(state), stream_ptr()), "tmp_grad_nonfinite")
 
 
-def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev):
+def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev, count_skip=True):
     """Same update with lr (fp32 [1]) and the step words (int32 [3]: calls, skipped, last call with a non-finite
     gradient -- a flagged call is skipped and not counted) read from device memory: CUDA-graph replayable."""
     for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v"), (lr_dev, "lr_dev")):
@@ -271,7 +271,8 @@ def adamw_step_dev(w, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step_dev
     if step_dev.numel() < 3:
         raise ValueError("adamw_step_dev: step_dev must hold 3 int32 words (calls, skipped, last bad call)")
     check(_lib.load().tmp_adamw_step_dev(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(lr_dev), float(beta1),
-                                         float(beta2), float(eps), float(weight_decay), ptr(step_dev), stream_ptr()),
+                                         float(beta2), float(eps), float(weight_decay), ptr(step_dev), int(count_skip),
+                                         stream_ptr()),
           "tmp_adamw_step_dev")
 
 

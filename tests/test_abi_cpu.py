@@ -44,7 +44,7 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc < 0 and "H==4" in _lib.last_error()
     rc = lib.tmp_adamw_step(1, 1, 1, 1, 6, 0.1, 0.9, 0.999, 1e-8, 0.0, 1, None)
     assert rc < 0
-    rc = lib.tmp_adamw_step_dev(1, 1, 1, 1, 8, None, 0.9, 0.999, 1e-8, 0.0, None, None)
+    rc = lib.tmp_adamw_step_dev(1, 1, 1, 1, 8, None, 0.9, 0.999, 1e-8, 0.0, None, 1, None)
     assert rc < 0
 
 
