@@ -328,7 +328,8 @@ def run_b200(a):
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        trainer.ddp_setup_env()      # NCCL may take as many CTAs as GradSync keeps SMs free of compute CTAs
+        dist.init_process_group("nccl", device_id=dev, pg_options=trainer.ddp_pg_options())
     _lib.load()
 
     n_img = 3 if a.multiimages else 1

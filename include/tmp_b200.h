@@ -30,6 +30,15 @@ extern "C" {
 int tmp_abi_version(void);
 const char* tmp_last_error(void);
 
+/* ---- e: SMs left to communication kernels -----------------------------------------------------------------
+ * Every persistent / one-wave grid of the library is sized from (physical SMs - reserved) with equal work per CTA.
+ * Data-parallel runs reserve a few SMs for NCCL's all-reduce CTAs (GradSync, trainer.py; the reference has no
+ * multi-GPU path): a compute kernel that finds SMs taken would otherwise run its last CTAs as a second
+ * wave. n in [0, 64); also read once from env TMP_B200_RESERVE_SMS. Call before capturing a CUDA graph of the step.
+ * tmp_num_sms: the count grid sizing currently uses. */
+int tmp_set_reserved_sms(int n);
+int tmp_num_sms(void);
+
 /* ---- a3/a4/a14: lengths and masks ------------------------------------------------------------------------
  * kv_len[3,B] int32 = number of attendable keys per (stream, sample) INCLUDING the 4 bottleneck keys and CLS.
  * Replaces get_attn_pad_mask/get_non_pad_mask (builder/models/src/transformer/utils.py:79-125) as called from

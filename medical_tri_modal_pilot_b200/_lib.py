@@ -19,6 +19,8 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "tmp_abi_version": [],
     "tmp_last_error": [],
+    "tmp_set_reserved_sms": [_i],
+    "tmp_num_sms": [],
     "tmp_build_lengths": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "tmp_debug_materialize_mask": [_vp, _i, _i, _vp, _vp],
     "tmp_umse_embed_fwd": [_vp, _ll, _pp, _pp, _vp, _vp, _i, _vp],

@@ -1,6 +1,7 @@
 // common.cu -- error string, driver entry-point lookup for TMA descriptors, device properties.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -78,16 +79,35 @@ static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* 
   return TMP_OK;
 }
 
+// SMs that grid sizing may use = physical SMs - reserved. Every persistent / one-wave grid of this library is sized from
+// this number with EQUAL work per CTA, so a kernel that finds a few SMs taken (NCCL's all-reduce CTAs during the
+// data-parallel backward) runs its last CTAs as a second wave and takes twice as long. With R SMs left to the
+// communication kernels (tmp_set_reserved_sms, or env TMP_B200_RESERVE_SMS) both fit side by side.
+static int g_reserved_sms = -1;
+
 int num_sms() {
   static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  return n;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  if (g_reserved_sms < 0) {
+    const char* e = getenv("TMP_B200_RESERVE_SMS");
+    g_reserved_sms = e ? atoi(e) : 0;
+    if (g_reserved_sms < 0) g_reserved_sms = 0;
+  }
+  const int avail = n - g_reserved_sms;
+  return avail > 0 ? avail : 1;
 }
 
 }  // namespace tmp
 
 extern "C" const char* tmp_last_error(void) { return tmp::g_err; }
-extern "C" int tmp_abi_version(void) { return 4; }   // 4: tmp_grad_nonfinite, three-word step_dev of tmp_adamw_step_dev (3: q_rows, fused attn_bwd protocol, fp32 mode)
+extern "C" int tmp_set_reserved_sms(int n) {
+  TMP_REQUIRE(n >= 0 && n < 64, "set_reserved_sms: n must be in [0, 64)");
+  tmp::g_reserved_sms = n;
+  return TMP_OK;
+}
+extern "C" int tmp_num_sms(void) { return tmp::num_sms(); }
+extern "C" int tmp_abi_version(void) { return 5; }   // 5: tmp_set_reserved_sms / tmp_num_sms; 4: tmp_grad_nonfinite, three-word step_dev of tmp_adamw_step_dev (3: q_rows, fused attn_bwd protocol, fp32 mode)

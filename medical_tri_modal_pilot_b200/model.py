@@ -181,12 +181,15 @@ class TRI_MBT_VSLTCLS(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("TRI_MBT_VSLTCLS (B200) needs CUDA tensors: the fused path has no CPU fallback")
         B = x.shape[0]
-        demographic = torch.cat([age.unsqueeze(1), gen.unsqueeze(1)], dim=1).float()
-        demo_embedding = self.ie_demo(demographic)
         missing = self.tri_missing_code(missing, B, x.device)
         # the frozen image encoder runs INSIDE the fused path, on the img modality's CUDA stream (FusedPath.forward calls
         # encode_images there), so the vslt / txt streams of layer 0 overlap it
         cls_out = self._fused(x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing)
+        # the demographic branch (reference tri_mbt_vsltcls.py:176-177, in front of the encoder there) is evaluated AFTER the fused path: its
+        # autograd nodes are then younger than the fused function's, so the engine runs their backward first and every head
+        # gradient exists when dL/dCLS reaches the fused backward (trainer.GradSync averages them during that backward)
+        demographic = torch.cat([age.unsqueeze(1), gen.unsqueeze(1)], dim=1).float()
+        demo_embedding = self.ie_demo(demographic)
         classInput = self.layer_norms_after_concat(cls_out)
         classInput = torch.cat([classInput, demo_embedding], dim=1)
         if "rmse" in getattr(self.args, "auxiliary_loss_type", "none"):

@@ -40,6 +40,18 @@ def _cuda_contig(t, dtype=None, name="tensor"):
     return t
 
 
+def set_reserved_sms(n: int) -> None:
+    """Leave n SMs to communication kernels: every persistent / one-wave grid is sized from (SMs - n). Call before a CUDA
+    graph of the step is captured (include/tmp_b200.h, tmp_set_reserved_sms)."""
+    lib = _lib.load()
+    if lib.tmp_set_reserved_sms(int(n)) != 0:
+        raise RuntimeError(f"tmp_set_reserved_sms failed: {_lib.last_error()}")
+
+
+def num_sms() -> int:
+    return int(_lib.load().tmp_num_sms())
+
+
 def lse_len(T: int) -> int:
     return (T + 127) // 128 * 128
 

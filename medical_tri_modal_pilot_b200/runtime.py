@@ -55,6 +55,7 @@ class FusedPath:
         self._ws_cache = {}       # (B, L, n_img) -> workspace dict (small LRU; captured graphs pin theirs, see pin())
         self._ctx_token = 0
         self.comm_hook = None     # optional callable(a, b): flat_g[a:b] is final (trainer.GradSync all-reduces it)
+        self.head_hook = None     # optional callable(): dL/dCLS has arrived, the classifier head's backward has run
         self.grad_post_scale = 1.0   # extra factor folded into the un-scaling pass (GradSync: 1 / world_size)
         self.skip_missing = True
         self.fuse_grad_dropout = os.environ.get("TMP_B200_FUSE_GRAD_DROPOUT", "1") != "0"   # A/B switch
@@ -308,31 +309,36 @@ class FusedPath:
         if training:
             self.step_dev.add_(1)
         ctx = dict(B=B, L=L, n_img=n_img, p=p, seed=self.seed_base, seed_dev=self.step_dev)
-        ctx["x"] = x.float().contiguous()
         ctx["img_time"] = img_time.float().reshape(B, n_img).contiguous()
-        ctx["txt_time"] = txt_time.float().contiguous()
         ctx["missing"] = missing.to(torch.long).contiguous()
-        T = self.T
-        ctx["kv_len"] = ops.build_lengths(input_lengths.to(torch.long).contiguous(), txt_lengths.to(torch.long).contiguous(),
-                                          ctx["img_time"], n_img, m.multiimages, ctx["missing"], int(self.skip_missing),
-                                          T[0], T[1], T[2])
         f32 = self.precision == "fp32"
         ctx["f32"] = f32
-        if not f32:
-            # refresh fp16 (+ transposed) parameter copies
-            ops.cast_weights(self.cast_descs, 1, self.total // 256, 256)              # flat fp32 -> fp16
-            ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
-        # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
         adt = torch.float32 if f32 else ACT
         Wop = self.W if f32 else self.H16       # GEMM weight operand: fp32 master (split in ops.gemm) or the fp16 copy
         # The three modality streams of a layer are independent until the bottleneck exchange (mbt_encoder.py:744-776):
         # vslt runs on the caller's stream, img / txt on two side streams, joined at every exchange. The frozen image
-        # encoder runs at the head of the img lane.
+        # encoder runs at the head of the img lane. It is the critical path of the forward pass (5 ms of kernels; the other
+        # lanes wait for it at the first exchange) and needs nothing but the pixels, `missing` and `img_time`, so the lane is
+        # forked BEFORE the per-step preparation of the other lanes (input casts, kv_len, the fp16 weight refresh: 0.18 ms
+        # that used to run in front of it); `_ev_prep` marks the point from which the refreshed fp16 weights may be read.
         self._fork()
         with self._lane(1):
             img_feats = m.encode_images(img, missing=ctx["missing"] if self.skip_missing else None, ready=ready.get("img"),
                                         img_time=ctx["img_time"])
             ctx["img16"] = img_feats.reshape(B * 49 * n_img, 768).to(adt).contiguous()
+        ctx["x"] = x.float().contiguous()
+        ctx["txt_time"] = txt_time.float().contiguous()
+        T = self.T
+        ctx["kv_len"] = ops.build_lengths(input_lengths.to(torch.long).contiguous(), txt_lengths.to(torch.long).contiguous(),
+                                          ctx["img_time"], n_img, m.multiimages, ctx["missing"], int(self.skip_missing),
+                                          T[0], T[1], T[2])
+        if not f32:
+            # refresh fp16 (+ transposed) parameter copies
+            ops.cast_weights(self.cast_descs, 1, self.total // 256, 256)              # flat fp32 -> fp16
+            ops.cast_weights(self.cast_descs[32:], self.n_desc - 1, 1024, 1024)        # transposed GEMM weights
+        self._prep_done()
+        # 768 -> 256 projections of the text tokens and image patches (tri_mbt_vsltcls.py:200, 210-211)
+        with self._lane(1):
             ops.gemm(ctx["img16"], Wop("linear.weight", D, 768), out=self.proj[1], bias=self.W("linear.bias", D))
             ops.stream_prologue_fwd(X0=self.ws[1]["X"][0], **self._prologue_args(1, ctx))
         with self._lane(2):
@@ -371,6 +377,7 @@ class FusedPath:
         if getattr(self, "_side", None) is None or self._side_dev != self.device:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
             self._ev_main = torch.cuda.Event()
+            self._ev_prep = torch.cuda.Event()
             self._ev_side = [torch.cuda.Event() for _ in range(2)]
             self._side_dev = self.device
 
@@ -387,6 +394,15 @@ class FusedPath:
         self._ev_main.record()
         for st in self._side:
             st.wait_event(self._ev_main)
+
+    def _prep_done(self):
+        """side lanes wait for everything issued so far on the caller's stream (second fork point of the forward pass: the
+        lanes were forked earlier and already hold work of their own)"""
+        if not self.multi_stream:
+            return
+        self._ev_prep.record()
+        for st in self._side:
+            st.wait_event(self._ev_prep)
 
     def _join(self):
         """the caller's stream waits for everything issued so far on the side lanes"""
@@ -486,6 +502,8 @@ class FusedPath:
                                "were overwritten. Run backward before the next forward.")
         if ctx["ws"] is not self._ws_cur:
             self._ensure_workspace(ctx["B"], ctx["L"], ctx["n_img"])
+        if self.head_hook is not None:
+            self.head_hook()
         # Gradient accumulation (a second backward without zero_grad in between): the kernels WRITE the flat gradient
         # buffer (and unscale it range by range), so the gradients still attached to the parameters are set aside and
         # added back at the end. After zero_grad(set_to_none=True) -- the torch default -- this costs nothing.

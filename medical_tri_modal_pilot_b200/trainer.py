@@ -28,13 +28,52 @@ def missing_to_num(missing: torch.Tensor) -> torch.Tensor:
     return 2 * m[:, 1] + m[:, 2]
 
 
+DDP_RESERVE_SMS_DEFAULT = 0
+
+
+def ddp_reserved_sms() -> int:
+    """SMs left to NCCL in data-parallel runs (env TMP_B200_DDP_RESERVE_SMS, default DDP_RESERVE_SMS_DEFAULT)."""
+    import os
+    return int(os.environ.get("TMP_B200_DDP_RESERVE_SMS", str(DDP_RESERVE_SMS_DEFAULT)))
+
+
+def ddp_setup_env() -> int:
+    """Call BEFORE `init_process_group`: caps the CTAs NCCL may use per collective (env NCCL_MAX_CTAS, read when the
+    communicator is created) at the number of SMs `GradSync` keeps free of compute CTAs. Returns that number."""
+    import os
+    r = ddp_reserved_sms()
+    if r > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(r))
+        os.environ.setdefault("NCCL_MIN_CTAS", str(min(r, 4)))
+    return r
+
+
+def ddp_pg_options():
+    """`pg_options` for `init_process_group("nccl", ...)`: NCCL's kernels on high-priority streams. The compute kernels are
+    persistent grids that hold every SM; an all-reduce launched next to them gets its CTAs scheduled one by one as SMs
+    drain, and it occupies those SMs for as long as its LAST channel is still waiting for one. High priority lets the block
+    scheduler place NCCL's CTAs first (env TMP_B200_DDP_HIGH_PRIO=0 turns it off for A/B runs)."""
+    import os
+    if os.environ.get("TMP_B200_DDP_HIGH_PRIO", "1") == "0":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 class GradSync:
     """Bucketed gradient all-reduce overlapped with the fused backward (NCCL, or gloo in the CPU tests).
 
     Attach with `GradSync(model, process_group)`; `missing_trainer` calls `finish()` between backward and
-    optimizer.step(). Averaging: every range is pre-divided by world_size on the compute stream, then summed."""
+    optimizer.step(). Averaging: every range is pre-divided by world_size on the compute stream, then summed.
 
-    def __init__(self, model, group=None, broadcast_from: int | None = 0, overlap: bool = True):
+    `reserve_sms` (default: `ddp_reserved_sms()`): SMs kept free of compute CTAs for NCCL's kernels. The compute kernels
+    are persistent / one-wave grids with equal work per CTA, so a kernel launched while NCCL holds a few SMs ran its last
+    CTAs as a second wave (twice its time) -- the bulk of the 0.45 ms/step that data parallelism cost from N = 2 on.
+    Pair it with `ddp_setup_env()` before `init_process_group` so that NCCL does not take more CTAs than that."""
+
+    def __init__(self, model, group=None, broadcast_from: int | None = 0, overlap: bool = True,
+                 reserve_sms: int | None = None):
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group)
@@ -43,10 +82,15 @@ class GradSync:
         self.comm_stream = None
         self.head_params = [p for n, p in model.named_parameters()
                             if p.requires_grad and not n.startswith("img_encoder.") and not self._is_fused(n)]
-        self._head_flat = None
+        self._head_done = set()      # ids of the head parameters whose gradient went out early (head_early)
         self.n_collectives = 0
         self.fp.comm_hook = self._on_range_ready
+        self.fp.head_hook = self._head_early
         self.fp.grad_post_scale = 1.0 / self.world      # averaging rides on the un-scaling pass of every range
+        self.reserve_sms = ddp_reserved_sms() if reserve_sms is None else int(reserve_sms)
+        if self.world > 1 and self.reserve_sms > 0 and next(model.parameters()).is_cuda:
+            from . import ops
+            ops.set_reserved_sms(self.reserve_sms)
         object.__setattr__(model, "grad_sync", self)      # found by train_step; not a submodule / state_dict entry
         if broadcast_from is not None:
             self.broadcast_parameters(broadcast_from)
@@ -61,22 +105,50 @@ class GradSync:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src, group=self.group)
 
+    def _comm(self, dev):
+        """The communication stream, made to wait for everything issued so far on the current stream."""
+        if self.comm_stream is None:
+            import os
+            hi = os.environ.get("TMP_B200_DDP_HIGH_PRIO", "1") != "0"
+            self.comm_stream = torch.cuda.Stream(device=dev, priority=-1 if hi else 0)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        return self.comm_stream
+
     # called by FusedPath.backward on the compute stream once flat_g[a:b] is final (unscaled and pre-divided by world_size)
     def _on_range_ready(self, a: int, b: int):
         g = self.fp.flat_g[a:b]
         if self.world == 1:
             return
         if g.is_cuda and self.overlap:
-            if self.comm_stream is None:
-                self.comm_stream = torch.cuda.Stream(device=g.device)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self.comm_stream.wait_event(ev)
-            with torch.cuda.stream(self.comm_stream):
+            with torch.cuda.stream(self._comm(g.device)):
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         self.n_collectives += 1
+
+    def _head_bucket(self, params):
+        """Average the gradients of `params` over the ranks: one flat bucket, three launches around the collective."""
+        grads = [p.grad for p in params]
+        flat = torch.cat([g.reshape(-1) for g in grads]).mul_(1.0 / self.world)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.n_collectives += 1
+        with torch.no_grad():
+            torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+    # called by FusedPath.backward when dL/dCLS arrives, i.e. after autograd has run the classifier head's backward: the
+    # head gradients that exist by then are averaged on the communication stream while the fused backward runs
+    def _head_early(self):
+        self._head_done = set()
+        if self.world == 1 or not self.overlap:
+            return
+        ready = [p for p in self.head_params if p.grad is not None]
+        if not ready or not ready[0].grad.is_cuda:
+            return
+        with torch.cuda.stream(self._comm(ready[0].grad.device)):
+            self._head_bucket(ready)
+        self._head_done = {id(p) for p in ready}
 
     def close(self):
         """Detach from the model and drop every captured step graph that references the communicator. A process group
@@ -84,6 +156,7 @@ class GradSync:
         in ncclCommDestroy in the first 2-GPU runs); call this first, then destroy the group."""
         import gc
         self.fp.comm_hook = None
+        self.fp.head_hook = None
         self.fp.grad_post_scale = 1.0
         cache = self.model.__dict__.pop("_graphed_steps", None)
         if cache:
@@ -98,19 +171,14 @@ class GradSync:
             torch.cuda.synchronize()
 
     def finish(self):
-        """Head bucket + join the communication stream. Call after loss.backward(), before optimizer.step()."""
+        """Head parameters not covered by `_head_early` + join the communication stream. Call after loss.backward(),
+        before optimizer.step()."""
         if self.world == 1:
             return
-        live = [p for p in self.head_params if p.grad is not None]
+        live = [p for p in self.head_params if p.grad is not None and id(p) not in self._head_done]
+        self._head_done = set()
         if live:
-            flat = torch.cat([p.grad.reshape(-1) for p in live]).mul_(1.0 / self.world)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.n_collectives += 1
-            off = 0
-            for p in live:
-                n = p.numel()
-                p.grad.copy_(flat[off: off + n].view_as(p.grad))
-                off += n
+            self._head_bucket(live)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in funcs:
         assert hasattr(lib, name), f"{name} declared in include/tmp_b200.h but not exported"
     lib.tmp_abi_version.restype = ctypes.c_int
-    assert lib.tmp_abi_version() == 4
+    assert lib.tmp_abi_version() == 5
 
 
 def test_ctypes_table_matches_header():

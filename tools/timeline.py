@@ -30,17 +30,29 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--graph", action="store_true", help="profile a CUDA-graph replay instead of an eager step")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
+    ap.add_argument("--steps", type=int, default=1, help="profile this many back-to-back steps (steady state)")
+    ap.add_argument("--dump", action="store_true", help="also write every kernel record (name, stream, start us, us)")
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    # under torchrun (WORLD_SIZE > 1): the data-parallel step (GradSync over NCCL); rank 0 writes its own timeline
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        trainer.ddp_setup_env()
+        dist.init_process_group("nccl", device_id=dev, pg_options=trainer.ddp_pg_options())
     args = make_args(transformer_num_layers=6, multiimages=1, mbt_only_vslt=1, input_types="vslt_img_txt",
                      imgtxt_time=1, dropout=0.1, batch_size=a.batch, img_pretrain="No", TIE_len=a.tie_len)
     args.device = dev
     torch.manual_seed(0)
     model = get_model(args)(args).to(dev).train()
+    if world > 1:
+        trainer.GradSync(model)
     opt = FlatAdamW(model, lr=1e-4, weight_decay=1e-6)
     crit = torch.nn.BCEWithLogitsLoss()
-    host = synth.make_batch(a.batch, a.tie_len, n_img=3, seed=1000, full_length=True, missing_mode="none",
+    host = synth.make_batch(a.batch, a.tie_len, n_img=3, seed=1000 + rank, full_length=True, missing_mode="none",
                             with_pixels=True, feats=False)
     miss = host["missing"]
     host["missing3"] = torch.stack([torch.zeros_like(miss), (miss >= 2).long(), (miss % 2).long()], 1).float()
@@ -61,8 +73,14 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        step(5)
+        for i in range(a.steps):
+            step(5 + i)
         torch.cuda.synchronize()
+    if rank != 0:
+        import torch.distributed as dist
+        dist.barrier()
+        model.grad_sync.close()
+        os._exit(0)
     tmp = a.out + ".trace.json"
     prof.export_chrome_trace(tmp)
     ev = json.load(open(tmp))["traceEvents"]
@@ -113,7 +131,7 @@ def main():
         by_name[n][1] += 1
     out = {
         "mode": "graph replay" if a.graph else "eager",
-        "span_ms": (t1 - t0) / 1e3, "busy_ms": busy / 1e3, "idle_ms": (t1 - t0 - busy) / 1e3,
+        "steps": a.steps, "span_ms": (t1 - t0) / 1e3, "busy_ms": busy / 1e3, "idle_ms": (t1 - t0 - busy) / 1e3,
         "concurrent_ms": conc / 1e3, "kernel_sum_ms": sum(e["dur"] for e in ks) / 1e3, "n_kernels": len(ks),
         "streams": {str(k): {"busy_ms": v[0] / 1e3, "n": v[1]} for k, v in streams.items()},
         "top_gaps_us": [{"gap": g[0], "at_ms": g[1] / 1e3, "after": g[2], "before": g[3]} for g in gaps[:25]],
@@ -156,13 +174,22 @@ def main():
         if small(e):
             seq.append([round((e["ts"] - t0) / 1e3, 3), round(e["dur"], 1), e["name"].replace("(anonymous namespace)::", "")[:80]])
     out["small_kernel_sequence"] = seq
+    out["world"] = world
+    if a.dump:
+        out["kernels"] = [[e["name"].replace("(anonymous namespace)::", "").replace("void ", "")[:48], e["args"].get("stream", -1),
+                           round(e["ts"] - t0, 1), round(e["dur"], 1), e["args"].get("grid", [0])[0]] for e in ks]
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
-    print(json.dumps({k: v for k, v in out.items() if k not in ("top_gaps_us", "top_kernels", "small_kernel_sequence")}))
+    print(json.dumps({k: v for k, v in out.items() if k not in ("top_gaps_us", "top_kernels", "small_kernel_sequence", "kernels")}))
     for g in out["top_gaps_us"][:15]:
         print(f"gap {g['gap']:7.1f} us at {g['at_ms']:7.3f} ms  after {g['after']}  before {g['before']}")
     for k in out["top_kernels"][:30]:
         print(f"{k[1]:8.3f} ms  n={k[2]:4d}  {k[0]}")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        model.grad_sync.close()
+        os._exit(0)
 
 
 if __name__ == "__main__":
