@@ -141,13 +141,18 @@ class GradSync:
     # head gradients that exist by then are averaged on the communication stream while the fused backward runs
     def _head_early(self):
         self._head_done = set()
-        if self.world == 1 or not self.overlap:
+        if self.world == 1:
             return
         ready = [p for p in self.head_params if p.grad is not None]
-        if not ready or not ready[0].grad.is_cuda:
+        if not ready:
             return
-        with torch.cuda.stream(self._comm(ready[0].grad.device)):
-            self._head_bucket(ready)
+        if ready[0].grad.is_cuda:
+            if not self.overlap:
+                return                                   # A/B mode: everything goes out in finish(), on the compute stream
+            with torch.cuda.stream(self._comm(ready[0].grad.device)):
+                self._head_bucket(ready)
+        else:
+            self._head_bucket(ready)                     # CPU tensors (gloo tests): synchronous
         self._head_done = {id(p) for p in ready}
 
     def close(self):

@@ -61,6 +61,24 @@ def _worker(rank, world, port, q):
         for k, p in enumerate(sync.head_params):
             assert torch.allclose(p.grad, torch.full_like(p, mean_scale * (k + 1)))
         assert sync.n_collectives == 4
+        # early head bucket: the gradients that exist when dL/dCLS reaches the fused backward go out then (FusedPath calls
+        # head_hook), the rest in finish() -- every gradient is averaged exactly once
+        for k, p in enumerate(sync.head_params):
+            p.grad = torch.full_like(p, float((rank + 1) * (k + 1))) if k < 2 else None
+        fp.head_hook()
+        assert sync.n_collectives == 5
+        for k, p in enumerate(sync.head_params):
+            if k >= 2:
+                p.grad = torch.full_like(p, float((rank + 1) * (k + 1)))
+        sync.finish()
+        assert sync.n_collectives == 6
+        for k, p in enumerate(sync.head_params):
+            assert torch.allclose(p.grad, torch.full_like(p, mean_scale * (k + 1))), k
+        fp.head_hook()                       # next step, all four ready early: one bucket, nothing left for finish()
+        sync.finish()
+        assert sync.n_collectives == 7
+        for k, p in enumerate(sync.head_params):     # identical on every rank already: the average changes nothing
+            assert torch.allclose(p.grad, torch.full_like(p, mean_scale * (k + 1))), k
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
