@@ -174,6 +174,24 @@ int tmp_adamw_step_dev(float* w, const float* g, float* m, float* v, long long n
  * pass through fp16 scratch with a static scale). Call it on the fully reduced gradient, before tmp_adamw_step_dev. */
 int tmp_grad_nonfinite(const float* g, long long n, int32_t* state, void* stream);
 
+/* ---- a12 / f3: classifier head in training mode (reference tri_mbt_vsltcls.py:176-177 demographic branch, :248-255 head;
+ * module definitions :72-76, :152-158). One forward launch, two backward launches, all fp32, no floating-point atomics
+ * (cross-CTA sums go through per-CTA partials added in a fixed order by the last CTA):
+ *   logit = Linear(256,1)(ReLU(BatchNorm1d(Linear(512,256)([LayerNorm(cls) | ReLU(LayerNorm(Linear(2,256)([age, gender])))]))))
+ * params / grads: 12 device pointers in the order layer_norms_after_concat.{weight,bias}, ie_demo.0.{weight[256,2],bias},
+ *   ie_demo.1.{weight,bias}, fc_list.0.{weight[256,512],bias}, fc_list.1.{weight,bias}, fc_list.3.{weight[1,256],bias[1]}.
+ * saved: 7 device pointers written by the forward and read by the backward: Z [B,512], XC [B,256], XD [B,256], rstd_c [B],
+ *   rstd_d [B], XH [B,256], invstd [256]. run_mean / run_var [256]: BatchNorm running statistics, updated in place with
+ *   `momentum` (unbiased variance), *nbt (int64 num_batches_tracked, may be NULL) += 1. 2 <= B <= 4096 (batch statistics).
+ * scratch: >= max(32 * B, 64 * 7 * 256) floats; counter: one uint32, zero before the first call, left at zero.
+ * tmp_head_bwd OVERWRITES the 12 gradient tensors and dcls [B,256]; DH: [B,256] scratch. */
+int tmp_head_fwd(const float* cls, const float* age, const float* gen, int B, const void* const* params, float* run_mean,
+                 float* run_var, long long* nbt, float momentum, float bn_eps, void* const* saved, float* scratch,
+                 unsigned int* counter, float* logits, void* stream);
+int tmp_head_bwd(const float* dlogit, const float* age, const float* gen, int B, const void* const* params,
+                 void* const* saved, void* const* grads, float* dcls, float* DH, float* scratch, unsigned int* counter,
+                 void* stream);
+
 /* ---- image-encoder feed: the glue of the frozen Swin-T forward around the tcgen05 GEMMs
  * (reference builder/models/src/swin_transformer.py: patch embedding :541-551, SwinTransformerBlock.forward :447-450,
  * shifted_window_attention :115-214, PatchMerging :34-46,75-86). Activations fp16 [tokens, Cp] (Cp = padded channel

@@ -45,6 +45,8 @@ SIGNATURES = {
     "tmp_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp],
     "tmp_adamw_step_dev": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _i, _vp],
     "tmp_grad_nonfinite": [_vp, _ll, _vp, _vp],
+    "tmp_head_fwd": [_vp, _vp, _vp, _i, _pp, _vp, _vp, _vp, _f, _f, _pp, _vp, _vp, _vp, _vp],
+    "tmp_head_bwd": [_vp, _vp, _vp, _i, _pp, _pp, _pp, _vp, _vp, _vp, _vp, _vp],
     # fp32 ("precise") mode: same operators on fp32-stored tensors, bf16x3 operand split, CUDA-core fp32 attention
     "tmp_layernorm_fwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
     "tmp_layernorm_bwd_f32": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _u32, _u32, _vp, _vp, _vp, _vp],
@@ -95,7 +97,7 @@ def last_error() -> str:
 
 
 # kernels launched per C-ABI call (tmp_mma_attn_bwd = delta + main + dQ convert); bench.py reports the total
-_KERNELS_PER_CALL = {"tmp_mma_attn_bwd(standalone)": 3, "tmp_attn_bwd_f32": 2}
+_KERNELS_PER_CALL = {"tmp_mma_attn_bwd(standalone)": 3, "tmp_attn_bwd_f32": 2, "tmp_head_bwd": 2}
 launch_count = 0
 
 

@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libtmp_b200.so")
 STAMP = os.path.join(PKG_DIR, "csrc", ".build_stamp")
-SOURCES = ["common.cu", "gemm_tc05.cu", "attn_fwd_tc05.cu", "attn_bwd_tc05.cu", "embed.cu", "rowops.cu", "swin.cu", "precise.cu"]
+SOURCES = ["common.cu", "gemm_tc05.cu", "attn_fwd_tc05.cu", "attn_bwd_tc05.cu", "embed.cu", "rowops.cu", "swin.cu", "precise.cu", "head.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -185,6 +185,10 @@ class TRI_MBT_VSLTCLS(nn.Module):
         # the frozen image encoder runs INSIDE the fused path, on the img modality's CUDA stream (FusedPath.forward calls
         # encode_images there), so the vslt / txt streams of layer 0 overlap it
         cls_out = self._fused(x, input_lengths, txts, txt_lengths, img, img_time, txt_time, missing)
+        from . import head
+        if head.usable(self, cls_out):
+            # training mode: LayerNorm + demographic branch + Linear / BatchNorm1d / ReLU / Linear in three launches (head.py)
+            return head.fused_head(self, cls_out, age, gen), None, None
         # the demographic branch (reference tri_mbt_vsltcls.py:176-177, in front of the encoder there) is evaluated AFTER the fused path: its
         # autograd nodes are then younger than the fused function's, so the engine runs their backward first and every head
         # gradient exists when dL/dCLS reaches the fused backward (trainer.GradSync averages them during that backward)

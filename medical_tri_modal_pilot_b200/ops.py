@@ -315,3 +315,28 @@ def swin_unwindow_add_ln(y, x, g, b, n_img, H, C, Cp, shift, hn, live=None):
 def swin_merge_ln(x, g, b, n_img, H, C, Cp, out, live=None):
     check(_lib.load().tmp_swin_merge_ln(ptr(x), ptr(g), ptr(b), n_img, H, H, C, Cp, ptr(out), ptr(live), stream_ptr()),
           "tmp_swin_merge_ln")
+
+
+# ---- classifier head (training mode): csrc/head.cu ---------------------------------------------------------------------
+HEAD_PARAM_ORDER = ("layer_norms_after_concat.weight", "layer_norms_after_concat.bias", "ie_demo.0.weight", "ie_demo.0.bias",
+                    "ie_demo.1.weight", "ie_demo.1.bias", "fc_list.0.weight", "fc_list.0.bias", "fc_list.1.weight",
+                    "fc_list.1.bias", "fc_list.3.weight", "fc_list.3.bias")
+
+
+def head_scratch_floats(B: int) -> int:
+    return max(32 * B, 64 * 7 * 256)
+
+
+def head_fwd(cls, age, gen, params, run_mean, run_var, nbt, momentum, eps, saved, scratch, counter, logits):
+    """params: 12 fp32 tensors in HEAD_PARAM_ORDER; saved: (Z [B,512], XC, XD [B,256], rstd_c, rstd_d [B], XH [B,256],
+    invstd [256]) written here; logits [B]."""
+    B = cls.shape[0]
+    check(_lib.load().tmp_head_fwd(ptr(cls), ptr(age), ptr(gen), B, ptr_array(params), ptr(run_mean), ptr(run_var), ptr(nbt),
+                                   float(momentum), float(eps), ptr_array(saved), ptr(scratch), ptr(counter), ptr(logits),
+                                   stream_ptr()), "tmp_head_fwd")
+
+
+def head_bwd(dlogit, age, gen, params, saved, grads, dcls, DH, scratch, counter):
+    B = dlogit.shape[0]
+    check(_lib.load().tmp_head_bwd(ptr(dlogit), ptr(age), ptr(gen), B, ptr_array(params), ptr_array(saved), ptr_array(grads),
+                                   ptr(dcls), ptr(DH), ptr(scratch), ptr(counter), stream_ptr()), "tmp_head_bwd")
