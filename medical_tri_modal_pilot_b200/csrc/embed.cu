@@ -376,7 +376,34 @@ __device__ __forceinline__ void flush8(float* sm, const float (&v)[8], int lane)
 // backward reductions share one tree, and the feature-embedding gradient goes to a WARP-PRIVATE [20,256] table in shared
 // memory (plain read-modify-write, each lane owns its 8 channels) instead of shared-memory atomics that eight warps
 // contended for on the five common feature ids. First version: 155-178 us at the bench shape (0.2 TB/s).
+//
+// Second version (the kernel sits on the serial tail of the step, alone on the GPU at 8 warps per SM -- registers AND shared
+// memory both cap it there): (1) rows are split evenly over the warps (a contiguous range each, walked in chunks of <= 32)
+// instead of whole 32-row groups, which left 826 of 1 184 warps with 64 rows and the rest with 32 at the bench shape and
+// ran the 9 728-row image stream on 38 blocks; (2) the gradient rows (and the projected rows of the img / txt streams)
+// come through a warp-private cp.async ring of kRing rows instead of a one-row register prefetch, so a row no longer
+// costs at least one global-load latency. Each lane copies and later reads its own 16 / 32 bytes: no cross-lane hand-off.
 struct BwdTok { float sv, rv, st, rt; };
+constexpr int kRing16 = 4, kRing32 = 2;       // ring depth in rows: 16-bit rows (512 B) / fp32 rows (1 KB)
+__device__ __forceinline__ void cp_async16_g2s(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// one lane's 8 elements of a row: global -> ring slot (16 B, or 2 x 16 B in the fp32 mode)
+template <int ST>
+__device__ __forceinline__ void ring_fill(void* slot_row, const void* base, size_t elem, int lane) {
+  if (ST == FMT_F32) {
+    const float* src = static_cast<const float*>(base) + elem;
+    float* dst = static_cast<float*>(slot_row) + lane * 8;
+    cp_async16_g2s(dst, src);
+    cp_async16_g2s(dst + 4, src + 4);
+  } else {
+    cp_async16_g2s(static_cast<h16*>(slot_row) + lane * 8, static_cast<const h16*>(base) + elem);
+  }
+}
 
 template <int KIND, int ST>
 __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdParams q) {
@@ -387,7 +414,12 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
   BwdTok* sTok = reinterpret_cast<BwdTok*>(sAcc + 16 * D);           // [8][32]
   RowMeta* sMeta = reinterpret_cast<RowMeta*>(sTok + 8 * 32);        // [8][32]
   float* sG = reinterpret_cast<float*>(sMeta + 8 * 32);              // KIND 0: [8 warps][20*256] feature-embedding gradient
+  constexpr int kRing = ST == FMT_F32 ? kRing32 : kRing16;
+  constexpr int kRowBytes = D * (ST == FMT_F32 ? 4 : 2);
+  char* sRing = reinterpret_cast<char*>(sG + (KIND == 0 ? 8 * 20 * D : 0));   // [8 warps][kRing][row]: dX0 rows (+ the same for proj, KIND 1)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  char* ringG = sRing + (size_t)wid * kRing * kRowBytes;
+  char* ringP = sRing + (size_t)(8 + wid) * kRing * kRowBytes;
   for (int i = threadIdx.x; i < 20 * D; i += blockDim.x) sW[i] = p.Wfeat[i];
   for (int i = threadIdx.x; i < 16 * D; i += blockDim.x) sAcc[i] = 0.f;
   if (KIND == 0)
@@ -409,16 +441,17 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
   float* sGw = sG + (size_t)wid * 20 * D + lane * 8;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long rows = (long long)p.B * p.T;
-  const long long n_grp = (rows + 31) / 32;
+  const long long per_warp = (rows + warps - 1) / warps;
+  const long long r_begin = min(rows, ((long long)blockIdx.x * (blockDim.x >> 5) + wid) * per_warp);
+  const long long r_end = min(rows, r_begin + per_warp);
   const uint32_t dkey = p.drop_thr16 ? dropout_key(effective_seed(p.seed, p.seed_dev), p.salt) : 0u;
 
-  for (long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + wid; grp < n_grp; grp += warps) {
-    const long long row0 = grp * 32;
+  for (long long row0 = r_begin; row0 < r_end; row0 += 32) {
     {
       const long long r = row0 + lane;
       RowMeta m{-1, 0, 0, 0};
       BwdTok tok{0.f, 0.f, 0.f, 0.f};
-      if (r < rows) {
+      if (r < r_end) {
         const int b = (int)(r / p.T), t = (int)(r - (long long)b * p.T);
         m.t = t;
         if (t < 4) m.code = -1 - t;
@@ -444,12 +477,25 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
       sMeta[wid * 32 + lane] = m;
       __syncwarp();
     }
-    const int cnt = (int)min(32LL, rows - row0);
-    float g[8], gn[8];
-    ld8<ST>(q.dX0, (size_t)row0 * D + lane * 8, g);
+    const int cnt = (int)min(32LL, r_end - row0);
+    // ring: row j of the chunk lives in slot j % kRing; one commit group per row (empty past the end of the chunk)
+    auto fill = [&](int j) {
+      if (j < cnt) {
+        ring_fill<ST>(ringG + (j % kRing) * kRowBytes, q.dX0, (size_t)(row0 + j) * D + lane * 8, lane);
+        if (KIND == 1) {
+          const RowMeta mj = sMeta[wid * 32 + j];
+          if (mj.code >= 0) ring_fill<ST>(ringP + (j % kRing) * kRowBytes, p.proj, (size_t)mj.proj_row * D + lane * 8, lane);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < kRing; ++j) fill(j);
     for (int j = 0; j < cnt; ++j) {
       const long long row = row0 + j;
-      if (j + 1 < cnt) ld8<ST>(q.dX0, (size_t)(row + 1) * D + lane * 8, gn);     // prefetch the next gradient row
+      cp_async_wait<kRing - 1>();        // this lane's copy of row j has landed (it reads back only its own bytes)
+      float g[8];
+      ld8<ST>(ringG + (j % kRing) * kRowBytes, (size_t)lane * 8, g);
       const RowMeta m = sMeta[wid * 32 + j];
       if (m.code < 0 && m.code > -5) {
         flush8(sAcc + (9 + (-m.code - 1)) * D, g, lane);      // bottleneck parameter rows (4 of T rows)
@@ -462,7 +508,7 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = 0.f;
           if (KIND == 0) branch_add(V, tk.sv, tk.rv, e);
-          else ld8<ST>(p.proj, (size_t)m.proj_row * D + lane * 8, e);
+          else ld8<ST>(ringP + (j % kRing) * kRowBytes, (size_t)lane * 8, e);
           branch_add(Tm, tk.st, tk.rt, e);
           const float4 f0 = *reinterpret_cast<const float4*>(&sW[m.code + lane * 8]);
           const float4 f1 = *reinterpret_cast<const float4*>(&sW[m.code + lane * 8 + 4]);
@@ -552,11 +598,10 @@ __global__ void __launch_bounds__(256) stream_prologue_bwd_kernel(PrologueBwdPar
           }
         }
       }
-      if (j + 1 < cnt) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = gn[i];
-      }
+      fill(j + kRing);      // refill the slot just consumed (its values went through the arithmetic above)
     }
+    cp_async_wait<0>();
+    __syncwarp();           // the next chunk overwrites this warp's sTok / sMeta
   }
   if (KIND == 0) {
     flush8(sAcc + 0 * D, aV.dw, lane); flush8(sAcc + 1 * D, aV.db, lane);
@@ -702,8 +747,11 @@ static int prologue_bwd_impl(int stf, int kind, int B, int n, const float* x, co
   q.g_val = g_val; q.g_tim = g_tim; q.g_feat = g_feat; q.g_cls = g_cls; q.g_bott = g_bott; q.g_ln = g_ln;
   q.dproj = dproj;
   // forward table + accumulators + per-warp row scalars (+ 8 warp-private feature-gradient tables for the vslt stream)
-  const int smem1 = (20 + 16) * D * 4 + 2 * 8 * 32 * 16;
-  const int smem0 = smem1 + 8 * 20 * D * 4;
+  // + the cp.async rings: 8 warps x 4 rows x 512 B (2 rows x 1 KB in the fp32 mode) = 16 KB, twice for the img / txt kernel
+  const int ring = 8 * kRing16 * D * 2;
+  static_assert(kRing16 * 2 == kRing32 * 4, "ring bytes are the same in both storage formats");
+  const int smem1 = (20 + 16) * D * 4 + 2 * 8 * 32 * 16 + 2 * ring;
+  const int smem0 = (20 + 16) * D * 4 + 2 * 8 * 32 * 16 + 8 * 20 * D * 4 + ring;
   const int smem = kind == 0 ? smem0 : smem1;
   static bool attr_set = false;
   if (!attr_set) {
@@ -713,9 +761,10 @@ static int prologue_bwd_impl(int stf, int kind, int B, int n, const float* x, co
     cudaFuncSetAttribute(stream_prologue_bwd_kernel<1, FMT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     attr_set = true;
   }
-  // one warp per 32-row group; the vslt kernel holds 200 KB of shared memory (one block per SM), the img / txt one 45 KB
-  long long blocks = ((long long)B * q.f.T + 255) / 256;
-  const long long cap = (long long)tmp::num_sms() * (kind == 0 ? 1 : 3);
+  // rows are split evenly over the warps of the grid, one block per SM at most (220 KB of shared memory for the vslt kernel,
+  // ~200 registers per thread for both): the few thousand rows of an img / txt stream spread over every SM, ~8 per warp
+  long long blocks = ((long long)B * q.f.T + 63) / 64;
+  const long long cap = (long long)tmp::num_sms();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;

@@ -151,9 +151,12 @@ def case_prologue():
     cls = torch.randn(256, device=dev); bott = torch.randn(4, 256, device=dev)
     lg = 1 + 0.1 * torch.randn(256, device=dev); lb = 0.1 * torch.randn(256, device=dev)
     pe = torch.randn(200, 256, device=dev)
-    for kind, B, n, drop in ((0, 5, 37, 0.0), (1, 5, 147, 0.0), (0, 7, 300, 0.25), (1, 9, 147, 0.25)):
+    # the last two: more rows than 32 per warp of a full grid (the backward walks a warp's row range in chunks of 32) and
+    # an img stream that fills every SM
+    for kind, B, n, drop in ((0, 5, 37, 0.0), (1, 5, 147, 0.0), (0, 7, 300, 0.25), (1, 9, 147, 0.25), (0, 40, 1000, 0.1),
+                             (1, 64, 147, 0.1)):
         T = n + 5
-        tag = f"{kind}" if drop == 0.0 else f"{kind}_drop"
+        tag = (f"{kind}" if drop == 0.0 else f"{kind}_drop") + ("_big" if B * n > 5000 else "")
         leaves = [t.clone().requires_grad_(True) for t in (*val4, *tim4, W, cls, bott, lg, lb)]
         v4, t4, Wl, cl, bo, lgl, lbl = leaves[0:4], leaves[4:8], leaves[8], leaves[9], leaves[10], leaves[11], leaves[12]
         if kind == 0:
