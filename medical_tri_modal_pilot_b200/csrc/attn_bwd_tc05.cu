@@ -689,11 +689,11 @@ extern "C" int tmp_mma_attn_bwd(const void* qkv, const void* O, const void* dO, 
     attr_set = true;
   }
   CUtensorMap tmQKV, tmDO, tmDQ, tmDKV;
-  int rc = tmp::encode_tmap_2d_bf16(&tmQKV, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BT);
+  int rc = tmp::encode_tmap_2d_h16(&tmQKV, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BT);
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_bf16(&tmDO, dO, 256, (uint64_t)B * T, (uint64_t)ld * 2, HD, BT);
+  rc = tmp::encode_tmap_2d_h16(&tmDO, dO, 256, (uint64_t)B * T, (uint64_t)ld * 2, HD, BT);
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_bf16(&tmDKV, dQKV, 768, (uint64_t)B * T, 768 * 2, 64, 32);   // dK / dV boxes [32 rows x 64 cols]
+  rc = tmp::encode_tmap_2d_h16(&tmDKV, dQKV, 768, (uint64_t)B * T, 768 * 2, 64, 32);   // dK / dV boxes [32 rows x 64 cols]
   if (rc) return rc;
   if (fused)   // fp16 reduce-add boxes [32 rows x 32 cols] into dQKV[:, 0:256]
     rc = tmp::encode_tmap_2d_f16_sw64(&tmDQ, dQKV, 256, (uint64_t)B * T, 768 * 2, 32, 32);

@@ -316,8 +316,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 }  // namespace
 
-// qkv: [B*T, 768] bf16.  kv_len: [B] int32 or NULL (= unmasked, reference `mask=None`).
-// O: [B*T, ld_o] bf16 (head h at columns h*64).  lse2: [B, H, T_lse] fp32, log2-domain logsumexp of the scaled scores.
+// qkv: [B*T, 768] fp16.  kv_len: [B] int32 or NULL (= unmasked, reference `mask=None`).
+// O: [B*T, ld_o] fp16 (head h at columns h*64).  lse2: [B, H, T_lse] fp32, log2-domain logsumexp of the scaled scores.
 // q_rows: only the leading q_rows query rows of every sample are computed (rounded up to whole 128-row tiles; T = all).
 // The last fused layer of `--mbt-only-vslt 1` only consumes the CLS row (row 4): its O / lse rows past the first tile are
 // never read, so they are not produced.
@@ -337,9 +337,9 @@ extern "C" int tmp_mma_attn_fwd(const void* qkv, const int32_t* kv_len, int B, i
     attr_set = true;
   }
   CUtensorMap tm, tmO;
-  int rc = tmp::encode_tmap_2d_bf16(&tm, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BQ);
+  int rc = tmp::encode_tmap_2d_h16(&tm, qkv, 768, (uint64_t)B * T, 768 * 2, HD, BQ);
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_bf16(&tmO, O, (uint64_t)ld_o, (uint64_t)B * T, (uint64_t)ld_o * 2, 64, 32);   // O boxes [32 rows x 64 cols]
+  rc = tmp::encode_tmap_2d_h16(&tmO, O, (uint64_t)ld_o, (uint64_t)B * T, (uint64_t)ld_o * 2, 64, 32);   // O boxes [32 rows x 64 cols]
   if (rc) return rc;
   dim3 grid((q_rows + BQ - 1) / BQ, H, B);
   const float scale_log2 = kLog2e / 8.0f;  // 1/sqrt(d_head=64) in log2 units (attention.py:16,35)

@@ -35,11 +35,11 @@ static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* 
                           uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
                           CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 
-int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+int encode_tmap_2d_h16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer) {
   return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
-int encode_tmap_2d_bf16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+int encode_tmap_2d_h16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                              uint32_t box_inner, uint32_t box_outer) {
   return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gaddr, inner, outer, row_stride_bytes, box_inner, box_outer,
                         CU_TENSOR_MAP_SWIZZLE_64B);

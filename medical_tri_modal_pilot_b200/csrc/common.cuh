@@ -16,12 +16,12 @@ void set_error(const char* fmt, ...);
 
 // cuTensorMapEncodeTiled resolved at run time through the runtime API (no link-time libcuda dependency:
 // the library must load on the CPU-only build box).
-int encode_tmap_2d_bf16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+int encode_tmap_2d_h16(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer);
 
 // 16-bit elements, 64B swizzle (box_inner = 32 elements = 64 B rows, dense in shared memory: with the 128B swizzle a
 // 64 B box row is padded to a 128 B pitch, measured): chunk c (16 B) of row r sits at r*64 + ((c ^ ((r >> 1) & 3)) << 4).
-int encode_tmap_2d_bf16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+int encode_tmap_2d_h16_sw64(CUtensorMap* map, const void* gaddr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                              uint32_t box_inner, uint32_t box_outer);
 
 // IEEE fp16 elements (element type matters for TMA reduce-add), 64B swizzle, box_inner = 32

@@ -8,7 +8,7 @@
 // polynomials of the scalar (no cross-lane reduction): mean = s*wbar + bbar, var = s^2*A + 2s*C + Dv.
 //
 // One warp per token row, lane l owns channels 8l..8l+7: every global access is a 16 B vector per lane,
-// 512 B contiguous per warp (16-bit rows). Forward tensors are fp16, gradient tensors bf16.
+// 512 B contiguous per warp (16-bit rows). Forward and gradient tensors are fp16 (gradients carry a static power-of-two scale).
 #include "common.cuh"
 #include "rowwise.cuh"
 
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 3) stream_prologue_fwd_ke
 // backward of the stream prologue. Gradient accumulators (fp32, atomically added):
 //   g_val / g_tim : [4,256] each = (dLinear.weight, dLinear.bias, dLN.weight, dLN.bias)
 //   g_feat [20,256], g_cls [256], g_bott [4,256], g_ln [2,256] = (dLN_in.weight, dLN_in.bias)
-//   dproj [B*n,256] bf16 (KIND 1): gradient wrt the projected rows
+//   dproj [B*n,256] fp16 (KIND 1): gradient wrt the projected rows
 // ------------------------------------------------------------------------------------------------
 struct PrologueBwdParams {
   PrologueParams f;

@@ -786,9 +786,9 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
                                      uint32_t seed, uint32_t salt, const uint32_t* seed_dev, void* out16, int out_fmt,
                                      float* out_f32, int ld_out, uint32_t* mask_out, const uint8_t* row_live,
                                      int rows_per_group, void* stream) {
-  void* out_bf16 = out16;
+  void* out_h16 = out16;
   TMP_REQUIRE(!row_live || rows_per_group > 0, "gemm: row_live needs rows_per_group > 0");
-  TMP_REQUIRE(A && B && (out_bf16 || out_f32), "gemm: null operand");
+  TMP_REQUIRE(A && B && (out_h16 || out_f32), "gemm: null operand");
   TMP_REQUIRE(fmt_ok(a_fmt) && fmt_ok(b_fmt) && fmt_ok(out_fmt) && (!gate || fmt_ok32(gate_fmt) || gate_fmt == FMT_MASK) &&
                   (!residual || fmt_ok32(res_fmt)),
               "gemm: operand / output formats must be 0 (fp16) or 1 (bf16); gate / residual may also be 2 (fp32)");
@@ -806,9 +806,9 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   static const int bn_force = getenv("TMP_B200_GEMM_BN") ? atoi(getenv("TMP_B200_GEMM_BN")) : 0;   // A/B timing only
   if (bn_force == 128 || (bn_force == 256 && N % 256 == 0)) BN = bn_force;
   CUtensorMap tmA, tmB;
-  int rc = tmp::encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
+  int rc = tmp::encode_tmap_2d_h16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN);
+  rc = tmp::encode_tmap_2d_h16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN);
   if (rc) return rc;
   EpiParams p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.bias = bias; p.relu = relu;
@@ -821,14 +821,14 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
   p.bias_scale = p.drop_fold ? p.drop_scale : 1.f;
   if (p.drop_fold) p.alpha = alpha * p.drop_scale;
   p.drop_seed = seed; p.drop_salt = salt; p.drop_seed_dev = seed_dev;
-  p.out = (uint16_t*)out_bf16; p.out_f32 = out_f32; p.ld_out = ld_out;
+  p.out = (uint16_t*)out_h16; p.out_f32 = out_f32; p.ld_out = ld_out;
   p.mask_out = mask_out;
   p.row_live = row_live; p.rows_per_group = rows_per_group;
   // compile-time specialised epilogue when the call is one of the hot combinations (TMP_EPI_MODES), else the generic one
   p.mode = -1;
   static const bool epi_generic = getenv("TMP_B200_GEMM_GENERIC_EPILOGUE") != nullptr;   // A/B timing
   int mode_cand = -1;
-  if (!epi_generic && out_bf16 && !out_f32 && out_fmt == FMT_F16 && (!gate || gate_fmt == FMT_MASK) &&
+  if (!epi_generic && out_h16 && !out_f32 && out_fmt == FMT_F16 && (!gate || gate_fmt == FMT_MASK) &&
       (!residual || res_fmt == FMT_F16) && (drop_p == 0.f || p.drop_fold) && relu >= 0 && relu <= 2) {
     int m = 0;
     if (bias) m |= EPI_BIAS;
@@ -854,9 +854,9 @@ extern "C" int tmp_gemm_bias_act_fwd(const void* A, int a_fmt, int lda, const vo
     return p;
   };
   CUtensorMap tmOut;
-  if (out_bf16) {
+  if (out_h16) {
     // 16-bit output written by TMA: boxes of [32 rows x 32 cols], 64B swizzle; rows >= M are clipped
-    rc = tmp::encode_tmap_2d_bf16_sw64(&tmOut, out_bf16, (uint64_t)N, (uint64_t)M, (uint64_t)ld_out * 2, 32, 32);
+    rc = tmp::encode_tmap_2d_h16_sw64(&tmOut, out_h16, (uint64_t)N, (uint64_t)M, (uint64_t)ld_out * 2, 32, 32);
     if (rc) return rc;
   } else {
     tmOut = tmA;
@@ -882,9 +882,9 @@ extern "C" int tmp_gemm_wgrad(const void* dY, int y_fmt, int ldy, const void* X,
   TMP_REQUIRE(fmt_ok(y_fmt) && fmt_ok(x_fmt) && y_fmt == x_fmt, "wgrad: dY and X must share one 16-bit format");
   TMP_REQUIRE(M > 0 && N % 128 == 0 && K % 128 == 0, "wgrad: need N,K multiples of 128 (M=%d N=%d K=%d)", M, N, K);
   CUtensorMap tmY, tmX;
-  int rc = tmp::encode_tmap_2d_bf16(&tmY, dY, (uint64_t)N, (uint64_t)M, (uint64_t)ldy * 2, 64, BK);
+  int rc = tmp::encode_tmap_2d_h16(&tmY, dY, (uint64_t)N, (uint64_t)M, (uint64_t)ldy * 2, 64, BK);
   if (rc) return rc;
-  rc = tmp::encode_tmap_2d_bf16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
+  rc = tmp::encode_tmap_2d_h16(&tmX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, BK);
   if (rc) return rc;
   CUtensorMap tmDW;   // dW [N, K] fp32, reduce-add boxes [32 rows x 32 cols]
   rc = tmp::encode_tmap_2d_f32(&tmDW, dW, (uint64_t)K, (uint64_t)N, (uint64_t)K * 4, 32, 32);

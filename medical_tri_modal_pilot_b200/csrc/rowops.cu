@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const void* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// bottleneck exchange (a7). Y_m: [B, T_m, 256] fp16 (forward) / bf16 (gradients); rows 0..3 of every present stream are replaced by the
+// bottleneck exchange (a7). Y_m: [B, T_m, 256] fp16 (forward and gradients); rows 0..3 of every present stream are replaced by the
 // per-sample mean over the modalities selected by `missing` (0: v,i,t  1: v,i  2: v,t  3: v).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mix_weights(long long code, float (&w)[3]) {
@@ -304,7 +304,7 @@ __global__ void bottleneck_mix_bwd_kernel(void* __restrict__ dYv, void* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (bf16 gradients in, fp32 atomics out)
+// column sums (bias gradients): out[N] += sum_rows dY[rows, N]   (fp16 gradients in, fp32 atomics out)
 // block = 256 threads = (N/8 column groups) x (rows in flight)
 // ------------------------------------------------------------------------------------------------
 template <int ST>
@@ -642,7 +642,7 @@ extern "C" int tmp_dropout_apply_f32(const float* in, float* out, long long n, f
   return dropout_apply_impl(FMT_F32, in, out, n, drop_p, seed, salt, seed_dev, stream);
 }
 
-// descs: device array of n_desc {const float* src; bf16* dst; bf16* dst_t; int R; int C}; max_R/max_C bound the grid
+// descs: device array of n_desc {const float* src; h16* dst; h16* dst_t; int R; int C}; max_R/max_C bound the grid
 extern "C" int tmp_cast_weights(const void* descs, int n_desc, int max_R, int max_C, void* stream) {
   TMP_REQUIRE(descs && n_desc > 0 && max_R > 0 && max_C > 0, "cast_weights: bad argument");
   dim3 grid((max_C + 31) / 32, (max_R + 31) / 32, n_desc);

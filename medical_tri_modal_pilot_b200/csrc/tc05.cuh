@@ -145,8 +145,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Instruction descriptor, kind::f16, BF16 x BF16 -> FP32 accumulate, dense.
 //   bits[4,6)=c_format(1=F32) [7,10)=a_format(1=BF16) [10,13)=b_format(1=BF16)
 //   bit15=a_major (0=K,1=MN)  bit16=b_major  [17,23)=N>>3  [24,29)=M>>4
-//   a_fmt / b_fmt: 0 = F16, 1 = BF16 (the two operands may differ: forward activations and weights are fp16,
-//   gradient tensors are bf16 -- see DESIGN.md "precision").
+//   a_fmt / b_fmt: 0 = F16, 1 = BF16 (the step uses fp16 for forward AND gradient tensors -- see DESIGN.md "Precision
+//   modes"; bf16 blocks only in the bf16x3 split of the fp32 mode).
 enum : int { FMT_F16 = 0, FMT_BF16 = 1, FMT_F32 = 2 };   // FMT_F32: storage format of the fp32 ("precise") mode only
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
   return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |

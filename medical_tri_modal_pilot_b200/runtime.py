@@ -138,7 +138,7 @@ class FusedPath:
         G = lambda n, *shape: flat_g[offs[n]:].as_strided(shape, _contig_strides(shape))
         H16 = lambda n, *shape: self.flat_w16[offs[n]:].as_strided(shape, _contig_strides(shape))
         self.W, self.G, self.H16 = W, G, H16
-        # transposed bf16 copies of the GEMM weights used by dgrad
+        # transposed fp16 copies of the GEMM weights used by dgrad
         F = "fusion_transformer"
         t_total = m.num_layers * 3 * (768 * 256 + 1024 * 256 * 2)
         self.flat_wT16 = torch.empty(t_total, dtype=ACT, device=device)
