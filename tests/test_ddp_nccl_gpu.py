@@ -71,3 +71,62 @@ def test_two_rank_allreduce_equals_single_rank_full_batch(tmp_path):
     cos = torch.nn.functional.cosine_similarity(g0.double(), g_full.double(), dim=0).item()
     rel = ((g0 - g_full).norm() / g_full.norm()).item()
     assert cos > 0.9999 and rel < 1e-2, (cos, rel)
+
+
+def _head_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from builder.trainer import GradSync
+    from test_model_parity_gpu import run_model
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    model, batch = _build(16)
+    sync = GradSync(model)
+    B = batch["x"].shape[0]
+    half = slice(rank * B // 2, (rank + 1) * B // 2)
+    himg = slice(rank * 3 * B // 2, (rank + 1) * 3 * B // 2)
+    b = {k: (v[himg] if k == "img_feats" else v[half]).contiguous() for k, v in batch.items()}
+    r = torch.randn(B, 1, generator=torch.Generator().manual_seed(5))[half].cuda()
+    res = {}
+    for mode in (True, False):            # the three-launch head (head.py) / the stock PyTorch modules
+        model.fused_head = mode
+        model.zero_grad(set_to_none=True)
+        out, _ = run_model(model, b)
+        (out * r).sum().backward()
+        sync.finish()
+        torch.cuda.synchronize()
+        res[mode] = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()
+                     if p.grad is not None and not n.startswith("fusion_transformer.")}
+        res[mode]["flat"] = model._fused.flat_g[: model._fused.live_end()].detach().cpu().clone()
+    torch.save(res, os.path.join(out_dir, f"h{rank}.pt"))
+    dist.barrier()
+    sync.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_head_gradients_fused_head_equals_stock_modules(tmp_path):
+    """Whole model under GradSync on two ranks: the gradients of the classifier-head parameters (averaged early, during the
+    fused backward) are the same on both ranks and the same whether the head ran as csrc/head.cu or as the stock modules."""
+    import torch.multiprocessing as mp
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_head_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    h0, h1 = torch.load(tmp_path / "h0.pt"), torch.load(tmp_path / "h1.pt")
+    names = [n for n in h0[True] if n != "flat"]
+    assert any(n.startswith("fc_list.0") for n in names) and any(n.startswith("ie_demo") for n in names), names
+    for mode in (True, False):
+        for n in h0[mode]:
+            assert torch.equal(h0[mode][n], h1[mode][n]), (mode, n)          # averaged: identical on every rank
+    # element-wise, relative to the tensor's largest element with a floor tied to the largest head gradient: BatchNorm in
+    # training mode makes the loss invariant to layer_norms_after_concat.bias and fc_list.0.bias (a constant shift of every
+    # row is removed with the batch mean), so those two gradients are rounding noise around an exact zero in BOTH modes
+    scale = max(h0[False][n].abs().max().item() for n in names)
+    for n in h0[True]:
+        a, c = h0[True][n].double().flatten(), h0[False][n].double().flatten()
+        err = (a - c).abs().max().item() / max(c.abs().max().item(), 1e-3 * scale)
+        assert err < 5e-3, (n, err)
+        if c.abs().max().item() > 1e-3 * scale:
+            cos = torch.nn.functional.cosine_similarity(a, c, dim=0).item()
+            assert cos > 0.9995, (n, cos)
+
