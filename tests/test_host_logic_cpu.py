@@ -120,3 +120,29 @@ def test_oracle_skip_missing_equivalence():
     b2["x"][pad] = torch.tensor([-5.0, 0.3, 7.0])
     out2 = O.forward(sd, b2, cfg)
     assert torch.equal(out1, out2)
+
+
+def test_fused_head_host_logic():
+    """head.py: the parameter order handed to tmp_head_fwd / tmp_head_bwd names real parameters of the expected shapes, the
+    scratch size covers both kernels' partial sums, and the three-launch head is never chosen off the GPU, in eval mode or
+    when switched off (the stock modules serve those cases)."""
+    from builder.models import get_model
+    from medical_tri_modal_pilot_b200 import head, ops
+    a = _args()
+    model = get_model(a)(a).train()
+    named = dict(model.named_parameters())
+    shapes = {"layer_norms_after_concat.weight": (256,), "ie_demo.0.weight": (256, 2), "fc_list.0.weight": (256, 512),
+              "fc_list.1.bias": (256,), "fc_list.3.weight": (1, 256), "fc_list.3.bias": (1,)}
+    assert len(ops.HEAD_PARAM_ORDER) == 12 and all(n in named for n in ops.HEAD_PARAM_ORDER)
+    for n, shp in shapes.items():
+        assert tuple(named[n].shape) == shp, n
+    assert [tuple(p.shape) for p in head._params(model)] == [tuple(named[n].shape) for n in ops.HEAD_PARAM_ORDER]
+    for B in (2, 64, 4096):
+        assert ops.head_scratch_floats(B) >= max(32 * B, 64 * 7 * 256)
+    cls = torch.zeros(4, 256)
+    assert not head.usable(model, cls)                       # CPU tensor: never
+    model.fused_head = False
+    assert not head.usable(model, cls)
+    model.fused_head = True
+    model.eval()
+    assert not head.usable(model, cls)
