@@ -140,9 +140,12 @@ def main():
     }
     # low-occupancy stretches: time during which only "small" kernels (grid < 64 blocks) are running -- the serial head /
     # tail of the step (classifier head, loss, optimizer glue), where most SMs idle although the GPU counts as busy
-    def small(e):
+    def _blocks(e):
         g = e["args"].get("grid", [1 << 20])
-        return (g[0] * (g[1] if len(g) > 1 else 1) * (g[2] if len(g) > 2 else 1)) < 64
+        return g[0] * (g[1] if len(g) > 1 else 1) * (g[2] if len(g) > 2 else 1)
+
+    def small(e):
+        return _blocks(e) < 64
     pts2 = []
     for e in ks:
         pts2.append((e["ts"], 1, small(e)))
@@ -177,7 +180,7 @@ def main():
     out["world"] = world
     if a.dump:
         out["kernels"] = [[e["name"].replace("(anonymous namespace)::", "").replace("void ", "")[:48], e["args"].get("stream", -1),
-                           round(e["ts"] - t0, 1), round(e["dur"], 1), e["args"].get("grid", [0])[0]] for e in ks]
+                           round(e["ts"] - t0, 1), round(e["dur"], 1), _blocks(e)] for e in ks]
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
     print(json.dumps({k: v for k, v in out.items() if k not in ("top_gaps_us", "top_kernels", "small_kernel_sequence", "kernels")}))
