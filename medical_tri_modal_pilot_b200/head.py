@@ -20,7 +20,7 @@ def usable(model, cls_out) -> bool:
     bn = model.fc_list[1]
     B = cls_out.shape[0]
     return bool(model.training and bn.training and bn.track_running_stats and bn.momentum is not None and bn.affine
-                and cls_out.is_cuda and cls_out.dtype == torch.float32 and 2 <= B <= 4096
+                and cls_out.is_cuda and cls_out.dtype == torch.float32 and 2 <= B <= MAX_B
                 and "rmse" not in getattr(model.args, "auxiliary_loss_type", "none")
                 and model.fc_list[0].weight.dtype == torch.float32)
 
@@ -30,9 +30,14 @@ def _params(model):
     return [sd[n] for n in ops.HEAD_PARAM_ORDER]
 
 
+MAX_B = 4096      # batch statistics of up to this many rows (tmp_head_fwd's documented range)
+
+
 def _workspace(model, B, dev):
+    """Partial-sum scratch + the two last-block counters. Sized once for the largest batch the kernels accept, so the
+    buffer a captured step graph points at is never replaced by a later, larger batch."""
     ws = model.__dict__.get("_head_ws")
-    need = ops.head_scratch_floats(B)
+    need = ops.head_scratch_floats(MAX_B)
     if ws is None or ws[0].device != dev or ws[0].numel() < need:
         ws = (torch.empty(need, dtype=torch.float32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev))
         model.__dict__["_head_ws"] = ws
