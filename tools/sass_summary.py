@@ -13,8 +13,9 @@ OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "
        "FFMA2", "MUFU.EX2"]
 
 
-def main():
-    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+def collect(lib=LIB):
+    """{kernel name (demangled, no parameter list): Counter of the mnemonics in OPS} for every kernel of the library."""
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
     cur, counts = None, collections.OrderedDict()
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -27,6 +28,11 @@ def main():
             for op in OPS:
                 if re.search(r"\b" + re.escape(op), line):
                     counts[cur][op] += 1
+    return counts
+
+
+def main():
+    counts = collect()
     print(f"{'kernel':58s} " + " ".join(f"{o.rstrip('.'):>8s}" for o in OPS))
     for k, c in counts.items():
         if any(c[o] for o in OPS[:10]):
