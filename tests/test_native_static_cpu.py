@@ -16,6 +16,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 @pytest.fixture(scope="module")
 def lib():
+    import sass_summary
+    if sass_summary.cuda_tool("cuobjdump") is None:
+        pytest.skip("cuobjdump (CUDA toolkit) not found")
     from medical_tri_modal_pilot_b200 import build
     return build.build()
 
@@ -70,7 +73,8 @@ STACK_CAP = 128      # bytes per thread: a few spilled registers are tolerated, 
 
 
 def test_register_and_stack_budgets(lib):
-    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    import sass_summary
+    out = subprocess.run([sass_summary.cuda_tool("cuobjdump"), "-res-usage", lib], capture_output=True, text=True, check=True).stdout
     seen = set()
     fn = None
     for line in out.splitlines():

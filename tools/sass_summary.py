@@ -13,9 +13,15 @@ OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "
        "FFMA2", "MUFU.EX2"]
 
 
+def cuda_tool(name):
+    """Path of a CUDA binary utility (PATH first, then next to the toolkit's nvcc); None when the toolkit is absent."""
+    import shutil
+    return shutil.which(name) or next((p for p in (f"/usr/local/cuda/bin/{name}",) if os.path.exists(p)), None)
+
+
 def collect(lib=LIB):
     """{kernel name (demangled, no parameter list): Counter of the mnemonics in OPS} for every kernel of the library."""
-    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([cuda_tool("cuobjdump"), "-sass", lib], capture_output=True, text=True, check=True).stdout
     cur, counts = None, collections.OrderedDict()
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)
